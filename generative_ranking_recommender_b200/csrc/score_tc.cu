@@ -1,0 +1,428 @@
+// Score pass on the 5th-generation tensor cores: X[n,dim] . C[K,dim]^T as 3xTF32 on tcgen05 with
+// TMA-staged tiles and TMEM accumulators, and everything that consumes the N x K distance matrix in
+// the reference fused into the epilogue so that matrix never exists in HBM:
+//   pairwise_distance_full (balancekmeans/__init__.py:576-603 over torch.cdist :596)
+//     d = sqrt(max(|x|^2 + |c|^2 - 2 x.c, 0))
+//   (-d).half() transposed to worker-major            (:29, :40)     -> scores_t [K][ld] fp16
+//   max / min of that matrix for eps                    (:33)          -> minmax_keys
+//   argmin (first index) and the runner-up              (:312, :328)   -> argmin, best2
+//   bincount of the argmin                              (:329)         -> counts
+//
+// Shape of the kernel (one CTA per SM, persistent over 128-row tiles of X):
+//   warp 8      TMA producer: per 32-float k-block, X tile [128 x 32] and the centroid hi/lo blocks
+//               [KC x 32] (128-byte swizzle, zero fill outside the tensors) into a smem ring.
+//   warps 4-7   transform: split the landed fp32 X block into tf32 hi = rna(x) (in place) and
+//               lo = rna(x - hi) (second buffer, same swizzled offsets - the map is elementwise), and
+//               accumulate |x|^2 per row in fp32; one thread per row.
+//   warp 9      one elected thread issues, per k-block, 4 x {hi.hi, hi.lo, lo.hi} tcgen05.mma
+//               kind::tf32 (M=128, N=KC, K=8) into a TMEM accumulator [128 lanes x KC columns];
+//               tcgen05.commit frees the ring slot / publishes the accumulator.
+//   warps 0-3   epilogue: tcgen05.ld 32 columns at a time (thread = row), distance, fp16 store,
+//               running best/second/argmin in registers; accumulators are double-buffered in TMEM so
+//               the epilogue of tile i overlaps the MMAs of tile i+1.
+// The lo.lo product is dropped (<= 2^-22 |x||c| per term), which leaves the dot products at fp32
+// accuracy (~1e-7 relative on d): far below the fp16 rounding of the scores and the 1e-5 near-tie gate.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace rqk {
+
+constexpr int TC_BM = 128;           // rows per tile (UMMA M)
+constexpr int TC_BK = 32;            // fp32 per k-block = one 128-byte swizzle row
+constexpr int TC_THREADS = 320;      // 10 warps
+constexpr int TC_EPI_WARP0 = 0, TC_XF_WARP0 = 4, TC_TMA_WARP = 8, TC_MMA_WARP = 9;
+
+// ---------------- PTX wrappers ----------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float to_tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
+//  layout SWIZZLE_128B=2 [61,64)).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+    d |= (uint64_t)1 << 16;                 // LBO (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;       // SBO
+    d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+// cute::UMMA::InstrDescriptor: c_format F32=1 [4,6), a/b format TF32=2 [7,10)/[10,13), K-major both,
+// N>>3 [17,23), M>>4 [24,29)
+__device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct ScoreTcParams {
+    long long n;
+    int dim, K, KC;          // KC = K rounded up to 16 (UMMA N)
+    int tmem_cols;           // columns per accumulator stage (power of two >= 32, >= KC)
+    int stages;
+    const float* c2;         // [K] |c|^2
+    ScoreOut o;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+score_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_chi,
+                const __grid_constant__ CUtensorMap map_clo, const ScoreTcParams P) {
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    // SWIZZLE_128B tiles need 1024-byte alignment; do not rely on the attribute alone
+    unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KC = P.KC, stages = P.stages;
+    const int kblocks = P.dim / TC_BK;
+    const long long ntiles = (P.n + TC_BM - 1) / TC_BM;
+
+    // ---- smem carve-up: per stage {A hi 16K, A lo 16K, B hi KC*128, B lo KC*128}, all 1024-aligned ----
+    const uint32_t a_bytes = TC_BM * TC_BK * 4;           // 16384
+    const uint32_t b_bytes = (uint32_t)KC * TC_BK * 4;    // KC*128, multiple of 2048
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    unsigned char* tail = smem + (size_t)stages * stage_bytes;
+    uint64_t* full_bar = (uint64_t*)tail;          // [stages]
+    uint64_t* xf_bar = full_bar + 8;               // [stages]
+    uint64_t* empty_bar = xf_bar + 8;              // [stages]
+    uint64_t* tmem_full = empty_bar + 8;           // [2]
+    uint64_t* tmem_empty = tmem_full + 2;          // [2]
+    uint64_t* x2_full = tmem_empty + 2;            // [2]
+    uint32_t* tmem_base_slot = (uint32_t*)(x2_full + 2);
+    float* x2s = (float*)(tmem_base_slot + 4);     // [2][128]
+    float* c2s = x2s + 2 * TC_BM;                  // [KC]
+    int* cnt_s = (int*)(c2s + 256);                // [256]
+
+    for (int i = threadIdx.x; i < 256; i += TC_THREADS) {
+        c2s[i] = (i < P.K) ? P.c2[i] : 0.f;
+        cnt_s[i] = 0;
+    }
+    if (warp == TC_TMA_WARP && lane == 0) {
+        tma_prefetch_desc(&map_x);
+        tma_prefetch_desc(&map_chi);
+        tma_prefetch_desc(&map_clo);
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&xf_bar[s], 128);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 128);
+            mbar_init(&x2_full[a], 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == TC_MMA_WARP) {
+        uint32_t ncols = 2u * (uint32_t)P.tmem_cols;
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == TC_TMA_WARP) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int row0 = (int)(tile * TC_BM);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    unsigned char* st = smem + (size_t)s * stage_bytes;
+                    mbar_expect_tx(&full_bar[s], a_bytes + 2 * b_bytes);
+                    tma_load_2d(st, &map_x, &full_bar[s], kb * TC_BK, row0);
+                    tma_load_2d(st + 2 * a_bytes, &map_chi, &full_bar[s], kb * TC_BK, 0);
+                    tma_load_2d(st + 2 * a_bytes + b_bytes, &map_clo, &full_bar[s], kb * TC_BK, 0);
+                    if (++s == stages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == TC_MMA_WARP) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(TC_BM, KC);
+            int s = 0; uint32_t ph = 0;
+            int a = 0; uint32_t aph = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[a], aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(a * P.tmem_cols);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full_bar[s], ph);    // centroid blocks landed (TMA)
+                    mbar_wait(&xf_bar[s], ph);      // hi/lo of the X block written by the transform warps
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint64_t a_hi = make_sw128_desc(st);
+                    const uint64_t a_lo = make_sw128_desc(st + a_bytes);
+                    const uint64_t b_hi = make_sw128_desc(st + 2 * a_bytes);
+                    const uint64_t b_lo = make_sw128_desc(st + 2 * a_bytes + b_bytes);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);   // +32 B along K inside the swizzle row
+                        umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+                        umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+                        umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+                    }
+                    umma_commit(&empty_bar[s]);      // frees the ring slot when these MMAs retire
+                    if (kb == kblocks - 1) umma_commit(&tmem_full[a]);
+                    if (++s == stages) { s = 0; ph ^= 1; }
+                }
+                if (++a == 2) { a = 0; aph ^= 1; }
+            }
+        }
+    } else if (warp >= TC_XF_WARP0 && warp < TC_XF_WARP0 + 4) {
+        // ===================== transform: hi/lo split + row norms =====================
+        const int r = (warp - TC_XF_WARP0) * 32 + lane;     // row of the tile owned by this thread
+        int s = 0; uint32_t ph = 0;
+        int a = 0; uint32_t aph = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            float nrm = 0.f;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&full_bar[s], ph);
+                unsigned char* st = smem + (size_t)s * stage_bytes;
+                float4* hi = reinterpret_cast<float4*>(st + (size_t)r * 128);
+                float4* lo = reinterpret_cast<float4*>(st + a_bytes + (size_t)r * 128);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int ch = (c + lane) & 7;          // rotate chunks across lanes: no bank conflicts
+                    float4 v = hi[ch];
+                    nrm = fmaf(v.x, v.x, nrm); nrm = fmaf(v.y, v.y, nrm);
+                    nrm = fmaf(v.z, v.z, nrm); nrm = fmaf(v.w, v.w, nrm);
+                    float4 h, l;
+                    h.x = to_tf32_rna(v.x); h.y = to_tf32_rna(v.y); h.z = to_tf32_rna(v.z); h.w = to_tf32_rna(v.w);
+                    l.x = to_tf32_rna(v.x - h.x); l.y = to_tf32_rna(v.y - h.y);
+                    l.z = to_tf32_rna(v.z - h.z); l.w = to_tf32_rna(v.w - h.w);
+                    hi[ch] = h;
+                    lo[ch] = l;
+                }
+                fence_proxy_async();                         // generic-proxy writes -> visible to the UMMA reads
+                mbar_arrive(&xf_bar[s]);
+                if (++s == stages) { s = 0; ph ^= 1; }
+            }
+            mbar_wait(&tmem_empty[a], aph ^ 1);              // x2s[a] is free once the epilogue two tiles back is done
+            x2s[a * TC_BM + r] = nrm;
+            mbar_arrive(&x2_full[a]);
+            if (++a == 2) { a = 0; aph ^= 1; }
+        }
+    } else if (warp < 4) {
+        // ===================== epilogue =====================
+        const int q = warp;                                  // TMEM lane quarter = warp % 4
+        const int r = q * 32 + lane;
+        int a = 0; uint32_t aph = 0;
+        unsigned int kmax = 0, kmin = 0xffffu;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const long long row = tile * TC_BM + r;
+            const bool rv = row < P.n;
+            mbar_wait(&x2_full[a], aph);
+            const float xn = x2s[a * TC_BM + r];
+            const int pid = (rv && P.o.mask_ids) ? P.o.mask_ids[row] : -1;
+            const int mlo = pid * P.o.mask_block, mhi = mlo + P.o.mask_block;
+            mbar_wait(&tmem_full[a], aph);
+            tc_fence_after();
+            float b1 = INFINITY, b2 = INFINITY;
+            int bi = 0;
+            for (int c0 = 0; c0 < KC; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * P.tmem_cols + c0), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int k = c0 + j;
+                    if (k < P.K) {
+                        float d2 = fmaf(-2.f, __uint_as_float(v[j]), xn + c2s[k]);
+                        float d = sqrtf(fmaxf(d2, 0.f));
+                        if (P.o.dist && rv) P.o.dist[row * P.K + k] = d;
+                        if (P.o.scores_t && rv) {
+                            __half h = __float2half_rn(-d);
+                            P.o.scores_t[(long long)k * P.o.ld + row] = h;
+                            unsigned int key = h2key(h2bits(h));
+                            kmax = max(kmax, key);
+                            kmin = min(kmin, key);
+                        }
+                        float dd = P.o.farthest ? -d : d;
+                        if (pid >= 0 && (k < mlo || k >= mhi)) dd = d + 10000.0f;
+                        if (dd < b1) { b2 = b1; b1 = dd; bi = k; }
+                        else if (dd < b2) b2 = dd;
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[a]);
+            if (rv) {
+                if (P.o.argmin) P.o.argmin[row] = bi;
+                if (P.o.best2) { P.o.best2[row * 2] = P.o.farthest ? -b1 : b1; P.o.best2[row * 2 + 1] = P.o.farthest ? -b2 : b2; }
+                if (P.o.counts) atomicAdd(&cnt_s[bi], 1);
+            }
+            if (++a == 2) { a = 0; aph ^= 1; }
+        }
+        if (P.o.scores_t && P.o.minmax_keys) {
+#pragma unroll
+            for (int off = 16; off; off >>= 1) {
+                kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, off));
+                kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, off));
+            }
+            if (lane == 0 && kmin <= kmax) {
+                atomicMax(&P.o.minmax_keys[0], kmax);
+                atomicMin(&P.o.minmax_keys[1], kmin);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (P.o.counts)
+        for (int i = threadIdx.x; i < P.K; i += TC_THREADS)
+            if (cnt_s[i]) atomicAdd(&P.o.counts[i], cnt_s[i]);
+    if (warp == TC_MMA_WARP) {
+        uint32_t ncols = 2u * (uint32_t)P.tmem_cols;
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
+// centroid preparation: hi = rna_tf32(c), lo = rna_tf32(c - hi), |c|^2
+__global__ void centroid_split_kernel(const float* __restrict__ c, int K, int dim, float* __restrict__ chi,
+                                      float* __restrict__ clo, float* __restrict__ c2) {
+    const int k = blockIdx.x;
+    float s = 0.f;
+    for (int d = threadIdx.x; d < dim; d += blockDim.x) {
+        float v = c[(long long)k * dim + d];
+        float h = to_tf32_rna(v);
+        chi[(long long)k * dim + d] = h;
+        clo[(long long)k * dim + d] = to_tf32_rna(v - h);
+        s = fmaf(v, v, s);
+    }
+    __shared__ float red[32];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < (blockDim.x + 31) / 32; ++i) t += red[i];
+        c2[k] = t;
+    }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+static int make_map_2d(CUtensorMap* m, const float* base, long long rows, int dim, int box_rows, CUtensorMapL2promotion l2) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return fail(RQK_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver%s");
+    cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)dim * 4};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(RQK_ERR_CUDA, "cuTensorMapEncodeTiled failed (%s%lld)", "", (long long)r);
+    return 0;
+}
+
+// workspace: chi [K][dim], clo [K][dim], c2 [K]
+int score_pass_tc(const float* x, long long n, int dim, const float* c, int K, float* chi, float* clo, float* c2,
+                  const ScoreOut& o, int num_sms, cudaStream_t stream) {
+    if (n == 0) return 0;
+    const int KC = round_up(K, 16);
+    int tcols = 32;
+    while (tcols < KC) tcols <<= 1;
+    ScoreTcParams P;
+    P.n = n; P.dim = dim; P.K = K; P.KC = KC; P.tmem_cols = tcols;
+    P.c2 = c2; P.o = o;
+    const size_t stage_bytes = 2 * (size_t)TC_BM * TC_BK * 4 + 2 * (size_t)KC * TC_BK * 4;
+    const size_t tail = 8 * 8 * 3 + 2 * 8 * 3 + 16 + 2 * TC_BM * 4 + 256 * 4 + 256 * 4 + 64;
+    int stages = (int)((225 * 1024 - tail - 1024) / stage_bytes);
+    if (stages > 6) stages = 6;
+    if (stages < 2) return fail(RQK_ERR_UNSUPPORTED, "score_pass_tc: K=%s%lld does not fit two pipeline stages", "", K);
+    P.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + tail + 1024;
+
+    centroid_split_kernel<<<K, 128, 0, stream>>>(c, K, dim, chi, clo, c2);
+    RQK_LAUNCH_OK();
+    CUtensorMap mx, mhi, mlo;
+    int rc;
+    if ((rc = make_map_2d(&mx, x, n, dim, TC_BM, CU_TENSOR_MAP_L2_PROMOTION_L2_128B))) return rc;
+    if ((rc = make_map_2d(&mhi, chi, K, dim, KC, CU_TENSOR_MAP_L2_PROMOTION_L2_256B))) return rc;
+    if ((rc = make_map_2d(&mlo, clo, K, dim, KC, CU_TENSOR_MAP_L2_PROMOTION_L2_256B))) return rc;
+    RQK_CUDA_OK(cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long ntiles = ceil_div<long long>(n, TC_BM);
+    int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
+    score_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(mx, mhi, mlo, P);
+    RQK_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace rqk

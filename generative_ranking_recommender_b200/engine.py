@@ -1,0 +1,308 @@
+"""Device-side operations of the RQ-KMeans hot path: thin wrappers that hand torch-owned device memory
+and the current CUDA stream to librqk_sm100a.so (C ABI, include/rqk.h).  torch is plumbing here
+(allocation, streams, torch.distributed); every byte of arithmetic happens in the library's kernels.
+
+Row sharding: when a `ShardGroup` with world_size > 1 is passed, `x` is this rank's
+contiguous row block.  The only data exchanged per iteration are
+  * K x D partial sums + K counts            (centroid update, one all_reduce)
+  * K argmin counts, 2 fp16 extrema           (loss / eps, tiny all_reduces)
+  * K*128 + K + 2 int32 per auction pass      (threshold histograms, one all_reduce)
+  * K int32 per auction pass                  (tie totals, one all_gather)
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import AuctionInfo, AuctionLayout, check, lib
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(dev: torch.device):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _req_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise _lib.RqkError(f"{name} must live on a CUDA device (got {t.device}); there is no CPU path")
+    _lib.require_device(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+class ShardGroup:
+    """Row sharding over a torch.distributed process group (one process per GPU)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.world = dist.get_world_size(group) if self.active else 1
+        self.rank = dist.get_rank(group) if self.active else 0
+
+    def all_reduce(self, t: torch.Tensor, op: str = "sum"):
+        if self.active:
+            ops = {"sum": self.dist.ReduceOp.SUM, "max": self.dist.ReduceOp.MAX, "min": self.dist.ReduceOp.MIN}
+            self.dist.all_reduce(t, op=ops[op], group=self.group)
+        return t
+
+    def all_gather(self, t: torch.Tensor) -> torch.Tensor:
+        if not self.active:
+            return t.unsqueeze(0)
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+        return out
+
+
+_NO_SHARD = None
+
+
+def no_shard() -> ShardGroup:
+    global _NO_SHARD
+    if _NO_SHARD is None:
+        g = ShardGroup.__new__(ShardGroup)
+        g.dist, g.group, g.active, g.world, g.rank = None, None, False, 1, 0
+        _NO_SHARD = g
+    return _NO_SHARD
+
+
+class _Scratch:
+    """Per-device cache of workspace buffers (the library never allocates)."""
+
+    def __init__(self):
+        self.bufs: Dict[Tuple[str, int], torch.Tensor] = {}
+
+    def get(self, key: str, nbytes: int, dev: torch.device) -> torch.Tensor:
+        k = (key, dev.index or 0)
+        b = self.bufs.get(k)
+        if b is None or b.numel() < nbytes:
+            self.bufs.pop(k, None)
+            b = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
+            self.bufs[k] = b
+        return b
+
+    def clear(self):
+        self.bufs.clear()
+
+
+SCRATCH = _Scratch()
+
+FLAG_FARTHEST = 1
+FLAG_SIMT = 2
+
+
+def pad_ld(n: int) -> int:
+    return (n + 127) // 128 * 128
+
+
+@dataclass
+class ScoreResult:
+    scores_t: Optional[torch.Tensor] = None   # fp16 [k, ld]
+    argmin: Optional[torch.Tensor] = None     # int32 [n]
+    best2: Optional[torch.Tensor] = None      # fp32 [n, 2]
+    counts: Optional[torch.Tensor] = None     # int32 [k]
+    minmax: Optional[torch.Tensor] = None     # int32 [2] (monotone fp16 keys: max, min)
+    dist: Optional[torch.Tensor] = None       # fp32 [n, k] (API parity only; the hot path never asks for it)
+
+
+def score_pass(x: torch.Tensor, centers: torch.Tensor, *, scores: bool = False, argmin: bool = True,
+               best2: bool = False, counts: bool = False, farthest: bool = False, simt: bool = False,
+               scores_out: Optional[torch.Tensor] = None, dist: bool = False) -> ScoreResult:
+    """pairwise_distance_full + its consumers in one pass over x (csrc/score_tc.cu)."""
+    _req_cuda(x, "x")
+    assert x.dtype == torch.float32 and centers.dtype == torch.float32
+    x = x.contiguous()
+    centers = centers.contiguous()
+    n, dim = x.shape
+    k = centers.shape[0]
+    dev = x.device
+    res = ScoreResult()
+    ld = pad_ld(n)
+    if scores:
+        if scores_out is not None and scores_out.shape == (k, ld):
+            res.scores_t = scores_out
+        else:
+            res.scores_t = torch.empty((k, ld), dtype=torch.float16, device=dev)
+        res.minmax = torch.empty(2, dtype=torch.int32, device=dev)
+    if argmin:
+        res.argmin = torch.empty(n, dtype=torch.int32, device=dev)
+    if best2:
+        res.best2 = torch.empty((n, 2), dtype=torch.float32, device=dev)
+    if counts:
+        res.counts = torch.zeros(k, dtype=torch.int32, device=dev)
+    if dist:
+        res.dist = torch.empty((n, k), dtype=torch.float32, device=dev)
+    L = lib()
+    wsb = L.rqk_score_workspace_bytes(n, k, dim)
+    ws = SCRATCH.get("score", wsb, dev)
+    flags = (FLAG_FARTHEST if farthest else 0) | (FLAG_SIMT if simt else 0)
+    check(L.rqk_score_pass(_ptr(x), n, dim, _ptr(centers), k, _ptr(res.scores_t), ld, _ptr(res.argmin),
+                           _ptr(res.best2), _ptr(res.counts), _ptr(res.minmax), _ptr(res.dist), flags, _ptr(ws), ws.numel(),
+                           _stream(dev)))
+    return res
+
+
+@dataclass
+class AuctionStats:
+    rounds: int
+    passes: int
+    cold_passes: int
+    window_misses: int
+    frozen_exit: bool
+    eps: float
+
+
+def _info_to_stats(info: AuctionInfo) -> AuctionStats:
+    eps = float(np.array([info.eps_bits], dtype=np.uint16).view(np.float16)[0])
+    return AuctionStats(int(info.rounds), int(info.passes), int(info.cold_passes), int(info.window_misses),
+                        bool(info.frozen_exit), eps)
+
+
+def auction(scores_t: torch.Tensor, n: int, minmax: torch.Tensor,
+            shard: Optional[ShardGroup] = None, n_global: Optional[int] = None) -> Tuple[torch.Tensor, AuctionStats]:
+    """auction_lap_half on a worker-major fp16 score matrix [k, ld] (csrc/auction.cu) -> int32 [n]."""
+    _req_cuda(scores_t, "scores_t")
+    assert scores_t.dtype == torch.float16 and scores_t.is_contiguous()
+    k, ld = scores_t.shape
+    dev = scores_t.device
+    L = lib()
+    assign = torch.empty(n, dtype=torch.int32, device=dev)
+    info = AuctionInfo()
+    shard = shard or no_shard()
+    if not shard.active:
+        wsb = L.rqk_auction_workspace_bytes(n, k)
+        ws = SCRATCH.get("auction", wsb, dev)
+        check(L.rqk_auction(_ptr(scores_t), ld, n, k, _ptr(minmax), _ptr(assign), _ptr(ws), ws.numel(),
+                            ctypes.byref(info), _stream(dev)))
+        return assign, _info_to_stats(info)
+
+    # ---- jobs sharded over ranks: same kernels, histograms summed between pass and resolve ----
+    assert n_global is not None
+    lay = AuctionLayout()
+    check(L.rqk_auction_layout_query(n, k, ctypes.byref(lay)))
+    ws = SCRATCH.get("auction", lay.total_bytes, dev)
+    red = ws[lay.reduce_offset: lay.reduce_offset + 4 * lay.reduce_count].view(torch.int32)
+    tie_total = ws[lay.tie_total_offset: lay.tie_total_offset + 4 * k].view(torch.int32)
+    mm = minmax.clone()
+    mx, mn = mm[0:1], mm[1:2]
+    shard.all_reduce(mx, "max")
+    shard.all_reduce(mn, "min")
+    st = _stream(dev)
+    check(L.rqk_auction_init(n, ld, k, _ptr(mm), _ptr(ws), ws.numel(), st))
+    batch = 6
+    for _ in range(0, 5000, batch):
+        for _q in range(batch):
+            check(L.rqk_auction_pass(_ptr(scores_t), ld, n, k, n_global, _ptr(ws), ws.numel(), st))
+            shard.all_reduce(red, "sum")
+            check(L.rqk_auction_resolve(n, ld, k, n_global, _ptr(ws), ws.numel(), st))
+            totals = shard.all_gather(tie_total)                      # [world, k]
+            offs = totals[: shard.rank].sum(dim=0, dtype=torch.int32) if shard.rank > 0 else \
+                torch.zeros(k, dtype=torch.int32, device=dev)
+            check(L.rqk_auction_tie_offset(n, ld, k, _ptr(offs.contiguous()), _ptr(ws), ws.numel(), st))
+        check(L.rqk_auction_poll(n, ld, k, _ptr(ws), ws.numel(), ctypes.byref(info), st))
+        if info.done:
+            break
+    if not info.done:
+        raise _lib.RqkError("sharded auction did not terminate")
+    check(L.rqk_auction_finalize(n, ld, k, _ptr(ws), ws.numel(), _ptr(assign), st))
+    return assign, _info_to_stats(info)
+
+
+def centroid_accumulate(x: torch.Tensor, assign: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Deterministic per-cluster sums [k, dim] fp32 and counts [k] int64 (csrc/centroid.cu)."""
+    _req_cuda(x, "x")
+    n, dim = x.shape
+    dev = x.device
+    L = lib()
+    sums = torch.empty((k, dim), dtype=torch.float32, device=dev)
+    counts = torch.empty(k, dtype=torch.int64, device=dev)
+    ws = SCRATCH.get("centroid", L.rqk_centroid_workspace_bytes(n, k, dim), dev)
+    check(L.rqk_centroid_accumulate(_ptr(x), n, dim, _ptr(assign), k, _ptr(sums), _ptr(counts), _ptr(ws),
+                                    ws.numel(), _stream(dev)))
+    return sums, counts
+
+
+def centroid_finalize(sums: torch.Tensor, counts: torch.Tensor, centers: torch.Tensor):
+    """centers <- sums / counts in place; returns (device fp32[2] = {shift, #empty}, int32 empty mask [k])."""
+    k, dim = sums.shape
+    dev = sums.device
+    out = torch.empty(2, dtype=torch.float32, device=dev)
+    empty = torch.empty(k, dtype=torch.int32, device=dev)
+    check(lib().rqk_centroid_finalize(_ptr(sums), _ptr(counts), k, dim, _ptr(centers), _ptr(out), _ptr(empty),
+                                      _stream(dev)))
+    return out, empty
+
+
+_group_end_cache: Dict[Tuple[Tuple[int, ...], int], torch.Tensor] = {}
+
+
+def _group_end(group_dims: Sequence[int], dev: torch.device) -> torch.Tensor:
+    key = (tuple(int(g) for g in group_dims), dev.index or 0)
+    t = _group_end_cache.get(key)
+    if t is None:
+        t = torch.tensor(np.cumsum(key[0]), dtype=torch.int32, device=dev)
+        _group_end_cache[key] = t
+    return t
+
+
+def residual_normalise(x: torch.Tensor, ids: torch.Tensor, centers: torch.Tensor, group_dims: Sequence[int],
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """r = x - centers[ids]; per dim-group r /= (|r| + 1e-8) (csrc/residual.cu).  out may be x."""
+    _req_cuda(x, "x")
+    n, dim = x.shape
+    dev = x.device
+    if out is None:
+        out = torch.empty_like(x)
+    ge = _group_end(group_dims, dev)
+    ids32 = ids if ids.dtype == torch.int32 else ids.to(torch.int32)
+    check(lib().rqk_residual_normalise(_ptr(x), n, dim, _ptr(ids32.contiguous()), _ptr(centers.contiguous()),
+                                       _ptr(ge), ge.numel(), _ptr(out), _stream(dev)))
+    return out
+
+
+def scale_dims(x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    n, dim = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib().rqk_scale_dims(_ptr(x), n, dim, _ptr(w), _ptr(out), _stream(x.device)))
+    return out
+
+
+def gather_rows(x: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
+    """x[rows] for centroid (re-)initialisation; rows int64 on the device."""
+    dim = x.shape[1]
+    out = torch.empty((rows.numel(), dim), dtype=torch.float32, device=x.device)
+    check(lib().rqk_gather_rows(_ptr(x), dim, _ptr(rows), rows.numel(), _ptr(out), _stream(x.device)))
+    return out
+
+
+def encode(x: torch.Tensor, centers: List[torch.Tensor], needs: Sequence[int], group_dims: Sequence[int],
+           weights: Optional[List[Optional[torch.Tensor]]] = None, mode: int = 0, simt: bool = False) -> torch.Tensor:
+    """Multi-level ids int32 [levels, n] (csrc/encode.cu).  mode 0 = the chain train() emits, mode 1 = predict()."""
+    _req_cuda(x, "x")
+    x = x.contiguous()
+    n, dim = x.shape
+    dev = x.device
+    levels = len(centers)
+    centers = [c.contiguous() for c in centers]
+    PtrArr = ctypes.c_void_p * levels
+    cptr = PtrArr(*[c.data_ptr() for c in centers])
+    wptr = PtrArr(*[(w.data_ptr() if w is not None else None) for w in (weights or [None] * levels)])
+    IntArr = ctypes.c_int32 * levels
+    ks = IntArr(*[int(c.shape[0]) for c in centers])
+    nd = IntArr(*[int(v) for v in needs])
+    ids = torch.empty((levels, n), dtype=torch.int32, device=dev)
+    ge = _group_end(group_dims, dev)
+    L = lib()
+    kmax = max(int(c.shape[0]) for c in centers)
+    ws = SCRATCH.get("encode", L.rqk_encode_workspace_bytes(n, dim, kmax), dev)
+    check(L.rqk_encode(_ptr(x), n, dim, levels, cptr, wptr, ks, nd, _ptr(ge), ge.numel(), _ptr(ids), mode,
+                       FLAG_SIMT if simt else 0, _ptr(ws), ws.numel(), _stream(dev)))
+    return ids
