@@ -185,34 +185,76 @@ def auction(scores_t: torch.Tensor, n: int, minmax: torch.Tensor,
 
     # ---- jobs sharded over ranks: same kernels, histograms summed between pass and resolve ----
     assert n_global is not None
-    lay = AuctionLayout()
-    check(L.rqk_auction_layout_query(n, k, ctypes.byref(lay)))
-    ws = SCRATCH.get("auction", lay.total_bytes, dev)
-    red = ws[lay.reduce_offset: lay.reduce_offset + 4 * lay.reduce_count].view(torch.int32)
-    tie_total = ws[lay.tie_total_offset: lay.tie_total_offset + 4 * k].view(torch.int32)
+    sess = AuctionSession(scores_t, n, n_global)
     mm = minmax.clone()
-    mx, mn = mm[0:1], mm[1:2]
-    shard.all_reduce(mx, "max")
-    shard.all_reduce(mn, "min")
-    st = _stream(dev)
-    check(L.rqk_auction_init(n, ld, k, _ptr(mm), _ptr(ws), ws.numel(), st))
+    shard.all_reduce(mm[0:1], "max")
+    shard.all_reduce(mm[1:2], "min")
+    sess.init(mm)
     batch = 6
+    info = None
     for _ in range(0, 5000, batch):
         for _q in range(batch):
-            check(L.rqk_auction_pass(_ptr(scores_t), ld, n, k, n_global, _ptr(ws), ws.numel(), st))
-            shard.all_reduce(red, "sum")
-            check(L.rqk_auction_resolve(n, ld, k, n_global, _ptr(ws), ws.numel(), st))
-            totals = shard.all_gather(tie_total)                      # [world, k]
-            offs = totals[: shard.rank].sum(dim=0, dtype=torch.int32) if shard.rank > 0 else \
-                torch.zeros(k, dtype=torch.int32, device=dev)
-            check(L.rqk_auction_tie_offset(n, ld, k, _ptr(offs.contiguous()), _ptr(ws), ws.numel(), st))
-        check(L.rqk_auction_poll(n, ld, k, _ptr(ws), ws.numel(), ctypes.byref(info), st))
+            sess.do_pass()
+            shard.all_reduce(sess.reduce_block, "sum")
+            sess.resolve()
+            totals = shard.all_gather(sess.tie_total)                 # [world, k]
+            sess.tie_offset(totals[: shard.rank].sum(dim=0, dtype=torch.int32) if shard.rank > 0 else None)
+        info = sess.poll()
         if info.done:
             break
-    if not info.done:
+    if info is None or not info.done:
         raise _lib.RqkError("sharded auction did not terminate")
-    check(L.rqk_auction_finalize(n, ld, k, _ptr(ws), ws.numel(), _ptr(assign), st))
-    return assign, _info_to_stats(info)
+    return sess.finalize(), _info_to_stats(info)
+
+
+class AuctionSession:
+    """One rank's side of the sharded auction protocol (the step entry points of include/rqk.h).
+    Per pass: do_pass() -> SUM `reduce_block` over ranks -> resolve() -> gather `tie_total` over ranks
+    -> tie_offset(sum over lower ranks).  Every rank then holds identical thresholds and state."""
+
+    def __init__(self, scores_t: torch.Tensor, n: int, n_global: int):
+        _req_cuda(scores_t, "scores_t")
+        assert scores_t.dtype == torch.float16 and scores_t.is_contiguous()
+        self.s, self.n, self.n_global = scores_t, int(n), int(n_global)
+        self.k, self.ld = scores_t.shape
+        self.dev = scores_t.device
+        self.L = lib()
+        lay = AuctionLayout()
+        check(self.L.rqk_auction_layout_query(self.n, self.k, ctypes.byref(lay)))
+        self.ws = torch.empty(int(lay.total_bytes), dtype=torch.uint8, device=self.dev)
+        self.reduce_block = self.ws[lay.reduce_offset: lay.reduce_offset + 4 * lay.reduce_count].view(torch.int32)
+        self.tie_total = self.ws[lay.tie_total_offset: lay.tie_total_offset + 4 * self.k].view(torch.int32)
+
+    def _args(self):
+        return _ptr(self.ws), self.ws.numel()
+
+    def init(self, minmax_global: torch.Tensor):
+        self._mm = minmax_global.contiguous()
+        check(self.L.rqk_auction_init(self.n, self.ld, self.k, _ptr(self._mm), *self._args(), _stream(self.dev)))
+
+    def do_pass(self):
+        check(self.L.rqk_auction_pass(_ptr(self.s), self.ld, self.n, self.k, self.n_global, *self._args(),
+                                      _stream(self.dev)))
+
+    def resolve(self):
+        check(self.L.rqk_auction_resolve(self.n, self.ld, self.k, self.n_global, *self._args(), _stream(self.dev)))
+
+    def tie_offset(self, offsets: Optional[torch.Tensor]):
+        if offsets is None:
+            return
+        self._offs = offsets.to(torch.int32).contiguous()
+        check(self.L.rqk_auction_tie_offset(self.n, self.ld, self.k, _ptr(self._offs), *self._args(),
+                                            _stream(self.dev)))
+
+    def poll(self) -> AuctionInfo:
+        info = AuctionInfo()
+        check(self.L.rqk_auction_poll(self.n, self.ld, self.k, *self._args(), ctypes.byref(info), _stream(self.dev)))
+        return info
+
+    def finalize(self) -> torch.Tensor:
+        assign = torch.empty(self.n, dtype=torch.int32, device=self.dev)
+        check(self.L.rqk_auction_finalize(self.n, self.ld, self.k, *self._args(), _ptr(assign), _stream(self.dev)))
+        return assign
 
 
 def centroid_accumulate(x: torch.Tensor, assign: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:

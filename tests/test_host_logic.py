@@ -1,0 +1,154 @@
+"""Host-side mirror of the reference interface: config validation, checkpoint files, iteration budget,
+error behaviour, and the rule that nothing computes without the CUDA library.  CPU only."""
+import json
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from generative_ranking_recommender_b200 import (CheckpointManager, HierarchicalRQKMeans, HierarchicalRQKMeansConfig,
+                                                   hierarchicalRqClusterParams)
+from generative_ranking_recommender_b200._lib import RqkError
+from generative_ranking_recommender_b200.balancekmeans import KMeans, _InitPrefetcher, pairwise_cosine
+
+
+def _cfg(**kw):
+    base = dict(layer_clusters=[128, 128, 256], need_clusters=[128, 128, 256], embedding_dim=512)
+    base.update(kw)
+    return HierarchicalRQKMeansConfig(**base)
+
+
+def test_config_normalisation_matches_reference():
+    c = _cfg()
+    assert c.group_dims == [512] and c.hierarchical_weights == [[1.0]] * 3 and c.iter_limit == 100
+    c = _cfg(group_dims=512, hierarchical_weights=0.3)          # scalar weight -> uniform 1/len(groups)
+    assert c.hierarchical_weights == [[1.0]] * 3
+    c = _cfg(group_dims=[128, 384])
+    assert c.hierarchical_weights == [[0.5, 0.5]] * 3
+
+
+@pytest.mark.parametrize("kw,msg", [
+    (dict(group_dims=[100, 100]), "Sum of group_dims 200 must equal embedding_dim 512"),
+    (dict(hierarchical_weights=[[1.0]]), "Length of hierarchical_weights 1 must equal length of layer_clusters 3"),
+    (dict(group_dims=[256, 256], hierarchical_weights=[[1.0]] * 3), "Length of hierarchical_weights[0] 1 must equal length of group_dims 2"),
+])
+def test_config_errors_verbatim(kw, msg):
+    with pytest.raises(ValueError) as e:
+        _cfg(**kw)
+    assert msg in str(e.value)
+
+
+def test_legacy_params_class():
+    p = hierarchicalRqClusterParams()
+    assert p.layer_clusters == [128, 256, 256] and p.need_clusters == [128, 128, 128] and p.group_dims == [1024]
+
+
+def test_adaptive_iter_limit_table(golden_dir):
+    rows = np.load(os.path.join(golden_dir, "iter_limit.npz"))["rows"]
+    f = HierarchicalRQKMeans._calculate_adaptive_iter_limit
+    for n, k, layer, base, sub, want in rows:
+        assert f(int(n), int(k), int(layer), int(base), bool(sub)) == int(want)
+
+
+def test_checkpoint_manager_files_and_resume_rule(tmp_path):
+    cm = CheckpointManager(str(tmp_path / "ck"))
+    assert cm.get_last_completed_layer() == -1
+    ids = torch.arange(10)
+    res = torch.randn(10, 4)
+    cen = torch.randn(3, 4)
+    cm.save_layer_checkpoint(0, ids, res, cen, None)
+    cm.save_layer_checkpoint(2, ids, res, cen, None)            # stale higher layer after a gap is ignored (A10)
+    assert cm.get_last_completed_layer() == 0
+    assert not (tmp_path / "ck" / "layer_0_checkpoint.tmp").exists()
+    raw = pickle.load(open(tmp_path / "ck" / "layer_0_checkpoint.pkl", "rb"))
+    assert set(raw) == {"layer", "cluster_ids", "residual_data", "cluster_centers", "match_matrix"}
+    assert isinstance(raw["cluster_ids"], np.ndarray) and raw["cluster_ids"].dtype == np.int64
+    assert raw["residual_data"].dtype == np.float32 and raw["cluster_centers"].shape == (3, 4)
+    back = cm.load_layer_checkpoint(0, torch.device("cpu"))
+    assert torch.equal(back["cluster_ids"], ids) and torch.equal(back["residual_data"], res)
+    with pytest.raises(ValueError):
+        cm.save_layer_checkpoint(1, ids, res, None, None)       # validation: centres must not be None
+    assert not (tmp_path / "ck" / "layer_1_checkpoint.pkl").exists()
+    cm.save_metadata({"num_layers": 3, "x": np.float32(1.5)})
+    assert cm.load_metadata()["num_layers"] == 3
+    cm.clear_checkpoints()
+    assert cm.get_last_completed_layer() == -1 and cm.load_metadata() is None
+
+
+def test_model_save_load_formats(tmp_path):
+    m = HierarchicalRQKMeans(_cfg(), device=torch.device("cpu"))
+    m.cluster_centers_list = [torch.randn(128, 512), torch.randn(128, 512), torch.randn(256, 512)]
+    m.is_trained = True
+    m.save_model(str(tmp_path / "model"))
+    cfg = json.load(open(tmp_path / "model" / "config.json"))
+    assert cfg["layer_clusters"] == [128, 128, 256] and cfg["group_dims"] == [512] and cfg["iter_limit"] == 100
+    centres = pickle.load(open(tmp_path / "model" / "cluster_centers.pkl", "rb"))
+    assert [c.shape for c in centres] == [(128, 512), (128, 512), (256, 512)] and centres[0].dtype == np.float32
+    assert not (tmp_path / "model" / "match_matrices.pkl").exists()
+    m2 = HierarchicalRQKMeans(_cfg(iter_limit=5), device=torch.device("cpu"))
+    assert not m2.is_trained
+    m2.load_model(str(tmp_path / "model"))
+    assert m2.is_trained and m2.config.iter_limit == 100
+    assert torch.equal(m2.cluster_centers_list[2], m.cluster_centers_list[2])
+    assert m2.get_training_status() == {"is_trained": True, "last_completed_layer": -1, "total_layers": 3,
+                                        "can_resume": False}
+
+
+def test_errors_match_reference():
+    m = HierarchicalRQKMeans(_cfg(), device=torch.device("cpu"))
+    with pytest.raises(ValueError, match="Input dimension 64 does not match config embedding_dim 512"):
+        m.train(np.zeros((10, 64), np.float32))
+    with pytest.raises(RuntimeError, match="Model not trained"):
+        m.predict(np.zeros((10, 512), np.float32))
+    m.is_trained, m.cluster_centers_list = True, [torch.zeros(128, 512)]
+    with pytest.raises(ValueError, match="Input dimension 64"):
+        m.predict(np.zeros((10, 64), np.float32))
+    with pytest.raises(NotImplementedError):
+        KMeans(4, device=torch.device("cuda:0")).fit(torch.zeros(8, 32), distance="manhattan")
+    with pytest.raises(NotImplementedError):
+        pairwise_cosine(None, None)
+
+
+def test_there_is_no_cpu_path():
+    """A CPU device (or a box without CUDA) must raise, never fall back to torch or the oracle."""
+    m = HierarchicalRQKMeans(_cfg(embedding_dim=32, layer_clusters=[4], need_clusters=[4]), device=torch.device("cpu"))
+    with pytest.raises(RqkError, match="no CPU fallback"):
+        m.train(np.zeros((64, 32), np.float32))
+    with pytest.raises(RqkError, match="no CPU fallback"):
+        KMeans(4, device=torch.device("cpu"), balanced=True).fit_by_min_loss(torch.zeros(64, 32), 16, iter_limit=1)
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception):
+            KMeans(4, device=torch.device("cuda:0"), balanced=True).predict(torch.zeros(8, 32))
+
+
+def test_product_never_imports_the_oracle():
+    import generative_ranking_recommender_b200 as pkg
+    root = os.path.dirname(pkg.__file__)
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "rqk_oracle" not in src, f
+
+
+def test_init_prefetcher_keeps_the_numpy_stream_exact():
+    np.random.seed(7)
+    a = np.random.choice(1000, 8, replace=False)
+    b = np.random.choice(1000, 8, replace=False)
+    after = np.random.randint(1 << 30)
+    # same stream, second draw prefetched on a thread
+    np.random.seed(7)
+    a2 = np.random.choice(1000, 8, replace=False)
+    p = _InitPrefetcher(1000, 8)
+    p.start()
+    b2 = p.take()
+    assert np.array_equal(a, a2) and np.array_equal(b, b2) and np.random.randint(1 << 30) == after
+    # a cancelled prefetch leaves no trace
+    np.random.seed(7)
+    np.random.choice(1000, 8, replace=False)
+    p = _InitPrefetcher(1000, 8)
+    p.start()
+    p.cancel()
+    assert np.array_equal(np.random.choice(1000, 8, replace=False), b)
