@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py - RQ-KMeans vectors/sec per iteration (512-d, [128,128,256]) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--rows R]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): 1M x 512 fp32 synthetic vectors per GPU (weak scaling: the fit is
+ONE balanced K-Means over all ranks' rows, sharded row-wise; per iteration only the K x 512 sums,
+K counts and the auction's threshold histograms cross NVLink).  A step = one `fit_by_min_loss`
+iteration of the reference (balancekmeans/__init__.py:304-362): fused score pass, balanced auction,
+centroid update, loss/shift read-back; steps cycle over the three levels (K = 128 on X, 128 and 256 on
+the normalised residuals).  value = rows of all ranks x steps / time (CUDA events, max over ranks).
+
+Extra keys: `e2e` = the same metric through HierarchicalRQKMeans.train() on HOST arrays (H2D of X and
+D2H of the ids inside the timed region); `roofline` = the auction pass kernel (one read of the K x N
+fp16 score matrix per launch) against the measured HBM copy bandwidth; `cpu_baseline` = the CPU oracle
+port of the reference (all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CLUSTERS = [128, 128, 256]
+DIM = 512
+METRIC = "RQ-KMeans vectors/sec per iteration (512-d, [128,128,256])"
+UNIT = "vectors/s"
+
+
+# --------------------------------------------------------------------------------------------
+def _env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        mhz, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                mhz.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        mhz.sort()
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(mhz)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def recorded_traffic(k):
+    """DRAM bytes per launch of the auction pass kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(f"auction_pass_k{k}")
+        except Exception:
+            return None
+    return None
+
+
+# --------------------------------------------------------------------------------------------
+def cpu_baseline_port(sample_rows, seed=1234):
+    """One fit_by_min_loss iteration of the oracle port per level on a bounded sample, all host threads.
+    Same regime as the bench workload (N % K != 0 -> the reference's 1002-round fallback)."""
+    import numpy as np
+    from oracle import rqk_oracle as O
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((sample_rows, DIM), dtype=np.float32)
+    per_level, rounds = [], []
+    cur = x
+    for lvl, k in enumerate(CLUSTERS):
+        c = cur[rng.choice(sample_rows, k, replace=False)].copy()
+        t0 = time.perf_counter()
+        d = O.pairwise_distance_full(cur, c, 100000)                     # :308
+        res = O.auction_lap_half(-d)                                     # :310
+        c1 = O.update_centers(cur, res.assignment, c)                    # :314-324
+        d2 = O.pairwise_distance_full(cur, c1, 100000)                   # :327
+        cnt = np.bincount(np.argmin(d2, axis=1), minlength=k)            # :328-329
+        O.overflow_loss(cnt, 1 << 30)
+        O.center_shift(c1, c)
+        per_level.append(time.perf_counter() - t0)
+        rounds.append(res.rounds)
+        if lvl < len(CLUSTERS) - 1:
+            cur = O.residual_normalised(cur, np.argmin(d2, axis=1), c1, [DIM])
+    total = sum(per_level)
+    return {"value": sample_rows * len(CLUSTERS) / total, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
+            "sample": f"{sample_rows} x {DIM} fp32 S-iso rows, one fit iteration per level {CLUSTERS}, "
+                      f"auction rounds {rounds}, {total:.1f} s CPU",
+            "seconds_per_level": [round(t, 2) for t in per_level]}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port; the reference itself is Python + torch CPU
+    and does not exist on the GPU box) on the box's host cores, same metric/unit/config."""
+    rank = _env_int("RANK", 0)
+    if rank != 0:
+        return
+    rows = args.cpu_rows
+    vals = []
+    base = None
+    for i in range(args.warmup + args.steps):
+        base = cpu_baseline_port(rows, seed=1234 + i)
+        if i >= args.warmup:
+            vals.append(base["value"])
+        if sum(base["seconds_per_level"]) * (args.warmup + args.steps - i - 1) > 240:
+            break
+    v = sum(vals) / max(len(vals), 1) if vals else base["value"]
+    steps = max(len(vals), 1)
+    base["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * rows / v, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp32 distance / fp16 auction (CPU)", "data": "synthetic",
+            "config": workload_config(args, args.gpus), "cpu_baseline": base,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"{args.rows} x {DIM} fp32 rows per GPU, 3-level RQ-KMeans {CLUSTERS} balanced fit iteration "
+                        f"(score pass + auction + centroid update), levels cycled",
+            "rows_per_gpu": args.rows, "rows_total": args.rows * world, "dim": DIM, "codebook": CLUSTERS,
+            "sharding": f"rows x{world}", "l2": "inputs (2 GB X + 256/512 MB scores per level) exceed the 126 MB L2"}
+
+
+# --------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=1000000, help="rows per GPU")
+    ap.add_argument("--cpu-rows", type=int, default=20032, help="rows of the CPU baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from generative_ranking_recommender_b200 import HierarchicalRQKMeans, HierarchicalRQKMeansConfig, engine
+    from generative_ranking_recommender_b200.balancekmeans import KMeans
+
+    rank, world, local = _env_int("RANK", 0), _env_int("WORLD_SIZE", 1), _env_int("LOCAL_RANK", 0)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    shard = engine.ShardGroup() if world > 1 else None
+    n = args.rows
+    n_global = n * world
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- synthetic level inputs, resident in HBM before anything is timed ----
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    x0 = torch.randn((n, DIM), device=dev, generator=g)
+    np.random.seed(42)
+    torch.manual_seed(42)
+    levels = []
+    cur = x0
+    for lvl, k in enumerate(CLUSTERS):
+        km = KMeans(n_clusters=k, device=dev, balanced=True, shard=shard)
+        km.cluster_centers = km.initialize(cur)
+        levels.append((km, cur))
+        if lvl < len(CLUSTERS) - 1:
+            km._iterate(cur, n_global)                       # one real iteration to get sensible centroids
+            ids = engine.score_pass(cur, km.cluster_centers, argmin=True).argmin
+            cur = engine.residual_normalise(cur, ids, km.cluster_centers, [DIM])
+    bufs = [None] * len(levels)
+    passes, rounds = [], []
+
+    def step(i):
+        lvl = i % len(levels)
+        km, xl = levels[lvl]
+        score, _assign, stats, _shift = km._iterate(xl, n_global, bufs[lvl])
+        bufs[lvl] = score.scores_t
+        c = score.counts.to(torch.int64)
+        if shard is not None:
+            shard.all_reduce(c, "sum")
+        c.cpu()                                              # loss read-back of the fit loop (:333-341)
+        if stats is not None:
+            passes.append(stats.passes)
+            rounds.append(stats.rounds)
+
+    for i in range(args.warmup):
+        step(i)
+    passes.clear()
+    rounds.clear()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = n_global * args.steps / (ms / 1e3)
+
+    # launches of our kernels inside the timed region: per step score pass (pad, minmax, split, tc) = 4,
+    # auction init (memset + init) 2 + 3 per pass (pass, resolve, tie prefix) + finalize 1, centroid update 8
+    gpu_launches = int(sum(4 + 2 + 3 * (-(-p // 6) * 6) + 1 + 8 for p in passes)) if passes else 0
+
+    # ---- roofline of the dominant kernel: one steady-state BID pass of the auction at level 0 ----
+    roofline = None
+    if rank == 0:
+        km, xl = levels[0]
+        sc = engine.score_pass(xl, km.cluster_centers, scores=True, argmin=False)
+        sess = engine.AuctionSession(sc.scores_t, n, n)
+        sess.init(sc.minmax)
+        for _ in range(8):                                   # cold start + first rounds
+            sess.do_pass()
+            sess.resolve()
+        times = []
+        for _ in range(6):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            sess.do_pass()
+            b.record()
+            sess.resolve()
+            torch.cuda.synchronize()
+            times.append(a.elapsed_time(b))
+        info = sess.poll()
+        t_pass = sum(times) / len(times)
+        k0 = CLUSTERS[0]
+        alg_bytes = 2.0 * k0 * n                             # one read of the fp16 score matrix (2*K per vector per round)
+        peak, how = measured_peaks()
+        achieved = alg_bytes / (t_pass * 1e-3) / 1e9
+        roofline = {"kernel": "auction_pass_kernel<128> (steady-state BID+HIST pass, K=128)", "bound": "hbm",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": recorded_traffic(k0), "algorithmic_bytes_per_launch": alg_bytes,
+                    "ms_per_launch": t_pass, "peak_source": how, "done_while_timing": bool(info.done)}
+
+    # ---- end to end through the public API: host array in, ids out ----
+    e2e = None
+    if not args.no_e2e:
+        xh = torch.empty((n, DIM), dtype=torch.float32, pin_memory=True)
+        xh.copy_(x0)
+        x_np = xh.numpy()
+        del levels, bufs, cur, x0
+        engine.SCRATCH.clear()
+        torch.cuda.empty_cache()
+        cfg = HierarchicalRQKMeansConfig(layer_clusters=CLUSTERS, need_clusters=CLUSTERS, embedding_dim=DIM,
+                                         group_dims=[DIM], hierarchical_weights=[[1.0]] * 3, iter_limit=20)
+        np.random.seed(42)
+        torch.manual_seed(42)
+        model = HierarchicalRQKMeans(cfg, device=dev, shard=shard)
+        barrier()
+        t0 = time.perf_counter()
+        out = model.train(x_np, resume=False)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        iters = sum(len(s) for s in model.fit_stats)
+        ids_bytes = sum(t.numel() * t.element_size() for t in out["cluster_ids"])
+        e2e = {"value": n_global * iters / dt, "unit": UNIT, "h2d_bytes_per_step": x_np.nbytes * world / max(iters, 1),
+               "d2h_bytes_per_step": ids_bytes * world / max(iters, 1), "seconds": dt, "iterations": iters,
+               "iterations_per_level": [len(s) for s in model.fit_stats],
+               "api": "HierarchicalRQKMeans.train(np.ndarray) -> cluster_ids (int64, host), iter_limit=20"}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            cpu = cpu_baseline_port(args.cpu_rows)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "3xTF32 distance (fp32 accumulate), fp16 auction, fp32 centroids",
+                "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
+                "gpu_launches": gpu_launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
+                "auction": {"passes_per_step": passes, "reference_rounds_per_step": rounds}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

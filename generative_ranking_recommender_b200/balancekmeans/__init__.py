@@ -273,6 +273,17 @@ class KMeans(object):
         shard.all_reduce(out, "sum")
         return out
 
+    def _iterate(self, X, n_global, scores_buf=None):
+        """One fit iteration on the device: fused score pass (scores for the auction + argmin counts of
+        the current centres), balanced assignment, centroid update.  Returns
+        (score result, assignment int32, auction stats, centre shift)."""
+        k = self.n_clusters
+        score = engine.score_pass(X, self.cluster_centers, scores=self.balanced and n_global >= k,
+                                  argmin=True, counts=True, scores_out=scores_buf)
+        assign, stats = self._assign(X, score, n_global)
+        shift = self._update(X, assign, n_global)
+        return score, assign, stats, shift
+
     def fit_by_min_loss(self, X, target_nodes_num, distance="euclidean", tol=1e-3, tqdm_flag=True, iter_limit=0,
                         gamma_for_soft_dtw=0.001, half=False, online=False, iter_k=None):
         """:259-365.  Sets self.cluster_centers to the centroids of the last iteration whose overflow
@@ -317,8 +328,10 @@ class KMeans(object):
                         pending = None
                     idx = prefetch.take() if (prefetch and prefetch.thread) else self._draw(n_global)
                     self.cluster_centers = self._rows(X, idx, n_global, row0)
-                score = engine.score_pass(X, self.cluster_centers, scores=self.balanced and n_global >= k,
-                                          argmin=True, counts=True, scores_out=scores_buf)
+                if prefetch and prefetch.thread is None and (iteration + 1) % 10 == 0 and \
+                        (iter_limit == 0 or iteration + 1 < iter_limit):
+                    prefetch.start()                                       # the draw of the coming re-init
+                score, assign, stats, shift = self._iterate(X, n_global, scores_buf)
                 scores_buf = score.scores_t
                 if pending is not None:                                    # :327-341 for the previous iteration
                     c = score.counts.to(torch.int64)
@@ -327,11 +340,6 @@ class KMeans(object):
                     if loss <= min_loss:                                   # `<=`: later ties win
                         min_loss, best = loss, pending
                     pending = None
-                if prefetch and prefetch.thread is None and (iteration + 1) % 10 == 0 and \
-                        (iter_limit == 0 or iteration + 1 < iter_limit):
-                    prefetch.start()                                       # the draw of the coming re-init
-                assign, stats = self._assign(X, score, n_global)
-                shift = self._update(X, assign, n_global)
                 pending = self.cluster_centers.clone()
                 iteration += 1
                 self.last_fit_stats.append({"iteration": iteration, "shift": shift,

@@ -13,18 +13,22 @@
 //          bidder) per job on the fly.
 //
 // One PASS = every CTA streams its contiguous range of 128-job (K<=128) or 64-job tiles, all K
-// workers deep, through a double-buffered cp.async pipeline:
-//   phase 1 (BID)  per (worker, job): bid = ((v - T_w) + eps) if v beats the worker's threshold T_w
-//                  (the (N/K+1)-th largest value, :66,:76), ties at T_w taken lowest job index first
-//                  up to the worker's quota; retain hack (:86-87) and the counter>1000 fallback
-//                  (:88-89) override; column max with first-argmax (:104); cost/owner update
-//                  (:118-123).
-//   phase 2 (HIST) the NEXT round's values of the same tile (still in shared memory) are
-//                  histogrammed per worker into a 128-bin window of fp16 keys placed just below
-//                  the current threshold, plus an "above the window" count.
+// workers deep, through a double-buffered cp.async pipeline.  Per tile:
+//   phase 1 (BID)  A warp owns a worker row of the tile, so ties are met in job order.  The sweep is a
+//                  half2 FILTER: v = S - cost (ownership ignored: the owner's true value S is only
+//                  larger) compared with the worker's threshold T_w, the (N/K+1)-th largest value
+//                  (:66).  The ~1 % survivors are compacted into a per-warp list and turned into bids
+//                  ((v - T_w) + eps, :76) there; ties at T_w are taken lowest job index first up to
+//                  the worker's quota.  The one owner entry of every job is handled by the job's
+//                  column thread (retain hack :86-87, counter>1000 fallback :88-89).  The column max
+//                  with first-argmax (:104) is an atomicMax on (bid << 16 | ~worker) in shared memory;
+//                  then cost/owner update (:118-123).
+//   phase 2 (HIST) the NEXT round's values of the same tile (still in shared memory) are filtered
+//                  against a <=128-key window predicted just below each threshold and histogrammed
+//                  (16-bit packed counters), plus an "above the window" count.
 // A 1-CTA RESOLVE kernel turns the merged histograms into exact thresholds (16-bit radix select:
-// window hit -> exact; miss or cold start -> coarse 128-bin pass over all keys, then refine), and
-// a K-CTA kernel prefix-sums per-CTA tie counts so the canonical tie rule is global.  So a
+// window hit -> exact; miss -> slide; cold start -> coarse 128-bin pass over all keys, then refine),
+// and a K-CTA kernel prefix-sums per-CTA tie counts so the canonical tie rule is global.  So a
 // steady-state round reads S exactly once.
 //
 // Exact fast-forward.  With N % K != 0 the reference cannot terminate before its counter>1000
@@ -41,13 +45,16 @@
 
 namespace rqk {
 
-constexpr int AUC_W = 128;        // histogram bins per worker
-constexpr int AUC_NW = 16;        // warps per CTA
+constexpr int AUC_W = 128;         // histogram bins per worker
+constexpr int AUC_NW = 16;         // warps per CTA
 constexpr int AUC_THREADS = AUC_NW * 32;
-constexpr int AUC_MAX_CTAS = 296; // 2 per SM
+constexpr int AUC_BASE_CTAS = 296; // 2 per SM
+constexpr int AUC_MAX_CTAS = 1024; // tie-prefix kernel limit
+constexpr int AUC_MAX_JOBS_PER_CTA = 65024;   // 16-bit per-CTA counters
 constexpr int AUC_MIN_TILES_PER_CTA = 2;
-constexpr int AUC_COLD_SHIFT = 9; // 128 bins x 512 keys cover all 65536 fp16 keys
-constexpr int AUC_WIN_ABOVE = 16; // predicted window = [T - 112, T + 16)
+constexpr int AUC_COLD_SHIFT = 9;  // 128 bins x 512 keys cover all 65536 fp16 keys
+constexpr int AUC_LIST_CAP = 160;  // per-warp survivor list entries (a full 128-job row always fits after a flush)
+constexpr int AUC_MIN_KEY = 0x0400; // key of the most negative finite half: fine windows never reach -inf
 
 enum { MODE_HIST = 0, MODE_BID = 1, MODE_DONE = 2 };
 
@@ -82,8 +89,9 @@ struct AuctionPtrs {
     int* win_shift;           // [K] log2 keys per bin
     int* tkey;                // [K] resolved threshold key, -1 = unresolved
     int* take;                // [K] ties at the threshold that still get a bid
+    int* miss_run;            // [K] consecutive window slides
     unsigned int* tieprefix;  // [G][K]
-    unsigned int* hist_cta;   // [G][K][W]
+    unsigned short* hist_cta; // [G][K][W] per-CTA histograms (16-bit: a CTA owns < 65536 jobs)
 };
 
 static inline int auction_tile_cols(int K) { return K <= 128 ? 128 : 64; }
@@ -91,7 +99,9 @@ static inline int auction_tile_cols(int K) { return K <= 128 ? 128 : 64; }
 static inline int auction_grid(long long N, int K) {
     long long tiles = ceil_div<long long>(N, auction_tile_cols(K));
     long long g = ceil_div<long long>(tiles, AUC_MIN_TILES_PER_CTA);
-    if (g > AUC_MAX_CTAS) g = AUC_MAX_CTAS;
+    if (g > AUC_BASE_CTAS) g = AUC_BASE_CTAS;
+    long long g16 = ceil_div<long long>(N, AUC_MAX_JOBS_PER_CTA);
+    if (g < g16) g = g16;
     if (g < 1) g = 1;
     return (int)g;
 }
@@ -110,8 +120,9 @@ static inline size_t auction_ws_layout(long long N, long long ld, int K, Auction
     size_t o_ws = take_((size_t)K * 4);
     size_t o_tk = take_((size_t)K * 4);
     size_t o_take = take_((size_t)K * 4);
+    size_t o_mr = take_((size_t)K * 4);
     size_t o_tp = take_((size_t)G * K * 4);
-    size_t o_hc = take_((size_t)G * K * AUC_W * 4);
+    size_t o_hc = take_((size_t)G * K * AUC_W * 2);
     if (reduce_off) *reduce_off = o_hist;
     if (tie_total_off) *tie_total_off = o_tt;
     if (p) {
@@ -127,8 +138,9 @@ static inline size_t auction_ws_layout(long long N, long long ld, int K, Auction
         p->win_shift = (int*)(base + o_ws);
         p->tkey = (int*)(base + o_tk);
         p->take = (int*)(base + o_take);
+        p->miss_run = (int*)(base + o_mr);
         p->tieprefix = (unsigned int*)(base + o_tp);
-        p->hist_cta = (unsigned int*)(base + o_hc);
+        p->hist_cta = (unsigned short*)(base + o_hc);
     }
     return off;
 }
@@ -145,11 +157,11 @@ __global__ void auction_init_kernel(AuctionPtrs p, long long ld, int K, const un
     }
     for (long long j = i; j < (long long)K * AUC_W + K + 2; j += stride) p.hist_g[j] = 0;
     for (long long j = i; j < K; j += stride) {
-        p.above_g[j] = 0;
         p.win_base[j] = 0;
         p.win_shift[j] = AUC_COLD_SHIFT;
         p.tkey[j] = -1;
         p.take[j] = 0;
+        p.miss_run[j] = 0;
     }
     if (i == 0) {
         AuctionState s;
@@ -179,10 +191,36 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+__device__ __forceinline__ __half2 u2h2(unsigned u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ unsigned h22u(__half2 h) { return *reinterpret_cast<unsigned*>(&h); }
+
+struct PassSmem {
+    __half* tile0;             // [2][K][J]
+    unsigned int* hist;        // [K][W/2] two 16-bit counters per word
+    unsigned int* above;       // [K]
+    unsigned int* tie_seen;    // [K]
+    int* r_take;               // [K]
+    int* r_base;               // [K]
+    unsigned short* r_T;       // [K] threshold value (fp16 bits)
+    unsigned short* r_lo;      // [K] lowest value of the window (fp16 bits)
+    unsigned char* r_shift;    // [K]
+    unsigned char* row_flag;   // [K] an owner entry ties with the threshold in this tile
+    unsigned int* colmax;      // [J] (bid << 16) | (0xffff - worker)
+    unsigned short* colcost;   // [J]
+    short* colown;             // [J]
+    unsigned char* colviol;    // [J]
+    unsigned int* wlist;       // [NW][LIST_CAP]
+};
+
+__device__ __forceinline__ void hist_add(unsigned int* hist, int w, int bin, unsigned int n = 1) {
+    atomicAdd(&hist[(w * AUC_W + bin) >> 1], n << ((bin & 1) * 16));
+}
+
 template <int J>
-__global__ void __launch_bounds__(AUC_THREADS, 1)
+__global__ void __launch_bounds__(AUC_THREADS, (J == 128 ? 2 : 1))
 auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int K, long long jpw, AuctionPtrs p) {
-    constexpr int CPL = J / 32;  // columns per lane
+    constexpr int CPL = J / 32;      // columns per lane
+    constexpr int NH2 = CPL / 2;     // half2 words per lane
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const AuctionState st = *p.st;
     if (st.mode == MODE_DONE) return;
@@ -190,52 +228,84 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
     const int ff = do_bid ? 0 : st.ff_pending;
     const int counter = st.counter;
     const __half eps = bits2h(st.eps_bits);
+    const unsigned int eps_bits = st.eps_bits;
     const bool retain = do_bid && counter >= 1 && counter < 100;   // :86 (index is set from round 1 on)
     const bool fallback = do_bid && counter > 1000;                // :88
 
     // ---- shared memory carve-up ----
-    __half* tile0 = (__half*)smem_raw;                       // [2][K][J]
-    size_t off = (size_t)2 * K * J * 2;
-    unsigned int* hist = (unsigned int*)(smem_raw + off);  off += (size_t)K * AUC_W * 4;
-    unsigned int* above = (unsigned int*)(smem_raw + off); off += (size_t)K * 4;
-    unsigned int* tie_seen = (unsigned int*)(smem_raw + off); off += (size_t)K * 4;
-    int* r_tkey = (int*)(smem_raw + off); off += (size_t)K * 4;
-    int* r_take = (int*)(smem_raw + off); off += (size_t)K * 4;
-    int* r_base = (int*)(smem_raw + off); off += (size_t)K * 4;
-    int* r_shift = (int*)(smem_raw + off); off += (size_t)K * 4;
-    unsigned short* colcost = (unsigned short*)(smem_raw + off); off += (size_t)J * 2;
-    short* colown = (short*)(smem_raw + off); off += (size_t)J * 2;
-    unsigned short* cand_bid = (unsigned short*)(smem_raw + off); off += (size_t)AUC_NW * J * 2;
-    short* cand_arg = (short*)(smem_raw + off); off += (size_t)AUC_NW * J * 2;
-    unsigned char* cand_viol = (unsigned char*)(smem_raw + off); off += (size_t)AUC_NW * J;
+    PassSmem sm;
+    {
+        unsigned char* q = smem_raw;
+        sm.tile0 = (__half*)q;               q += (size_t)2 * K * J * 2;
+        sm.hist = (unsigned int*)q;          q += (size_t)K * AUC_W * 2;
+        sm.above = (unsigned int*)q;         q += (size_t)K * 4;
+        sm.tie_seen = (unsigned int*)q;      q += (size_t)K * 4;
+        sm.r_take = (int*)q;                 q += (size_t)K * 4;
+        sm.r_base = (int*)q;                 q += (size_t)K * 4;
+        sm.colmax = (unsigned int*)q;        q += (size_t)J * 4;
+        sm.wlist = (unsigned int*)q;         q += (size_t)AUC_NW * AUC_LIST_CAP * 4;
+        sm.colcost = (unsigned short*)q;     q += (size_t)J * 2;
+        sm.colown = (short*)q;               q += (size_t)J * 2;
+        sm.r_T = (unsigned short*)q;         q += (size_t)K * 2;
+        sm.r_lo = (unsigned short*)q;        q += (size_t)K * 2;
+        sm.r_shift = (unsigned char*)q;      q += (size_t)K;
+        sm.row_flag = (unsigned char*)q;     q += (size_t)K;
+        sm.colviol = (unsigned char*)q;      q += (size_t)J;
+    }
     __shared__ unsigned int s_nwith, s_nviol;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned int lt = (1u << lane) - 1u;
     const int G = gridDim.x, b = blockIdx.x;
     const long long tiles_total = (N + J - 1) / J;
     const long long t_begin = tiles_total * b / G, t_end = tiles_total * (b + 1) / G;
+    unsigned int* my_list = sm.wlist + warp * AUC_LIST_CAP;
 
-    for (int i = tid; i < K * AUC_W; i += AUC_THREADS) hist[i] = 0;
+    for (int i = tid; i < K * AUC_W / 2; i += AUC_THREADS) sm.hist[i] = 0;
     for (int i = tid; i < K; i += AUC_THREADS) {
-        above[i] = 0;
-        tie_seen[i] = p.tieprefix[(size_t)b * K + i];
-        r_tkey[i] = p.tkey[i];
-        r_take[i] = p.take[i];
-        r_base[i] = p.win_base[i];
-        r_shift[i] = p.win_shift[i];
+        sm.above[i] = 0;
+        sm.tie_seen[i] = p.tieprefix[(size_t)b * K + i];
+        int tk = p.tkey[i];
+        sm.r_T[i] = (unsigned short)key2h((unsigned)(tk < 0 ? 0 : tk));
+        sm.r_take[i] = p.take[i];
+        int base = p.win_base[i];
+        sm.r_base[i] = base;
+        sm.r_lo[i] = (unsigned short)key2h((unsigned)base);
+        sm.r_shift[i] = (unsigned char)p.win_shift[i];
+        sm.row_flag[i] = 0;
     }
+    for (int i = tid; i < J; i += AUC_THREADS) { sm.colmax[i] = 0; sm.colviol[i] = 0; }
     if (tid == 0) { s_nwith = 0; s_nviol = 0; }
 
     auto issue_tile = [&](long long t, int buf) {
-        // K rows x (J*2) bytes, 16 B per cp.async
         constexpr int CHUNKS_PER_ROW = J * 2 / 16;
         const int total = K * CHUNKS_PER_ROW;
-        __half* dst = tile0 + (size_t)buf * K * J;
+        __half* dst = sm.tile0 + (size_t)buf * K * J;
         const __half* src = S + t * J;
         for (int c = tid; c < total; c += AUC_THREADS) {
             int row = c / CHUNKS_PER_ROW, ch = c % CHUNKS_PER_ROW;
             cp_async16(dst + (size_t)row * J + ch * 8, src + (size_t)row * ld + ch * 8);
         }
+    };
+
+    // turn a surviving (worker, column, value) into a bid on the column's packed maximum
+    auto process_bid = [&](unsigned int e) {
+        const int w = e >> 24, col = (e >> 16) & 0xff;
+        const __half v = bits2h(e & 0xffffu);
+        const int o = sm.colown[col];
+        const bool own = (o == w);
+        if (fallback && w == 0 && o < 0) return;                            // :89 overrides worker 0's own bid
+        unsigned int bid = h2bits(__hadd(__hsub(v, bits2h(sm.r_T[w])), eps));   // :76, two roundings
+        if (retain && own) bid = eps_bits;                                  // :87
+        if (!own) sm.colviol[col] = 1;                                      // fresh bid on a job the bidder does not own
+        atomicMax(&sm.colmax[col], (bid << 16) | (0xffffu - (unsigned)w));  // :104 highest bid, lowest worker on ties
+    };
+    // histogram a surviving next-round value
+    auto process_hist = [&](unsigned int e) {
+        const int w = e >> 16;
+        const int rel = (int)h2key(e & 0xffffu) - sm.r_base[w];
+        if (rel >= AUC_W) atomicAdd(&sm.above[w], 1u);
+        else hist_add(sm.hist, w, rel);
     };
 
     if (t_begin < t_end) issue_tile(t_begin, 0);
@@ -244,14 +314,15 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
 
     for (long long t = t_begin; t < t_end; ++t) {
         const int buf = (int)((t - t_begin) & 1);
-        const __half* tile = tile0 + (size_t)buf * K * J;
+        const __half* tile = sm.tile0 + (size_t)buf * K * J;
         const long long col0 = t * J;
-        // stage per-column state
+        const int ncols = (int)((N - col0) < J ? (N - col0) : J);   // valid columns of this tile
+        // ---- stage per-column state ----
         if (tid < J) {
             long long col = col0 + tid;
             unsigned short c = 0;
             short o = -1;
-            if (col < N) {
+            if (tid < ncols) {
                 __half ch = p.cost[col];
                 o = p.owner[col];
                 if (ff > 0 && o >= 0) {   // retain fast-forward: (99-c) rounds of cost += eps
@@ -260,124 +331,147 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
                 }
                 c = __half_as_ushort(ch);
             }
-            colcost[tid] = c;
-            colown[tid] = o;
+            sm.colcost[tid] = c;
+            sm.colown[tid] = o;
         }
         // prefetch the next tile into the other buffer (its last readers finished before the
         // barrier that closed the previous iteration)
         if (t + 1 < t_end) issue_tile(t + 1, buf ^ 1);
         cp_async_commit();
         cp_async_wait<1>();
-        __syncthreads();
+        __syncthreads();                                                     // S0: tile + column state visible
 
-        __half c_r[CPL];
-        short o_r[CPL];
-        bool valid[CPL];
+        __half2 c2[NH2];
 #pragma unroll
-        for (int i = 0; i < CPL; ++i) {
-            c_r[i] = __ushort_as_half(colcost[lane * CPL + i]);
-            o_r[i] = colown[lane * CPL + i];
-            valid[i] = (col0 + lane * CPL + i) < N;
-        }
+        for (int h = 0; h < NH2; ++h) c2[h] = u2h2(reinterpret_cast<const unsigned*>(sm.colcost)[lane * NH2 + h]);
 
         if (do_bid) {
-            // ---------------- phase 1: bids of this round ----------------
-            unsigned short best[CPL];
-            short arg[CPL];
-            bool viol[CPL];
-#pragma unroll
-            for (int i = 0; i < CPL; ++i) { best[i] = 0; arg[i] = -1; viol[i] = false; }
-            for (int w = warp; w < K; w += AUC_NW) {
-                const __half T = bits2h(key2h((unsigned)r_tkey[w]));
-                const unsigned int quota = (unsigned int)r_take[w];
-                const __half* row = tile + (size_t)w * J + lane * CPL;
-                __half v[CPL];
-                bool gt[CPL], eq[CPL], own[CPL];
-                unsigned int anyeq = 0;
-#pragma unroll
-                for (int i = 0; i < CPL; ++i) {
-                    __half s = row[i];
-                    own[i] = (o_r[i] == (short)w);
-                    v[i] = own[i] ? s : __hsub(s, c_r[i]);      // :119,:123
-                    gt[i] = valid[i] && __hgt(v[i], T);
-                    eq[i] = valid[i] && __heq(v[i], T);
-                    anyeq |= eq[i] ? 1u : 0u;
+            // ---------------- owner entries: one per job, handled by the job's column thread ----------------
+            if (tid < ncols) {
+                const int o = sm.colown[tid];
+                unsigned int init = 0;
+                if (o >= 0) {
+                    const __half s = tile[(size_t)o * J + tid];              // owner's value is S itself (:123)
+                    const __half T = bits2h(sm.r_T[o]);
+                    unsigned int bid = 0;
+                    if (__hgt(s, T)) bid = h2bits(__hadd(__hsub(s, T), eps));
+                    else if (__heq(s, T) && sm.r_take[o] > 0) sm.row_flag[o] = 1;   // tie: the row's warp ranks it
+                    if (retain) bid = eps_bits;                              // :87
+                    if (bid) init = (bid << 16) | (0xffffu - (unsigned)o);
+                } else if (fallback) {
+                    init = (eps_bits << 16) | 0xffffu;                       // :89 worker 0 takes never-bid jobs
                 }
-                bool sel[CPL];
+                if (init) atomicMax(&sm.colmax[tid], init);
+            }
+            __syncthreads();                                                 // S1: row flags visible
+
+            // ---------------- phase 1 sweep: filter, compact, bid ----------------
+            int wn = 0;
+            for (int w = warp; w < K; w += AUC_NW) {
+                if (wn > AUC_LIST_CAP - J) {                                 // flush so a whole row always fits
+                    __syncwarp();
+                    for (int i = lane; i < wn; i += 32) process_bid(my_list[i]);
+                    __syncwarp();
+                    wn = 0;
+                }
+                const unsigned int Tb = sm.r_T[w];
+                const __half Th = bits2h(Tb);
+                const __half2 T2 = __half2half2(Th);
+                const unsigned* row = reinterpret_cast<const unsigned*>(tile + (size_t)w * J) + lane * NH2;
+                const bool flagged = sm.row_flag[w] != 0;
+                unsigned int vraw[NH2], gem = 0, m[NH2];
+                if (!flagged) {
 #pragma unroll
-                for (int i = 0; i < CPL; ++i) sel[i] = false;
-                if (quota > 0 && __any_sync(0xffffffffu, anyeq)) {
+                    for (int h = 0; h < NH2; ++h) {
+                        __half2 v2 = __hsub2(u2h2(row[h]), c2[h]);           // S - cost, ownership ignored
+                        vraw[h] = h22u(v2);
+                        m[h] = __hge2_mask(v2, T2);
+                        gem |= m[h];
+                    }
+                } else {
+#pragma unroll
+                    for (int h = 0; h < NH2; ++h) {                          // exact values incl. owner entries
+                        unsigned int sr = row[h], cr = h22u(c2[h]);
+                        if (sm.colown[lane * CPL + 2 * h] == w) cr &= 0xffff0000u;
+                        if (sm.colown[lane * CPL + 2 * h + 1] == w) cr &= 0x0000ffffu;
+                        __half2 v2 = __hsub2(u2h2(sr), u2h2(cr));
+                        vraw[h] = h22u(v2);
+                        m[h] = __hge2_mask(v2, T2);
+                        gem |= m[h];
+                    }
+                }
+                if (!__any_sync(0xffffffffu, gem != 0)) continue;
+                // survivors: v >= T.  In the unflagged path owner entries belong to the column thread.
+                bool cand[CPL], eq[CPL];
+                unsigned int vb[CPL];
+                bool anyeq = false;
+#pragma unroll
+                for (int e = 0; e < CPL; ++e) {
+                    const unsigned int half_sel = (e & 1) * 16;
+                    vb[e] = (vraw[e >> 1] >> half_sel) & 0xffffu;
+                    cand[e] = ((m[e >> 1] >> half_sel) & 1u) != 0 && (lane * CPL + e) < ncols;
+                    if (cand[e] && !flagged && sm.colown[lane * CPL + e] == w) cand[e] = false;
+                    eq[e] = cand[e] && __heq(bits2h(vb[e]), Th);
+                    anyeq |= eq[e];
+                }
+                const int quota = sm.r_take[w];
+                if (__any_sync(0xffffffffu, anyeq)) {
                     // canonical tie rule: lowest job index first, globally (tieprefix + tiles so far)
                     unsigned int before = 0, total = 0, mine = 0;
-                    const unsigned int lt = (1u << lane) - 1u;
 #pragma unroll
-                    for (int i = 0; i < CPL; ++i) {
-                        unsigned int m = __ballot_sync(0xffffffffu, eq[i]);
-                        before += __popc(m & lt);
-                        total += __popc(m);
+                    for (int e = 0; e < CPL; ++e) {
+                        unsigned int mm = __ballot_sync(0xffffffffu, eq[e]);
+                        before += __popc(mm & lt);
+                        total += __popc(mm);
                     }
-                    unsigned int seen = tie_seen[w];
+                    const unsigned int seen = sm.tie_seen[w];
 #pragma unroll
-                    for (int i = 0; i < CPL; ++i) {
-                        if (eq[i]) {
-                            sel[i] = (seen + before + mine) < quota;
+                    for (int e = 0; e < CPL; ++e) {
+                        if (eq[e]) {
+                            if (!((long long)(seen + before + mine) < (long long)quota)) cand[e] = false;
                             mine++;
                         }
                     }
                     __syncwarp();
-                    if (lane == 0) tie_seen[w] = seen + total;
+                    if (lane == 0) sm.tie_seen[w] = seen + total;
+                    __syncwarp();
                 }
 #pragma unroll
-                for (int i = 0; i < CPL; ++i) {
-                    unsigned short bid = 0;
-                    if (gt[i] || sel[i]) {
-                        bid = __half_as_ushort(__hadd(__hsub(v[i], T), eps));   // :76, two roundings
-                        if (!own[i]) viol[i] = true;                            // fresh bid on a job not owned
-                    }
-                    if (retain && own[i]) bid = __half_as_ushort(eps);          // :87
-                    if (fallback && w == 0 && valid[i] && o_r[i] < 0) bid = __half_as_ushort(eps);  // :89
-                    // bids are >= 0: unsigned compare of the bit patterns == numeric compare
-                    if (bid > best[i]) { best[i] = bid; arg[i] = (short)w; }
+                for (int e = 0; e < CPL; ++e) {
+                    unsigned int mm = __ballot_sync(0xffffffffu, cand[e]);
+                    if (cand[e])
+                        my_list[wn + __popc(mm & lt)] = ((unsigned)w << 24) | ((unsigned)(lane * CPL + e) << 16) | vb[e];
+                    wn += __popc(mm);
                 }
             }
-#pragma unroll
-            for (int i = 0; i < CPL; ++i) {
-                cand_bid[warp * J + lane * CPL + i] = best[i];
-                cand_arg[warp * J + lane * CPL + i] = arg[i];
-                cand_viol[warp * J + lane * CPL + i] = viol[i] ? 1 : 0;
-            }
-            __syncthreads();
-            // ---------------- column max, first argmax (:104), cost/owner update (:118-123) ----------------
+            __syncwarp();
+            for (int i = lane; i < wn; i += 32) process_bid(my_list[i]);
+            __syncthreads();                                                 // S2: all bids in colmax
+
+            // ---------------- highest bid per job, cost/owner update (:104, :118-123) ----------------
             if (tid < J) {
-                unsigned short bb = 0;
-                short ba = -1;
-                bool vv = false;
-#pragma unroll 4
-                for (int q = 0; q < AUC_NW; ++q) {
-                    unsigned short cb = cand_bid[q * J + tid];
-                    short ca = cand_arg[q * J + tid];
-                    if (cb > bb || (cb == bb && cb != 0 && ca < ba)) { bb = cb; ba = ca; }
-                    vv |= cand_viol[q * J + tid] != 0;
-                }
-                long long col = col0 + tid;
-                bool has = false;
-                if (col < N) {
-                    short old_owner = colown[tid];
-                    if (bb != 0) {
+                const unsigned int pk = sm.colmax[tid];
+                bool has = false, vv = false;
+                if (tid < ncols) {
+                    const long long col = col0 + tid;
+                    const short old_owner = sm.colown[tid];
+                    vv = sm.colviol[tid] != 0;
+                    if (pk) {
                         has = true;
-                        __half nc = __hadd(__ushort_as_half(colcost[tid]), __ushort_as_half(bb));
-                        colcost[tid] = __half_as_ushort(nc);
-                        colown[tid] = ba;
+                        const short wnr = (short)(0xffffu - (pk & 0xffffu));
+                        const __half nc = __hadd(__ushort_as_half(sm.colcost[tid]), bits2h(pk >> 16));
+                        sm.colcost[tid] = __half_as_ushort(nc);
+                        sm.colown[tid] = wnr;
                         p.cost[col] = nc;
-                        p.owner[col] = ba;
+                        p.owner[col] = wnr;
                     } else {
-                        colown[tid] = -1;
+                        sm.colown[tid] = -1;
                         p.owner[col] = -1;
-                        if (old_owner >= 0) vv = true;   // an owned job lost its bidder
+                        if (old_owner >= 0) vv = true;                       // an owned job lost its bidder
                     }
-                } else {
-                    vv = false;
                 }
+                sm.colmax[tid] = 0;
+                sm.colviol[tid] = 0;
                 unsigned int mh = __ballot_sync(0xffffffffu, has);
                 unsigned int mv = __ballot_sync(0xffffffffu, vv);
                 if (lane == 0) {
@@ -385,61 +479,110 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
                     if (mv) atomicAdd(&s_nviol, __popc(mv));
                 }
             }
-            __syncthreads();
+            for (int i = tid; i < K; i += AUC_THREADS) sm.row_flag[i] = 0;
+            __syncthreads();                                                 // S4: new column state visible
 #pragma unroll
-            for (int i = 0; i < CPL; ++i) {
-                c_r[i] = __ushort_as_half(colcost[lane * CPL + i]);
-                o_r[i] = colown[lane * CPL + i];
-            }
+            for (int h = 0; h < NH2; ++h) c2[h] = u2h2(reinterpret_cast<const unsigned*>(sm.colcost)[lane * NH2 + h]);
         }
 
         // ---------------- phase 2: histogram of the values the next selection will see ----------------
-        for (int w = warp; w < K; w += AUC_NW) {
-            const int base = r_base[w], shift = r_shift[w];
-            const __half* row = tile + (size_t)w * J + lane * CPL;
-            unsigned int nabove = 0;
-#pragma unroll
-            for (int i = 0; i < CPL; ++i) {
-                __half s = row[i];
-                __half v = (o_r[i] == (short)w) ? s : __hsub(s, c_r[i]);
-                int key = (int)h2key(h2bits(v));
-                bool in = valid[i] && key >= base;
-                int bin = (key - base) >> shift;
-                bool ab = in && bin >= AUC_W;
-                bool hb = in && bin < AUC_W;
-                nabove += __popc(__ballot_sync(0xffffffffu, ab));
-                // coarse passes put nearly everything in one bin: aggregate when the warp agrees
-                unsigned int act = __ballot_sync(0xffffffffu, hb);
-                if (act) {
-                    int lead = __ffs(act) - 1;
-                    int lbin = __shfl_sync(0xffffffffu, bin, lead);
-                    unsigned int same = __ballot_sync(0xffffffffu, hb && bin == lbin);
-                    if (same == act) {
-                        if (lane == lead) atomicAdd(&hist[w * AUC_W + lbin], __popc(act));
-                    } else if (hb) {
-                        atomicAdd(&hist[w * AUC_W + bin], 1u);
+        // owner entries (value = S) of fine-window rows: one per job, by the column thread
+        if (tid < ncols) {
+            const int o = sm.colown[tid];
+            if (o >= 0 && sm.r_shift[o] == 0) {
+                const int rel = (int)h2key(h2bits(tile[(size_t)o * J + tid])) - sm.r_base[o];
+                if (rel >= AUC_W) atomicAdd(&sm.above[o], 1u);
+                else if (rel >= 0) hist_add(sm.hist, o, rel);
+            }
+        }
+        {
+            int wn = 0;
+            for (int w = warp; w < K; w += AUC_NW) {
+                const int shift = sm.r_shift[w];
+                const unsigned* row = reinterpret_cast<const unsigned*>(tile + (size_t)w * J) + lane * NH2;
+                if (shift == 0) {
+                    if (wn > AUC_LIST_CAP - J) {
+                        __syncwarp();
+                        for (int i = lane; i < wn; i += 32) process_hist(my_list[i]);
+                        __syncwarp();
+                        wn = 0;
                     }
+                    const __half2 lo2 = __half2half2(bits2h(sm.r_lo[w]));
+                    unsigned int vraw[NH2], m[NH2], gem = 0;
+#pragma unroll
+                    for (int h = 0; h < NH2; ++h) {
+                        __half2 v2 = __hsub2(u2h2(row[h]), c2[h]);
+                        vraw[h] = h22u(v2);
+                        m[h] = __hge2_mask(v2, lo2);
+                        gem |= m[h];
+                    }
+                    if (!__any_sync(0xffffffffu, gem != 0)) continue;
+#pragma unroll
+                    for (int e = 0; e < CPL; ++e) {
+                        const unsigned int half_sel = (e & 1) * 16;
+                        bool c = ((m[e >> 1] >> half_sel) & 1u) != 0 && (lane * CPL + e) < ncols;
+                        if (c && sm.colown[lane * CPL + e] == w) c = false;     // owner entry: done by the column thread
+                        unsigned int mm = __ballot_sync(0xffffffffu, c);
+                        if (c) my_list[wn + __popc(mm & lt)] = ((unsigned)w << 16) | ((vraw[e >> 1] >> half_sel) & 0xffffu);
+                        wn += __popc(mm);
+                    }
+                } else {
+                    // coarse / refining window (cold start, slide): exact values, warp-aggregated counting
+                    const int base = sm.r_base[w];
+                    unsigned int nabove = 0;
+#pragma unroll
+                    for (int e = 0; e < CPL; ++e) {
+                        const int cidx = lane * CPL + e;
+                        const unsigned int sr = (row[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+                        const __half v = (sm.colown[cidx] == w) ? bits2h(sr)
+                                                               : __hsub(bits2h(sr), __ushort_as_half(sm.colcost[cidx]));
+                        const int key = (int)h2key(h2bits(v));
+                        const bool in = cidx < ncols && key >= base;
+                        const int bin = (key - base) >> shift;
+                        const bool ab = in && bin >= AUC_W;
+                        const bool hb = in && bin < AUC_W;
+                        nabove += __popc(__ballot_sync(0xffffffffu, ab));
+                        unsigned int act = __ballot_sync(0xffffffffu, hb);
+                        if (act) {
+                            int lead = __ffs(act) - 1;
+                            int lbin = __shfl_sync(0xffffffffu, bin, lead);
+                            unsigned int same = __ballot_sync(0xffffffffu, hb && bin == lbin);
+                            if (same == act) {
+                                if (lane == lead) hist_add(sm.hist, w, lbin, __popc(act));
+                            } else if (hb) {
+                                hist_add(sm.hist, w, bin);
+                            }
+                        }
+                    }
+                    if (lane == 0 && nabove) atomicAdd(&sm.above[w], nabove);
                 }
             }
-            if (lane == 0 && nabove) above[w] += nabove;   // row w belongs to this warp only
+            __syncwarp();
+            for (int i = lane; i < wn; i += 32) process_hist(my_list[i]);
         }
-        __syncthreads();
+        __syncthreads();                                                     // S6: tile buffer + column state free
     }
     cp_async_wait<0>();
 
     // ---- publish: per-CTA dump (for the tie prefix) + merge of non-empty bins ----
-    unsigned int* dump = p.hist_cta + (size_t)b * K * AUC_W;
-    for (int i = tid; i < K * AUC_W; i += AUC_THREADS) {
-        unsigned int h = hist[i];
+    unsigned int* dump = reinterpret_cast<unsigned int*>(p.hist_cta + (size_t)b * K * AUC_W);
+    for (int i = tid; i < K * AUC_W / 2; i += AUC_THREADS) {
+        unsigned int h = sm.hist[i];
         dump[i] = h;
-        if (h) atomicAdd(&p.hist_g[i], h);
+        if (h & 0xffffu) atomicAdd(&p.hist_g[2 * i], h & 0xffffu);
+        if (h >> 16) atomicAdd(&p.hist_g[2 * i + 1], h >> 16);
     }
     for (int i = tid; i < K; i += AUC_THREADS)
-        if (above[i]) atomicAdd(&p.above_g[i], above[i]);
+        if (sm.above[i]) atomicAdd(&p.above_g[i], sm.above[i]);
     if (tid == 0 && do_bid) {
         if (s_nwith) atomicAdd(p.n_with, s_nwith);
         if (s_nviol) atomicAdd(p.n_viol, s_nviol);
     }
+}
+
+static inline size_t auction_pass_smem(int K, int J) {
+    return (size_t)2 * K * J * 2 + (size_t)K * AUC_W * 2 + (size_t)K * 16 + (size_t)J * 4 +
+           (size_t)AUC_NW * AUC_LIST_CAP * 4 + (size_t)J * 4 + (size_t)K * 4 + (size_t)K * 2 + (size_t)J + 64;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -518,6 +661,7 @@ auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
                 found_bin = __shfl_sync(0xffffffffu, found_bin, src);
                 g_above = __shfl_sync(0xffffffffu, g_above, src);
                 if (lane == 0) {
+                    p.miss_run[w] = 0;
                     if (shift == 0) {
                         p.tkey[w] = base + found_bin;
                         p.take[w] = (int)(jpw - (long long)g_above);
@@ -529,9 +673,20 @@ auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
                         atomicAdd(&s_unresolved, 1);
                     }
                 }
-            } else if (lane == 0) {   // window missed the threshold: restart coarse
-                p.win_base[w] = 0;
-                p.win_shift[w] = AUC_COLD_SHIFT;
+            } else if (lane == 0) {
+                // the window missed the threshold: slide one window up / down, restart coarse if that
+                // keeps failing (or if the window was a refinement, which cannot miss by construction)
+                const int run = p.miss_run[w];
+                const bool is_above = ab >= (unsigned long long)need;
+                int nb = is_above ? base + (AUC_W << shift) : base - (AUC_W << shift);
+                if (shift != 0 || run >= 2 || nb < AUC_MIN_KEY || nb > 65536 - AUC_W) {
+                    p.win_base[w] = 0;
+                    p.win_shift[w] = AUC_COLD_SHIFT;
+                    p.miss_run[w] = 0;
+                } else {
+                    p.win_base[w] = nb;
+                    p.miss_run[w] = run + 1;
+                }
                 p.tkey[w] = -1;
                 atomicAdd(&s_unresolved, 1);
                 if (shift == 0) atomicAdd(&s_miss, 1);
@@ -542,6 +697,7 @@ auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
             p.win_base[w] = 0;
             p.win_shift[w] = AUC_COLD_SHIFT;
             p.tkey[w] = -1;
+            p.miss_run[w] = 0;
         }
     }
     __syncthreads();
@@ -567,36 +723,44 @@ auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
 }
 
 // After a resolve that leaves every worker resolved: per-CTA exclusive prefix of the number of
-// values equal to the threshold (bin tkey-base of the per-CTA dumps), and the next prediction
-// window.  Grid = K CTAs.
-__global__ void __launch_bounds__(512, 1)
+// values equal to the threshold (bin tkey-base of the per-CTA dumps), and the window predicted for
+// the values after this round's cost update.  Grid = K CTAs.
+__global__ void __launch_bounds__(AUC_MAX_CTAS, 1)
 auction_tieprefix_kernel(AuctionPtrs p, int K, int G) {
     if (p.st->mode != MODE_BID) return;
     const int w = blockIdx.x, tid = threadIdx.x;
-    __shared__ unsigned int cnt[512];
+    __shared__ unsigned int cnt[AUC_MAX_CTAS];
     const int base = p.win_base[w];
-    const int bin = p.tkey[w] - base;   // shift is 0 when resolved
+    const int tk = p.tkey[w];
+    const int bin = tk - base;   // shift is 0 when resolved
     unsigned int c = 0;
     if (tid < G) c = p.hist_cta[((size_t)tid * K + w) * AUC_W + bin];
     cnt[tid] = c;
     __syncthreads();
-    // Hillis-Steele inclusive scan over <= 512 CTAs
-    for (int d = 1; d < 512; d <<= 1) {
+    for (int d = 1; d < AUC_MAX_CTAS; d <<= 1) {   // Hillis-Steele inclusive scan
         unsigned int v = (tid >= d) ? cnt[tid - d] : 0;
         __syncthreads();
         cnt[tid] += v;
         __syncthreads();
     }
     if (tid < G) p.tieprefix[(size_t)tid * K + w] = cnt[tid] - c;
-    if (tid == 511) p.tie_total[w] = cnt[511];
+    if (tid == AUC_MAX_CTAS - 1) p.tie_total[w] = cnt[AUC_MAX_CTAS - 1];
     __syncthreads();
     if (tid == 0) {
-        // prediction for the values after this round's cost update: thresholds only move down
-        int nb = p.tkey[w] - (AUC_W - AUC_WIN_ABOVE);
-        if (nb < 0) nb = 0;
-        if (nb > 65536 - AUC_W) nb = 65536 - AUC_W;
-        p.win_base[w] = nb;
-        p.win_shift[w] = 0;
+        // Every held job's cost rises by >= eps per round, so thresholds sink by about eps:
+        // window = [T - 2.4 eps, T + 0.4 eps], capped at 128 keys (coarser bins + a refine pass beyond).
+        const float T = __half2float(bits2h(key2h((unsigned)tk)));
+        const float e = __half2float(bits2h(p.st->eps_bits));
+        int lo = (int)h2key(h2bits(__float2half_rn(T - 2.4f * e)));
+        int hi = (int)h2key(h2bits(__float2half_rn(T + 0.4f * e)));
+        if (hi < tk + 2) hi = tk + 2;
+        if (lo > tk - 8) lo = tk - 8;
+        if (lo < AUC_MIN_KEY) lo = AUC_MIN_KEY;
+        int span = hi - lo + 1, shift = 0;
+        while ((span >> shift) > AUC_W) ++shift;
+        if (shift == 0 && lo > 65536 - AUC_W) lo = 65536 - AUC_W;
+        p.win_base[w] = lo;
+        p.win_shift[w] = shift;
     }
 }
 
@@ -635,9 +799,9 @@ static int auction_prepare(int64_t n, int64_t ld, int32_t k, void* workspace, si
     size_t need = auction_ws_layout(n, ld, k, &a->p, (char*)workspace);
     if (workspace_bytes < need) return fail(RQK_ERR_WORKSPACE, "%s: workspace %lld < %lld bytes", who, (long long)workspace_bytes, (long long)need);
     a->G = auction_grid(n, k);
+    if (a->G > AUC_MAX_CTAS) return fail(RQK_ERR_UNSUPPORTED, "%s: n=%lld jobs per GPU exceed the 66 M limit of this build", who, n);
     a->J = auction_tile_cols(k);
-    a->smem = (size_t)2 * k * a->J * 2 + (size_t)k * AUC_W * 4 + (size_t)k * 4 * 6 + (size_t)a->J * 4 +
-              (size_t)AUC_NW * a->J * 5 + 64;
+    a->smem = auction_pass_smem(k, a->J);
     return 0;
 }
 }  // namespace rqk
@@ -725,7 +889,7 @@ int rqk_auction_resolve(int64_t n, int64_t ld, int32_t k, int64_t n_global, void
     if (rc) return rc;
     cudaStream_t stream = (cudaStream_t)stream_;
     auction_resolve_kernel<<<1, 1024, 0, stream>>>(a.p, n_global, k, n_global / k);
-    auction_tieprefix_kernel<<<k, 512, 0, stream>>>(a.p, k, a.G);
+    auction_tieprefix_kernel<<<k, AUC_MAX_CTAS, 0, stream>>>(a.p, k, a.G);
     RQK_LAUNCH_OK();
     return 0;
 }
@@ -793,8 +957,8 @@ int rqk_auction(const void* scores_t, int64_t ld, int64_t n, int32_t k, const vo
     rqk_auction_info st;
     memset(&st, 0, sizeof(st));
     const int batch = 6;
-    // hard stop: the reference itself cannot exceed 1002 rounds; each round is <= 4 passes
-    for (int it = 0; it < 5000 && !st.done; it += batch) {
+    // hard stop: the reference itself cannot exceed 1002 rounds; each round is a handful of passes at most
+    for (int it = 0; it < 8000 && !st.done; it += batch) {
         for (int q = 0; q < batch; ++q) {
             if ((rc = rqk_auction_pass(scores_t, ld, n, k, n, workspace, workspace_bytes, stream_))) return rc;
             if ((rc = rqk_auction_resolve(n, ld, k, n, workspace, workspace_bytes, stream_))) return rc;

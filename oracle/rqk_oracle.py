@@ -68,10 +68,21 @@ def lib():
         for name in ("rqk_oracle_hsub", "rqk_oracle_hadd"):
             getattr(L, name).argtypes = [p, p, p, i64]
             getattr(L, name).restype = None
+        L.rqk_oracle_num_threads.restype = ctypes.c_int
+        L.rqk_oracle_set_threads.argtypes = [ctypes.c_int]
         L.rqk_oracle_eps.argtypes = [ctypes.c_uint16, ctypes.c_uint16]
         L.rqk_oracle_eps.restype = ctypes.c_uint16
         _lib = L
     return _lib
+
+
+def num_threads() -> int:
+    """Host threads the C auction uses (OpenMP over workers; results do not depend on it)."""
+    return int(lib().rqk_oracle_num_threads())
+
+
+def set_threads(n: int) -> None:
+    lib().rqk_oracle_set_threads(int(n))
 
 
 # --------------------------------------------------------------------------------------------

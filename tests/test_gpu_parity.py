@@ -1,0 +1,421 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs, against the fixtures recorded from the unmodified reference, and - at BASELINE sizes - through
+size-independent properties.  Needs a B200: `pytest -m gpu`.
+
+Tolerances (north-star): integer codes / counts bit-exact except vectors whose fp64 top-2 distance gap is
+below 1e-5 relative (count asserted small and reported); centroids within 1e-4 relative; the fp16 score
+matrix equal on >= 99.9 % of entries (the rest differ by one fp16 ulp at rounding boundaries)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import rqk_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+NEAR_TIE = 1e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from generative_ranking_recommender_b200 import _lib
+    _lib.require_device(0)          # loads librqk_sm100a.so and fails loudly on a non-sm_100 part
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def engine(dev):
+    from generative_ranking_recommender_b200 import engine as e
+    return e
+
+
+def _scores_to_device(s_bits, dev, engine):
+    k, n = s_bits.shape
+    st = torch.full((k, engine.pad_ld(n)), float("-inf"), dtype=torch.float16)
+    st[:, :n] = torch.from_numpy(np.ascontiguousarray(s_bits).view(np.float16))
+    return st.to(dev)
+
+
+def _mm(st, n):
+    from generative_ranking_recommender_b200.balancekmeans import _minmax_keys
+    return _minmax_keys(st[:, :n])
+
+
+# ------------------------------------------------------------------------------------------------
+# score pass
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,k,dim", [(1, 1, 32), (128, 16, 32), (300, 5, 64), (5000, 16, 64), (4097, 128, 512),
+                                     (3001, 256, 128), (20000, 128, 512), (9999, 256, 512), (777, 100, 96)])
+@pytest.mark.parametrize("simt", [False, True])
+def test_score_pass_matches_oracle(dev, engine, n, k, dim, simt):
+    rng = np.random.default_rng(n + k)
+    x = O.synth_mix(n, dim, seed=n, modes=max(8, k))
+    c = x[rng.choice(n, k, replace=(k > n))].copy()
+    c[k // 2:] += 0.01 * rng.standard_normal((k - k // 2, dim)).astype(np.float32)
+    xd, cd = torch.from_numpy(x).to(dev), torch.from_numpy(c).to(dev)
+    r = engine.score_pass(xd, cd, scores=True, argmin=True, best2=True, counts=True, dist=True, simt=simt)
+    d = O.pairwise_distance_full(x, c, 100000)
+    d64 = O.distance_exact64(x, c)
+    s = r.scores_t.cpu().numpy().view(np.uint16)
+    assert (s[:, n:] == 0xFC00).all(), "padding columns must hold -inf"
+    s_ref = O.score_matrix_half_t(d)
+    assert (s[:, :n] == s_ref).mean() >= 0.999
+    ulp_off = np.abs(s[:, :n].astype(np.int32) - s_ref.astype(np.int32))
+    zero = (O.h2f(s[:, :n]) == 0) | (O.h2f(s_ref) == 0)       # d == 0 vs cancellation noise (x is a centre)
+    assert ulp_off[~zero].max(initial=0) <= 1
+    dist = r.dist.cpu().numpy().astype(np.float64)
+    scale = (x.astype(np.float64) ** 2).sum(1)[:, None] + (c.astype(np.float64) ** 2).sum(1)[None, :]
+    assert (np.abs(dist ** 2 - d64 ** 2) <= 2e-5 * scale + 1e-12).all()
+    am = r.argmin.cpu().numpy()
+    near = O.top2_relative_gap(d64) < NEAR_TIE if k > 1 else np.zeros(n, bool)
+    bad = (am != np.argmin(d, axis=1)) & ~near
+    assert bad.sum() == 0, f"{bad.sum()} argmin mismatches outside near-ties ({near.sum()} near-ties)"
+    assert near.mean() < 0.01
+    assert np.array_equal(r.counts.cpu().numpy(), np.bincount(am, minlength=k))
+    keys = np.where(s[:, :n] == 0x8000, 0, s[:, :n]).astype(np.int64)
+    keys = np.where(keys & 0x8000, (~keys) & 0xFFFF, keys | 0x8000)
+    mm = r.minmax.cpu().numpy()
+    assert mm[0] == keys.max() and mm[1] == keys.min()
+    b2 = r.best2.cpu().numpy()
+    assert np.allclose(b2[:, 0], dist.min(1), rtol=1e-6, atol=1e-7)
+
+
+def test_score_pass_farthest_quirk(dev, engine):
+    """auction_lap_half with N < K returns argmin of the NEGATED distance (reference :24-26)."""
+    x = O.synth_mix(50, 64, seed=3)
+    c = O.synth_mix(64, 64, seed=4)
+    r = engine.score_pass(torch.from_numpy(x).to(dev), torch.from_numpy(c).to(dev), argmin=True, farthest=True)
+    want = O.auction_lap_half(-O.pairwise_distance_full(x, c)).assignment
+    assert (r.argmin.cpu().numpy() == want).mean() > 0.98
+
+
+def test_tensor_core_and_cuda_core_kernels_agree(dev, engine):
+    x = torch.from_numpy(O.synth_mix(30000, 512, seed=9)).to(dev)
+    c = x[:128].clone() * 1.01
+    a = engine.score_pass(x, c, scores=True, argmin=True)
+    b = engine.score_pass(x, c, scores=True, argmin=True, simt=True)
+    assert (a.scores_t == b.scores_t).float().mean() > 0.999
+    assert (a.argmin == b.argmin).float().mean() > 0.9995
+
+
+# ------------------------------------------------------------------------------------------------
+# balanced auction
+# ------------------------------------------------------------------------------------------------
+def test_auction_golden_vectors_from_reference(dev, engine, golden_dir):
+    g = np.load(os.path.join(golden_dir, "auction.npz"))
+    from generative_ranking_recommender_b200.balancekmeans import auction_lap_half
+    so = ao = 0
+    for (n, k), rounds in zip(g["shapes"], g["rounds"]):
+        sc = g["scores"][so:so + n * k].reshape(n, k)
+        ref = g["assign"][ao:ao + n]
+        so += n * k
+        ao += n
+        got = auction_lap_half(torch.from_numpy(sc).to(dev)).cpu().numpy()
+        assert np.array_equal(got, ref), (n, k)
+        if n >= k:
+            assert auction_lap_half.last_stats.rounds == rounds
+
+
+@pytest.mark.parametrize("n,k,dim", [(64, 4, 64), (130, 4, 64), (1000, 8, 64), (4096, 16, 64), (4100, 16, 64),
+                                     (6000, 32, 128), (20000, 128, 128), (20010, 128, 128), (12800, 256, 64),
+                                     (12900, 256, 64), (256, 256, 64), (300, 256, 64), (16384, 64, 64)])
+def test_auction_bit_exact_vs_oracle(dev, engine, n, k, dim):
+    """Identical fp16 matrix in -> identical assignment out, including the 1002-round fallback regime
+    (which the GPU reaches through the frozen-state fast-forward while the oracle simulates every round)."""
+    rng = np.random.default_rng(n)
+    x = O.synth_mix(n, dim, seed=n, modes=max(8, k))
+    c = x[rng.choice(n, k, replace=False)]
+    s = O.score_matrix_half_t(O.pairwise_distance_full(x, c, 100000))
+    ref = O.auction_lap_half_t(s)
+    st = _scores_to_device(s, dev, engine)
+    a, stats = engine.auction(st, n, _mm(st, n))
+    a = a.cpu().numpy().astype(np.int64)
+    assert np.array_equal(a, ref.assignment), f"{(a != ref.assignment).sum()} of {n} differ"
+    assert stats.rounds == ref.rounds
+    assert abs(stats.eps - ref.eps) == 0
+    if n % k:
+        assert stats.rounds == 1002 and stats.frozen_exit and stats.passes < 200
+        sizes = np.bincount(a, minlength=k)
+        assert sizes[0] == n // k + n % k and (sizes[1:] == n // k).all()
+    else:
+        assert (np.bincount(a, minlength=k) == n // k).all()
+
+
+def test_auction_heavy_ties(dev, engine):
+    """Few distinct fp16 values: the canonical lowest-job-index rule decides almost every round."""
+    rng = np.random.default_rng(5)
+    n, k = 5000, 16
+    vals = -(rng.integers(0, 12, size=(k, n)) * 0.25).astype(np.float16)
+    s = vals.view(np.uint16)
+    ref = O.auction_lap_half_t(s)
+    assert ref.ambiguous_rounds > 0
+    st = _scores_to_device(s, dev, engine)
+    a, stats = engine.auction(st, n, _mm(st, n))
+    assert np.array_equal(a.cpu().numpy().astype(np.int64), ref.assignment)
+    assert stats.rounds == ref.rounds
+
+
+def test_auction_constant_matrix(dev, engine):
+    n, k = 1024, 8
+    s = np.full((k, n), np.float16(-1.5)).view(np.uint16)
+    ref = O.auction_lap_half_t(s)
+    st = _scores_to_device(s, dev, engine)
+    a, stats = engine.auction(st, n, _mm(st, n))
+    assert np.array_equal(a.cpu().numpy().astype(np.int64), ref.assignment) and stats.rounds == ref.rounds
+
+
+@pytest.mark.parametrize("n,k,split", [(4100, 16, 2), (20010, 128, 3), (12900, 256, 2), (4096, 16, 4)])
+def test_sharded_auction_protocol_single_gpu_emulation(dev, engine, n, k, split):
+    """The multi-GPU protocol (jobs sharded over ranks; reduce block summed between pass and resolve; tie
+    totals gathered) driven for `split` virtual ranks in ONE process with the same C-ABI step functions.
+    Must equal the unsharded result bit for bit."""
+    rng = np.random.default_rng(n + split)
+    x = O.synth_mix(n, 64, seed=n, modes=max(8, k))
+    c = x[rng.choice(n, k, replace=False)]
+    s = O.score_matrix_half_t(O.pairwise_distance_full(x, c, 100000))
+    ref = O.auction_lap_half_t(s)
+    bounds = np.linspace(0, n, split + 1).astype(int)
+    bounds[1:-1] += rng.integers(-50, 50, split - 1)
+    full = _scores_to_device(s, dev, engine)
+    mm = _mm(full, n)
+    sess = []
+    for r in range(split):
+        lo, hi = bounds[r], bounds[r + 1]
+        st = _scores_to_device(s[:, lo:hi], dev, engine)
+        sess.append(engine.AuctionSession(st, hi - lo, n))
+        sess[-1].init(mm)
+    done = False
+    for _ in range(3000):
+        for q in sess:
+            q.do_pass()
+        total = sum(q.reduce_block.clone() for q in sess)
+        for q in sess:
+            q.reduce_block.copy_(total)
+            q.resolve()
+        tt = torch.stack([q.tie_total.clone() for q in sess])
+        for r, q in enumerate(sess):
+            q.tie_offset(tt[:r].sum(0, dtype=torch.int32) if r else None)
+        infos = [q.poll() for q in sess]
+        assert len({(i.done, i.counter, i.passes) for i in infos}) == 1, "ranks must stay in lock step"
+        if infos[0].done:
+            done = True
+            break
+    assert done
+    a = torch.cat([q.finalize() for q in sess]).cpu().numpy().astype(np.int64)
+    assert np.array_equal(a, ref.assignment)
+    assert infos[0].rounds == ref.rounds
+
+
+# ------------------------------------------------------------------------------------------------
+# centroid update, residual
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,k,dim", [(5000, 16, 64), (40001, 128, 512), (70000, 256, 512), (1000, 7, 36)])
+def test_centroid_update(dev, engine, n, k, dim):
+    x = O.synth_mix(n, dim, seed=3)
+    a = np.random.default_rng(1).integers(0, k, n).astype(np.int32)
+    a[a == 3] = 4                                                # cluster 3 empty
+    c0 = x[:k].copy()
+    xd, ad = torch.from_numpy(x).to(dev), torch.from_numpy(a).to(dev)
+    sums, counts = engine.centroid_accumulate(xd, ad, k)
+    sums2, _ = engine.centroid_accumulate(xd, ad.clone(), k)
+    assert torch.equal(sums, sums2), "the reduction must be deterministic"
+    assert np.array_equal(counts.cpu().numpy(), np.bincount(a, minlength=k))
+    cd = torch.from_numpy(c0).to(dev)
+    out, empty = engine.centroid_finalize(sums, counts, cd)
+    nz = np.bincount(a, minlength=k) > 0
+    ref64 = np.stack([x[a == i].astype(np.float64).mean(0) if nz[i] else c0[i] for i in range(k)])
+    got = cd.cpu().numpy()
+    assert np.abs(got - ref64).max() <= 1e-6 * np.abs(ref64).max()
+    assert np.array_equal(got[~nz], c0[~nz]) and empty.cpu().numpy()[3] == 1 and out[1].item() == 1
+    shift = np.sqrt(((ref64 - c0) ** 2).sum(1)).sum()
+    assert abs(out[0].item() - shift) <= 1e-5 * shift
+
+
+@pytest.mark.parametrize("n,dim,groups", [(3000, 64, [64]), (3000, 512, [512]), (1000, 96, [32, 64]),
+                                          (1000, 512, [128, 384]), (10, 512, [512])])
+def test_residual_normalise(dev, engine, n, dim, groups):
+    x = O.synth_mix(n, dim, seed=5)
+    c = x[:8].copy() * 0.9
+    ids = np.random.default_rng(2).integers(0, 8, n).astype(np.int32)
+    ref = O.residual_normalised(x, ids, c, groups)
+    xd = torch.from_numpy(x).to(dev)
+    got = engine.residual_normalise(xd, torch.from_numpy(ids).to(dev), torch.from_numpy(c).to(dev), groups)
+    assert np.abs(got.cpu().numpy() - ref).max() < 2e-7
+    engine.residual_normalise(xd, torch.from_numpy(ids).to(dev), torch.from_numpy(c).to(dev), groups, out=xd)
+    assert torch.equal(xd, got), "in-place residual must equal the out-of-place one"
+
+
+# ------------------------------------------------------------------------------------------------
+# encode / predict against the reference's own outputs
+# ------------------------------------------------------------------------------------------------
+def test_encode_matches_reference_fixture(dev, engine, golden_dir):
+    g = np.load(os.path.join(golden_dir, "encode.npz"))
+    x = O.synth_mix(int(g["n"]), int(g["dim"]), seed=int(g["seed"]), modes=int(g["modes"]))
+    centers = [g["c0"], g["c1"], g["c2"]]
+    cd = [torch.from_numpy(c).to(dev) for c in centers]
+    xd = torch.from_numpy(x).to(dev)
+    dim = int(g["dim"])
+    for mode, key in ((0, "train_ids"), (1, "predict_ids")):
+        ids = engine.encode(xd, cd, [int(v) for v in g["clusters"]], [dim], None, mode=mode).t().cpu().numpy()
+        ok = np.cumprod(ids == g[key], axis=1).astype(bool)       # a flip at level l excuses later levels
+        assert ok[:, 0].mean() >= 0.9998 and ok[:, 2].mean() >= 0.999, (mode, ok.mean(0))
+    assert (g["predict_ids"][:, 1] != g["train_ids"][:, 1]).any()   # the +10000 quirk is really exercised
+
+
+def test_predict_api_and_weights(dev, engine):
+    from generative_ranking_recommender_b200 import HierarchicalRQKMeans, HierarchicalRQKMeansConfig
+    n, dim = 4000, 64
+    x = O.synth_mix(n, dim, seed=8, modes=64)
+    cfg = HierarchicalRQKMeansConfig(layer_clusters=[8, 8, 16], need_clusters=[8, 8, 16], embedding_dim=dim,
+                                     group_dims=[16, 48], hierarchical_weights=[[1.0, 0.5], [0.7, 1.0], [1.0, 1.0]],
+                                     iter_limit=10)
+    np.random.seed(3)
+    torch.manual_seed(3)
+    m = HierarchicalRQKMeans(cfg, device=dev)
+    out = m.train(x, resume=False)
+    ids = np.column_stack([t.numpy() for t in out["cluster_ids"]])
+    assert ids.dtype == np.int64 and ids.shape == (n, 3) and not out["cluster_ids"][0].is_cuda
+    centers = [c.cpu().numpy() for c in out["cluster_centers"]]
+    chain = np.column_stack(O.encode_train_chain(x, centers, cfg.group_dims, cfg.hierarchical_weights))
+    ok = np.cumprod(ids == chain, axis=1).astype(bool)
+    assert ok[:, 0].mean() > 0.999 and ok[:, 2].mean() > 0.99
+    assert np.array_equal(m.encode_like_train(x), ids)
+    pred = m.predict(x)
+    want = O.predict_hierarchy(x, centers, cfg.need_clusters, cfg.group_dims, cfg.hierarchical_weights)
+    okp = np.cumprod(pred == want, axis=1).astype(bool)
+    assert pred.dtype == np.int64 and okp[:, 0].mean() > 0.999 and okp[:, 2].mean() > 0.98
+
+
+# ------------------------------------------------------------------------------------------------
+# fit: teacher-forced iteration, statistical end-to-end, checkpoint/resume
+# ------------------------------------------------------------------------------------------------
+def test_fit_iteration_teacher_forced_on_reference_stage(dev, engine, golden_dir):
+    g = np.load(os.path.join(golden_dir, "stage.npz"))
+    x = O.synth_mix(int(g["n"]), int(g["dim"]), seed=int(g["seed"]), modes=int(g["modes"]))
+    k = int(g["k"])
+    xd = torch.from_numpy(x).to(dev)
+    c0 = torch.from_numpy(g["c0"]).to(dev)
+    r = engine.score_pass(xd, c0, scores=True, argmin=True)
+    s = r.scores_t[:, :len(x)].cpu().numpy().view(np.uint16)
+    assert (s.T == g["s_bits"]).mean() >= 0.9995                  # vs the reference's own (-D).half()
+    # auction on the reference's fp16 matrix: equal to the canonical oracle, statistically equal to torch.topk's
+    st = _scores_to_device(np.ascontiguousarray(g["s_bits"].T), dev, engine)
+    a, stats = engine.auction(st, len(x), _mm(st, len(x)))
+    a = a.cpu().numpy().astype(np.int64)
+    ref = O.auction_lap_half_t(np.ascontiguousarray(g["s_bits"].T))
+    assert np.array_equal(a, ref.assignment) and abs(stats.rounds - int(g["rounds"])) <= 3
+    assert (a != g["assign"]).mean() < 0.05
+    # centroid update teacher-forced on the reference's assignment
+    sums, counts = engine.centroid_accumulate(xd, torch.from_numpy(g["assign"].astype(np.int32)).to(dev), k)
+    cd = c0.clone()
+    out, _ = engine.centroid_finalize(sums, counts, cd)
+    assert np.allclose(cd.cpu().numpy(), g["c1"], rtol=1e-4, atol=1e-6)
+    assert abs(out[0].item() - float(g["shift"])) <= 1e-5 * float(g["shift"])
+    cnt = engine.score_pass(xd, torch.from_numpy(g["c1"]).to(dev), argmin=True, counts=True)
+    assert (cnt.argmin.cpu().numpy() == g["argmin"]).mean() >= 0.9995
+    assert np.abs(cnt.counts.cpu().numpy() - g["counts"]).sum() <= 4
+
+
+def test_full_fit_statistics_overlap_reference(dev, engine, golden_dir):
+    from generative_ranking_recommender_b200 import HierarchicalRQKMeans, HierarchicalRQKMeansConfig
+    g = np.load(os.path.join(golden_dir, "fit_stats.npz"))
+    rows = g["rows"]
+    clusters = [int(c) for c in g["clusters"]]
+    x = O.synth_mix(int(g["n"]), int(g["dim"]), seed=int(g["data_seed"]), modes=int(g["modes"]))
+    dim, n = int(g["dim"]), float(g["n"])
+    mine = []
+    for seed in rows[:, 0]:
+        np.random.seed(int(seed))
+        torch.manual_seed(int(seed))
+        cfg = HierarchicalRQKMeansConfig(layer_clusters=clusters, need_clusters=clusters, embedding_dim=dim,
+                                         iter_limit=int(g["iter_limit"]))
+        m = HierarchicalRQKMeans(cfg, device=dev)
+        out = m.train(x, resume=False)
+        ids = np.column_stack([t.numpy() for t in out["cluster_ids"]])
+        st = O.collision_stats(ids)
+        mine.append([st["unique_ids"], st["colliding_ids"], st["songs_in_collision"], st["max_collision"]])
+        assert [len(s) for s in m.fit_stats] == [15, 15, 13]         # adaptive iteration budget (:288-366)
+    mine, ref = np.array(mine, float), rows[:, 1:5].astype(float)
+    assert abs(mine[:, 0].mean() - ref[:, 0].mean()) < 0.015 * n, (mine, ref)
+    assert 0.5 * ref[:, 1].min() <= mine[:, 1].mean() <= 2.0 * ref[:, 1].max()
+    assert mine[:, 3].max() <= 2 * ref[:, 3].max() + 2
+
+
+def test_fit_is_deterministic_and_seeded_like_the_reference(dev, engine):
+    from generative_ranking_recommender_b200.balancekmeans import KMeans
+    x = torch.from_numpy(O.synth_mix(6000, 64, seed=2, modes=64)).to(dev)
+    runs = []
+    for _ in range(2):
+        np.random.seed(11)
+        torch.manual_seed(11)
+        km = KMeans(n_clusters=16, device=dev, balanced=True)
+        km.fit_by_min_loss(x, target_nodes_num=10 ** 9, iter_limit=12, tqdm_flag=False)
+        runs.append(km.cluster_centers.clone())
+    assert torch.equal(runs[0], runs[1])
+    # the initial draw is the reference's: np.random.choice on the global legacy RNG
+    np.random.seed(11)
+    idx = np.random.choice(6000, 16, replace=False)
+    np.random.seed(11)
+    c0 = KMeans(n_clusters=16, device=dev).initialize(x)
+    assert torch.equal(c0, x[torch.from_numpy(idx).to(dev)])
+
+
+def test_checkpoint_resume(dev, engine, tmp_path):
+    from generative_ranking_recommender_b200 import HierarchicalRQKMeans, HierarchicalRQKMeansConfig
+    n, dim = 3000, 64
+    x = O.synth_mix(n, dim, seed=4, modes=32)
+    cfg = HierarchicalRQKMeansConfig(layer_clusters=[8, 8, 8], need_clusters=[8, 8, 8], embedding_dim=dim, iter_limit=10)
+    ck = str(tmp_path / "ck")
+    np.random.seed(5)
+    torch.manual_seed(5)
+    m = HierarchicalRQKMeans(cfg, checkpoint_dir=ck, device=dev)
+    full = m.train(x, resume=False)
+    assert m.get_training_status()["last_completed_layer"] == 2
+    os.remove(os.path.join(ck, "layer_2_checkpoint.pkl"))
+    m2 = HierarchicalRQKMeans(cfg, checkpoint_dir=ck, device=dev)
+    assert m2.get_training_status() == {"is_trained": False, "last_completed_layer": 1, "total_layers": 3,
+                                        "can_resume": True}
+    res = m2.train(x, resume=True)
+    for l in (0, 1):
+        assert torch.equal(res["cluster_ids"][l].cpu(), full["cluster_ids"][l])
+    assert len(res["cluster_ids"]) == 3 and res["cluster_ids"][2].shape == (n,)
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE sizes: size-independent properties
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,k", [(1000000, 128), (1048576, 128), (1000000, 256)])
+def test_full_size_iteration_properties(dev, engine, n, k):
+    g = torch.Generator(device=dev)
+    g.manual_seed(1)
+    x = torch.randn((n, 512), device=dev, generator=g)
+    c = x[torch.randperm(n, device=dev, generator=g)[:k]].clone()
+    sc = engine.score_pass(x, c, scores=True, argmin=True, counts=True, best2=True)
+    assert int(sc.counts.sum()) == n
+    # sampled rows against an fp64 recomputation
+    rows = torch.randint(0, n, (2000,), device=dev, generator=g)
+    d64 = torch.cdist(x[rows].double(), c.double())
+    s = sc.scores_t[:, rows].t().float()
+    assert ((-s - d64.float()).abs() <= d64.float() * 1.2e-3 + 1e-3).all()            # fp16 rounding of -d
+    gap = torch.sort(d64, dim=1).values
+    near = (gap[:, 1] - gap[:, 0]) / gap[:, 0] < NEAR_TIE
+    assert ((sc.argmin[rows].long() != d64.argmin(1)) & ~near).sum() == 0
+    a, stats = engine.auction(sc.scores_t, n, sc.minmax)
+    sizes = torch.bincount(a.long(), minlength=k)
+    jpw, rem = n // k, n % k
+    if rem:
+        assert stats.rounds == 1002 and stats.frozen_exit
+        assert sizes[0].item() == jpw + rem and (sizes[1:] == jpw).all()
+    else:
+        assert stats.rounds < 200 and (sizes == jpw).all()
+    a2, _ = engine.auction(sc.scores_t, n, sc.minmax)
+    assert torch.equal(a, a2), "the auction must be deterministic"
+    sums, counts = engine.centroid_accumulate(x, a, k)
+    assert torch.equal(counts, sizes)
+    # linearity: the K cluster sums add up to the column sums of X (fp32 tolerance)
+    tot = x.double().sum(0)
+    assert ((sums.double().sum(0) - tot).abs() <= 1e-3 * x.double().abs().sum(0) / n ** 0.5 + 1e-2).all()
