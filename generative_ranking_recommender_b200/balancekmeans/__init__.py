@@ -22,7 +22,7 @@ from typing import List, Optional
 import numpy as np
 import torch
 
-from .. import engine
+from .. import engine, sharding
 from .._lib import RqkError
 
 __all__ = ["KMeans", "auction_lap_half", "auction_lap_full", "pairwise_distance_full",
@@ -197,11 +197,9 @@ class KMeans(object):
             return engine.gather_rows(X, idx)
         # sharded: every rank drew the same indices; owners fill their rows, the rest stays zero
         out = torch.zeros((len(indices), X.shape[1]), dtype=torch.float32, device=X.device)
-        local = (indices >= row0) & (indices < row0 + X.shape[0])
-        if local.any():
-            pos = torch.from_numpy(np.nonzero(local)[0]).to(X.device)
-            idx = torch.from_numpy((indices[local] - row0).astype(np.int64)).to(X.device)
-            out[pos] = engine.gather_rows(X, idx)
+        pos, loc = sharding.owned_rows(indices, row0, X.shape[0])
+        if len(pos):
+            sharding.scatter_owned(out, pos, engine.gather_rows(X, torch.from_numpy(loc).to(X.device)))
         shard.all_reduce(out, "sum")          # exact: one non-zero contribution per row
         return out
 
@@ -216,8 +214,7 @@ class KMeans(object):
         if shard is None or not shard.active:
             return n_local, 0
         sizes = shard.all_gather(torch.tensor([n_local], dtype=torch.int64, device=_cuda_device(self.device)))
-        sizes = sizes.view(-1).tolist()
-        return int(sum(sizes)), int(sum(sizes[: shard.rank]))
+        return sharding.global_rows(sizes.view(-1).tolist(), shard.rank)
 
     # -- the fit loops ------------------------------------------------------------------------
     def _check_distance(self, distance, half):

@@ -14,18 +14,20 @@
 //
 // One PASS = every CTA streams its contiguous range of 128-job (K<=128) or 64-job tiles, all K
 // workers deep, through a double-buffered cp.async pipeline.  Per tile:
-//   phase 1 (BID)  A warp owns a worker row of the tile, so ties are met in job order.  The sweep is a
-//                  half2 FILTER: v = S - cost (ownership ignored: the owner's true value S is only
-//                  larger) compared with the worker's threshold T_w, the (N/K+1)-th largest value
-//                  (:66).  The ~1 % survivors are compacted into a per-warp list and turned into bids
-//                  ((v - T_w) + eps, :76) there; ties at T_w are taken lowest job index first up to
-//                  the worker's quota.  The one owner entry of every job is handled by the job's
-//                  column thread (retain hack :86-87, counter>1000 fallback :88-89).  The column max
-//                  with first-argmax (:104) is an atomicMax on (bid << 16 | ~worker) in shared memory;
-//                  then cost/owner update (:118-123).
-//   phase 2 (HIST) the NEXT round's values of the same tile (still in shared memory) are filtered
-//                  against a <=128-key window predicted just below each threshold and histogrammed
-//                  (16-bit packed counters), plus an "above the window" count.
+//   sweep    A warp owns a worker row of the tile, so ties are met in job order.  The sweep is a half2
+//            FILTER: v = S - cost (ownership ignored: the owner's true value S is only larger)
+//            against the low edge of the worker's histogram window, which lies below its threshold
+//            T_w, the (N/K+1)-th largest value (:66).  Because costs only grow, the survivors are a
+//            superset of BOTH this round's bidders (v >= T_w) and the next round's in-window values.
+//            The few-percent survivors go to lane-private 16-bit lists in shared memory.
+//   stage A  (BID) survivors with v >= T_w become bids ((v - T_w) + eps, :76); ties at T_w are taken
+//            lowest job index first up to the worker's quota.  The one owner entry of every job is
+//            handled by the job's column thread (retain hack :86-87, counter>1000 fallback :88-89).
+//            The column max with first-argmax (:104) is an atomicMax on (bid << 16 | ~worker) in
+//            shared memory; then cost/owner update (:118-123).
+//   stage B  (HIST) the same survivors, re-valued with the NEW costs, are histogrammed into the
+//            <=128-key window predicted just below each threshold (16-bit packed counters), plus an
+//            "above the window" count: the input of the next round's threshold selection.
 // A 1-CTA RESOLVE kernel turns the merged histograms into exact thresholds (16-bit radix select:
 // window hit -> exact; miss -> slide; cold start -> coarse 128-bin pass over all keys, then refine),
 // and a K-CTA kernel prefix-sums per-CTA tie counts so the canonical tie rule is global.  So a
@@ -53,7 +55,7 @@ constexpr int AUC_MAX_CTAS = 1024; // tie-prefix kernel limit
 constexpr int AUC_MAX_JOBS_PER_CTA = 65024;   // 16-bit per-CTA counters
 constexpr int AUC_MIN_TILES_PER_CTA = 2;
 constexpr int AUC_COLD_SHIFT = 9;  // 128 bins x 512 keys cover all 65536 fp16 keys
-constexpr int AUC_LIST_CAP = 160;  // per-warp survivor list entries (a full 128-job row always fits after a flush)
+constexpr int AUC_CAPL = 10;       // lane-private survivor slots per tile (overflow -> direct path for that tile)
 constexpr int AUC_MIN_KEY = 0x0400; // key of the most negative finite half: fine windows never reach -inf
 
 enum { MODE_HIST = 0, MODE_BID = 1, MODE_DONE = 2 };
@@ -70,8 +72,9 @@ struct AuctionState {
     int window_misses;
     unsigned int eps_bits;
     unsigned int smax_bits, smin_bits;
+    int need_sample;    // windows are cold: estimate them from a sample before the next pass
     int error;
-    int pad_[16];
+    int pad_[15];
 };
 
 struct AuctionPtrs {
@@ -167,6 +170,7 @@ __global__ void auction_init_kernel(AuctionPtrs p, long long ld, int K, const un
         AuctionState s;
         memset(&s, 0, sizeof(s));
         s.mode = MODE_HIST;
+        s.need_sample = 1;
         unsigned int smax = key2h(minmax_keys[0]), smin = key2h(minmax_keys[1]);
         // eps = (max - min) / 50 in fp16 (two roundings), floored at half(1e-4)  (:33-34)
         __half range = __hsub(bits2h(smax), bits2h(smin));
@@ -201,21 +205,25 @@ struct PassSmem {
     unsigned int* tie_seen;    // [K]
     int* r_take;               // [K]
     int* r_base;               // [K]
-    unsigned short* r_T;       // [K] threshold value (fp16 bits)
-    unsigned short* r_lo;      // [K] lowest value of the window (fp16 bits)
+    unsigned int* r_T2;        // [K] threshold as a duplicated half2
+    unsigned int* r_lo2;       // [K] sweep filter as a duplicated half2 (window low value; T for coarse rows)
     unsigned char* r_shift;    // [K]
     unsigned char* row_flag;   // [K] an owner entry ties with the threshold in this tile
     unsigned int* colmax;      // [J] (bid << 16) | (0xffff - worker)
     unsigned short* colcost;   // [J]
     short* colown;             // [J]
     unsigned char* colviol;    // [J]
-    unsigned int* wlist;       // [NW][LIST_CAP]
+    unsigned short* llist;     // [CAPL][THREADS] lane-private survivors: (worker << 8) | (column << 1) | rejected_tie
 };
 
 __device__ __forceinline__ void hist_add(unsigned int* hist, int w, int bin, unsigned int n = 1) {
     atomicAdd(&hist[(w * AUC_W + bin) >> 1], n << ((bin & 1) * 16));
 }
 
+// One pass.  Per tile: ONE half2 sweep filters S - cost_old against the low edge of each worker's
+// window (a superset of both the bidders, v >= T, and of the next round's in-window values, because
+// costs only grow); survivors go to lane-private lists and are visited twice: stage A turns them
+// into bids with the old costs, stage B histograms them with the new costs.
 template <int J>
 __global__ void __launch_bounds__(AUC_THREADS, (J == 128 ? 2 : 1))
 auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int K, long long jpw, AuctionPtrs p) {
@@ -242,40 +250,44 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
         sm.tie_seen = (unsigned int*)q;      q += (size_t)K * 4;
         sm.r_take = (int*)q;                 q += (size_t)K * 4;
         sm.r_base = (int*)q;                 q += (size_t)K * 4;
+        sm.r_T2 = (unsigned int*)q;          q += (size_t)K * 4;
+        sm.r_lo2 = (unsigned int*)q;         q += (size_t)K * 4;
         sm.colmax = (unsigned int*)q;        q += (size_t)J * 4;
-        sm.wlist = (unsigned int*)q;         q += (size_t)AUC_NW * AUC_LIST_CAP * 4;
+        sm.llist = (unsigned short*)q;       q += (size_t)AUC_CAPL * AUC_THREADS * 2;
         sm.colcost = (unsigned short*)q;     q += (size_t)J * 2;
         sm.colown = (short*)q;               q += (size_t)J * 2;
-        sm.r_T = (unsigned short*)q;         q += (size_t)K * 2;
-        sm.r_lo = (unsigned short*)q;        q += (size_t)K * 2;
         sm.r_shift = (unsigned char*)q;      q += (size_t)K;
         sm.row_flag = (unsigned char*)q;     q += (size_t)K;
         sm.colviol = (unsigned char*)q;      q += (size_t)J;
     }
-    __shared__ unsigned int s_nwith, s_nviol;
+    __shared__ unsigned int s_nwith, s_nviol, s_direct;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned int lt = (1u << lane) - 1u;
     const int G = gridDim.x, b = blockIdx.x;
     const long long tiles_total = (N + J - 1) / J;
     const long long t_begin = tiles_total * b / G, t_end = tiles_total * (b + 1) / G;
-    unsigned int* my_list = sm.wlist + warp * AUC_LIST_CAP;
+    unsigned short* my_list = sm.llist + tid;           // slot i at my_list[i * AUC_THREADS]
 
     for (int i = tid; i < K * AUC_W / 2; i += AUC_THREADS) sm.hist[i] = 0;
     for (int i = tid; i < K; i += AUC_THREADS) {
         sm.above[i] = 0;
         sm.tie_seen[i] = p.tieprefix[(size_t)b * K + i];
-        int tk = p.tkey[i];
-        sm.r_T[i] = (unsigned short)key2h((unsigned)(tk < 0 ? 0 : tk));
+        const int tk = p.tkey[i];
+        const unsigned int Tb = key2h((unsigned)(tk < 0 ? 0 : tk));
+        sm.r_T2[i] = Tb | (Tb << 16);
         sm.r_take[i] = p.take[i];
-        int base = p.win_base[i];
+        const int base = p.win_base[i], shift = p.win_shift[i];
         sm.r_base[i] = base;
-        sm.r_lo[i] = (unsigned short)key2h((unsigned)base);
-        sm.r_shift[i] = (unsigned char)p.win_shift[i];
+        sm.r_shift[i] = (unsigned char)shift;
+        // fine rows are filtered at the window's low edge; coarse rows (cold start, refinement) are
+        // histogrammed by the direct path, so their sweep only has to find bidders
+        const unsigned int lob = (shift == 0) ? key2h((unsigned)base) : (do_bid ? Tb : 0x7c00u /* +inf: nothing */);
+        sm.r_lo2[i] = lob | (lob << 16);
         sm.row_flag[i] = 0;
     }
     for (int i = tid; i < J; i += AUC_THREADS) { sm.colmax[i] = 0; sm.colviol[i] = 0; }
-    if (tid == 0) { s_nwith = 0; s_nviol = 0; }
+    if (tid == 0) { s_nwith = 0; s_nviol = 0; s_direct = 0; }
 
     auto issue_tile = [&](long long t, int buf) {
         constexpr int CHUNKS_PER_ROW = J * 2 / 16;
@@ -286,26 +298,6 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
             int row = c / CHUNKS_PER_ROW, ch = c % CHUNKS_PER_ROW;
             cp_async16(dst + (size_t)row * J + ch * 8, src + (size_t)row * ld + ch * 8);
         }
-    };
-
-    // turn a surviving (worker, column, value) into a bid on the column's packed maximum
-    auto process_bid = [&](unsigned int e) {
-        const int w = e >> 24, col = (e >> 16) & 0xff;
-        const __half v = bits2h(e & 0xffffu);
-        const int o = sm.colown[col];
-        const bool own = (o == w);
-        if (fallback && w == 0 && o < 0) return;                            // :89 overrides worker 0's own bid
-        unsigned int bid = h2bits(__hadd(__hsub(v, bits2h(sm.r_T[w])), eps));   // :76, two roundings
-        if (retain && own) bid = eps_bits;                                  // :87
-        if (!own) sm.colviol[col] = 1;                                      // fresh bid on a job the bidder does not own
-        atomicMax(&sm.colmax[col], (bid << 16) | (0xffffu - (unsigned)w));  // :104 highest bid, lowest worker on ties
-    };
-    // histogram a surviving next-round value
-    auto process_hist = [&](unsigned int e) {
-        const int w = e >> 16;
-        const int rel = (int)h2key(e & 0xffffu) - sm.r_base[w];
-        if (rel >= AUC_W) atomicAdd(&sm.above[w], 1u);
-        else hist_add(sm.hist, w, rel);
     };
 
     if (t_begin < t_end) issue_tile(t_begin, 0);
@@ -352,10 +344,10 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
                 unsigned int init = 0;
                 if (o >= 0) {
                     const __half s = tile[(size_t)o * J + tid];              // owner's value is S itself (:123)
-                    const __half T = bits2h(sm.r_T[o]);
+                    const __half T = bits2h(sm.r_T2[o] & 0xffffu);
                     unsigned int bid = 0;
                     if (__hgt(s, T)) bid = h2bits(__hadd(__hsub(s, T), eps));
-                    else if (__heq(s, T) && sm.r_take[o] > 0) sm.row_flag[o] = 1;   // tie: the row's warp ranks it
+                    else if (__heq(s, T)) sm.row_flag[o] = 1;                // tie: the row's warp ranks it exactly
                     if (retain) bid = eps_bits;                              // :87
                     if (bid) init = (bid << 16) | (0xffffu - (unsigned)o);
                 } else if (fallback) {
@@ -364,71 +356,58 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
                 if (init) atomicMax(&sm.colmax[tid], init);
             }
             __syncthreads();                                                 // S1: row flags visible
+        }
 
-            // ---------------- phase 1 sweep: filter, compact, bid ----------------
-            int wn = 0;
-            for (int w = warp; w < K; w += AUC_NW) {
-                if (wn > AUC_LIST_CAP - J) {                                 // flush so a whole row always fits
-                    __syncwarp();
-                    for (int i = lane; i < wn; i += 32) process_bid(my_list[i]);
-                    __syncwarp();
-                    wn = 0;
-                }
-                const unsigned int Tb = sm.r_T[w];
-                const __half Th = bits2h(Tb);
-                const __half2 T2 = __half2half2(Th);
-                const unsigned* row = reinterpret_cast<const unsigned*>(tile + (size_t)w * J) + lane * NH2;
-                const bool flagged = sm.row_flag[w] != 0;
-                unsigned int vraw[NH2], gem = 0, m[NH2];
-                if (!flagged) {
+        // ---------------- the sweep: filter S - cost against the window's low edge, compact ----------------
+        int cnt = 0;
+        for (int w = warp; w < K; w += AUC_NW) {
+            const __half2 lo2 = u2h2(sm.r_lo2[w]);
+            const unsigned* row = reinterpret_cast<const unsigned*>(tile + (size_t)w * J) + lane * NH2;
+            const bool flagged = do_bid && sm.row_flag[w] != 0;
+            __half2 v2[NH2];
+            unsigned int m[NH2];
+            if (!flagged) {
 #pragma unroll
-                    for (int h = 0; h < NH2; ++h) {
-                        __half2 v2 = __hsub2(u2h2(row[h]), c2[h]);           // S - cost, ownership ignored
-                        vraw[h] = h22u(v2);
-                        m[h] = __hge2_mask(v2, T2);
-                        gem |= m[h];
-                    }
-                } else {
-#pragma unroll
-                    for (int h = 0; h < NH2; ++h) {                          // exact values incl. owner entries
-                        unsigned int sr = row[h], cr = h22u(c2[h]);
-                        if (sm.colown[lane * CPL + 2 * h] == w) cr &= 0xffff0000u;
-                        if (sm.colown[lane * CPL + 2 * h + 1] == w) cr &= 0x0000ffffu;
-                        __half2 v2 = __hsub2(u2h2(sr), u2h2(cr));
-                        vraw[h] = h22u(v2);
-                        m[h] = __hge2_mask(v2, T2);
-                        gem |= m[h];
-                    }
+                for (int h = 0; h < NH2; ++h) {
+                    v2[h] = __hsub2(u2h2(row[h]), c2[h]);                    // ownership ignored: the owner's S is only larger
+                    m[h] = __hge2_mask(v2[h], lo2);
                 }
-                if (!__any_sync(0xffffffffu, gem != 0)) continue;
-                // survivors: v >= T.  In the unflagged path owner entries belong to the column thread.
-                bool cand[CPL], eq[CPL];
-                unsigned int vb[CPL];
-                bool anyeq = false;
+            } else {
 #pragma unroll
-                for (int e = 0; e < CPL; ++e) {
-                    const unsigned int half_sel = (e & 1) * 16;
-                    vb[e] = (vraw[e >> 1] >> half_sel) & 0xffffu;
-                    cand[e] = ((m[e >> 1] >> half_sel) & 1u) != 0 && (lane * CPL + e) < ncols;
-                    if (cand[e] && !flagged && sm.colown[lane * CPL + e] == w) cand[e] = false;
-                    eq[e] = cand[e] && __heq(bits2h(vb[e]), Th);
-                    anyeq |= eq[e];
+                for (int h = 0; h < NH2; ++h) {                              // exact values incl. owner entries
+                    unsigned int cr = h22u(c2[h]);
+                    if (sm.colown[lane * CPL + 2 * h] == w) cr &= 0xffff0000u;
+                    if (sm.colown[lane * CPL + 2 * h + 1] == w) cr &= 0x0000ffffu;
+                    v2[h] = __hsub2(u2h2(row[h]), u2h2(cr));
+                    m[h] = __hge2_mask(v2[h], lo2);
                 }
-                const int quota = sm.r_take[w];
-                if (__any_sync(0xffffffffu, anyeq)) {
-                    // canonical tie rule: lowest job index first, globally (tieprefix + tiles so far)
+            }
+            unsigned int rej = 0;                                            // bit e: tie at T_w that gets no bid
+            if (do_bid) {
+                const __half2 T2 = u2h2(sm.r_T2[w]);
+                unsigned int anye = 0, em[NH2];
+#pragma unroll
+                for (int h = 0; h < NH2; ++h) { em[h] = __heq2_mask(v2[h], T2); anye |= em[h]; }
+                if (__any_sync(0xffffffffu, anye != 0)) {
+                    // canonical tie rule: lowest job index first, globally (tieprefix + tiles so far).
+                    // In unflagged rows owner entries cannot tie (the column thread would have flagged the row).
+                    bool eq[CPL];
                     unsigned int before = 0, total = 0, mine = 0;
 #pragma unroll
                     for (int e = 0; e < CPL; ++e) {
+                        const int cidx = lane * CPL + e;
+                        eq[e] = ((em[e >> 1] >> ((e & 1) * 16)) & 1u) != 0 && cidx < ncols &&
+                                (flagged || sm.colown[cidx] != w);
                         unsigned int mm = __ballot_sync(0xffffffffu, eq[e]);
                         before += __popc(mm & lt);
                         total += __popc(mm);
                     }
                     const unsigned int seen = sm.tie_seen[w];
+                    const long long quota = sm.r_take[w];
 #pragma unroll
                     for (int e = 0; e < CPL; ++e) {
                         if (eq[e]) {
-                            if (!((long long)(seen + before + mine) < (long long)quota)) cand[e] = false;
+                            if (!((long long)(seen + before + mine) < quota)) rej |= 1u << e;
                             mine++;
                         }
                     }
@@ -436,16 +415,75 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
                     if (lane == 0) sm.tie_seen[w] = seen + total;
                     __syncwarp();
                 }
+            }
 #pragma unroll
-                for (int e = 0; e < CPL; ++e) {
-                    unsigned int mm = __ballot_sync(0xffffffffu, cand[e]);
-                    if (cand[e])
-                        my_list[wn + __popc(mm & lt)] = ((unsigned)w << 24) | ((unsigned)(lane * CPL + e) << 16) | vb[e];
-                    wn += __popc(mm);
+            for (int e = 0; e < CPL; ++e) {
+                if ((m[e >> 1] >> ((e & 1) * 16)) & 1u) {
+                    const unsigned int entry = ((unsigned)w << 8) | ((unsigned)(lane * CPL + e) << 1) | ((rej >> e) & 1u);
+                    if (cnt < AUC_CAPL) {
+                        my_list[cnt * AUC_THREADS] = (unsigned short)entry;
+                        ++cnt;
+                    } else {
+                        cnt = AUC_CAPL + 1;                                  // overflow: handled by the direct path
+                    }
                 }
             }
-            __syncwarp();
-            for (int i = lane; i < wn; i += 32) process_bid(my_list[i]);
+        }
+        if (cnt > AUC_CAPL) s_direct = 1;
+        if (do_bid) {
+            __syncthreads();                                                 // S1b: overflow flag visible
+            const bool direct = s_direct != 0;
+            // ---------------- stage A: survivors -> bids (old costs / owners) ----------------
+            auto bid_one = [&](int w, int col, bool rejected, bool flagged_row) {
+                const int o = sm.colown[col];
+                const bool own = (o == w);
+                if (own && !flagged_row) return;                             // the column thread did it
+                const __half s = tile[(size_t)w * J + col];
+                const __half v = own ? s : __hsub(s, __ushort_as_half(sm.colcost[col]));
+                const __half T = bits2h(sm.r_T2[w] & 0xffffu);
+                if (!(__hgt(v, T) || (__heq(v, T) && !rejected))) return;    // a histogram-only survivor
+                if (fallback && w == 0 && o < 0) return;                     // :89 overrides worker 0's own bid
+                unsigned int bid = h2bits(__hadd(__hsub(v, T), eps));        // :76, two roundings
+                if (retain && own) bid = eps_bits;                           // :87
+                if (!own) sm.colviol[col] = 1;                               // fresh bid on a job the bidder does not own
+                atomicMax(&sm.colmax[col], (bid << 16) | (0xffffu - (unsigned)w));   // :104
+            };
+            if (!direct) {
+                const int n = cnt;
+                for (int i = 0; i < n; ++i) {
+                    const unsigned int e = my_list[i * AUC_THREADS];
+                    bid_one(e >> 8, (e >> 1) & 127, (e & 1u) != 0, sm.row_flag[e >> 8] != 0);
+                }
+            } else {
+                // a lane's list overflowed (degenerate / tie-heavy data): redo the tile without lists
+                for (int w = warp; w < K; w += AUC_NW) {
+                    const bool flagged = sm.row_flag[w] != 0;
+                    const __half T = bits2h(sm.r_T2[w] & 0xffffu);
+                    bool eq[CPL];
+                    unsigned int before = 0, total = 0, mine = 0;
+#pragma unroll
+                    for (int e = 0; e < CPL; ++e) {
+                        const int cidx = lane * CPL + e;
+                        const bool own = sm.colown[cidx] == w;
+                        const __half s = tile[(size_t)w * J + cidx];
+                        const __half v = own ? s : __hsub(s, __ushort_as_half(sm.colcost[cidx]));
+                        eq[e] = cidx < ncols && __heq(v, T) && (flagged || !own);
+                        unsigned int mm = __ballot_sync(0xffffffffu, eq[e]);
+                        before += __popc(mm & lt);
+                        total += __popc(mm);
+                    }
+                    // this row's ties were already ranked by the sweep: undo and redo from the tile's start state
+                    const unsigned int seen = sm.tie_seen[w] - total;
+                    const long long quota = sm.r_take[w];
+#pragma unroll
+                    for (int e = 0; e < CPL; ++e) {
+                        const int cidx = lane * CPL + e;
+                        bool rejected = false;
+                        if (eq[e]) { rejected = !((long long)(seen + before + mine) < quota); mine++; }
+                        if (cidx < ncols) bid_one(w, cidx, rejected, flagged);
+                    }
+                }
+            }
             __syncthreads();                                                 // S2: all bids in colmax
 
             // ---------------- highest bid per job, cost/owner update (:104, :118-123) ----------------
@@ -480,14 +518,13 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
                 }
             }
             for (int i = tid; i < K; i += AUC_THREADS) sm.row_flag[i] = 0;
-            __syncthreads();                                                 // S4: new column state visible
-#pragma unroll
-            for (int h = 0; h < NH2; ++h) c2[h] = u2h2(reinterpret_cast<const unsigned*>(sm.colcost)[lane * NH2 + h]);
         }
+        __syncthreads();                                                     // S4: new column state + overflow flag visible
+        const bool direct = s_direct != 0;
 
-        // ---------------- phase 2: histogram of the values the next selection will see ----------------
+        // ---------------- stage B: histogram of the values the next selection will see ----------------
         // owner entries (value = S) of fine-window rows: one per job, by the column thread
-        if (tid < ncols) {
+        if (tid < ncols && !direct) {
             const int o = sm.colown[tid];
             if (o >= 0 && sm.r_shift[o] == 0) {
                 const int rel = (int)h2key(h2bits(tile[(size_t)o * J + tid])) - sm.r_base[o];
@@ -495,72 +532,53 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
                 else if (rel >= 0) hist_add(sm.hist, o, rel);
             }
         }
-        {
-            int wn = 0;
-            for (int w = warp; w < K; w += AUC_NW) {
-                const int shift = sm.r_shift[w];
-                const unsigned* row = reinterpret_cast<const unsigned*>(tile + (size_t)w * J) + lane * NH2;
-                if (shift == 0) {
-                    if (wn > AUC_LIST_CAP - J) {
-                        __syncwarp();
-                        for (int i = lane; i < wn; i += 32) process_hist(my_list[i]);
-                        __syncwarp();
-                        wn = 0;
-                    }
-                    const __half2 lo2 = __half2half2(bits2h(sm.r_lo[w]));
-                    unsigned int vraw[NH2], m[NH2], gem = 0;
+        if (!direct) {
+            const int n = cnt;
+            for (int i = 0; i < n; ++i) {
+                const unsigned int e = my_list[i * AUC_THREADS];
+                const int w = e >> 8, col = (e >> 1) & 127;
+                if (sm.r_shift[w] != 0 || sm.colown[col] == w) continue;     // coarse row / owner entry: done elsewhere
+                const __half v = __hsub(tile[(size_t)w * J + col], __ushort_as_half(sm.colcost[col]));
+                const int rel = (int)h2key(h2bits(v)) - sm.r_base[w];
+                if (rel >= AUC_W) atomicAdd(&sm.above[w], 1u);
+                else if (rel >= 0) hist_add(sm.hist, w, rel);
+            }
+        }
+        // coarse / refining windows (cold start, slide) and overflowed tiles: exact values, every element
+        for (int w = warp; w < K; w += AUC_NW) {
+            const int shift = sm.r_shift[w];
+            if (shift == 0 && !direct) continue;
+            const unsigned* row = reinterpret_cast<const unsigned*>(tile + (size_t)w * J) + lane * NH2;
+            const int base = sm.r_base[w];
+            unsigned int nabove = 0;
 #pragma unroll
-                    for (int h = 0; h < NH2; ++h) {
-                        __half2 v2 = __hsub2(u2h2(row[h]), c2[h]);
-                        vraw[h] = h22u(v2);
-                        m[h] = __hge2_mask(v2, lo2);
-                        gem |= m[h];
+            for (int e = 0; e < CPL; ++e) {
+                const int cidx = lane * CPL + e;
+                const unsigned int sr = (row[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+                const __half v = (sm.colown[cidx] == w) ? bits2h(sr)
+                                                       : __hsub(bits2h(sr), __ushort_as_half(sm.colcost[cidx]));
+                const int key = (int)h2key(h2bits(v));
+                const bool in = cidx < ncols && key >= base;
+                const int bin = (key - base) >> shift;
+                const bool ab = in && bin >= AUC_W;
+                const bool hb = in && bin < AUC_W;
+                nabove += __popc(__ballot_sync(0xffffffffu, ab));
+                unsigned int act = __ballot_sync(0xffffffffu, hb);
+                if (act) {
+                    int lead = __ffs(act) - 1;
+                    int lbin = __shfl_sync(0xffffffffu, bin, lead);
+                    unsigned int same = __ballot_sync(0xffffffffu, hb && bin == lbin);
+                    if (same == act) {
+                        if (lane == lead) hist_add(sm.hist, w, lbin, __popc(act));
+                    } else if (hb) {
+                        hist_add(sm.hist, w, bin);
                     }
-                    if (!__any_sync(0xffffffffu, gem != 0)) continue;
-#pragma unroll
-                    for (int e = 0; e < CPL; ++e) {
-                        const unsigned int half_sel = (e & 1) * 16;
-                        bool c = ((m[e >> 1] >> half_sel) & 1u) != 0 && (lane * CPL + e) < ncols;
-                        if (c && sm.colown[lane * CPL + e] == w) c = false;     // owner entry: done by the column thread
-                        unsigned int mm = __ballot_sync(0xffffffffu, c);
-                        if (c) my_list[wn + __popc(mm & lt)] = ((unsigned)w << 16) | ((vraw[e >> 1] >> half_sel) & 0xffffu);
-                        wn += __popc(mm);
-                    }
-                } else {
-                    // coarse / refining window (cold start, slide): exact values, warp-aggregated counting
-                    const int base = sm.r_base[w];
-                    unsigned int nabove = 0;
-#pragma unroll
-                    for (int e = 0; e < CPL; ++e) {
-                        const int cidx = lane * CPL + e;
-                        const unsigned int sr = (row[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
-                        const __half v = (sm.colown[cidx] == w) ? bits2h(sr)
-                                                               : __hsub(bits2h(sr), __ushort_as_half(sm.colcost[cidx]));
-                        const int key = (int)h2key(h2bits(v));
-                        const bool in = cidx < ncols && key >= base;
-                        const int bin = (key - base) >> shift;
-                        const bool ab = in && bin >= AUC_W;
-                        const bool hb = in && bin < AUC_W;
-                        nabove += __popc(__ballot_sync(0xffffffffu, ab));
-                        unsigned int act = __ballot_sync(0xffffffffu, hb);
-                        if (act) {
-                            int lead = __ffs(act) - 1;
-                            int lbin = __shfl_sync(0xffffffffu, bin, lead);
-                            unsigned int same = __ballot_sync(0xffffffffu, hb && bin == lbin);
-                            if (same == act) {
-                                if (lane == lead) hist_add(sm.hist, w, lbin, __popc(act));
-                            } else if (hb) {
-                                hist_add(sm.hist, w, bin);
-                            }
-                        }
-                    }
-                    if (lane == 0 && nabove) atomicAdd(&sm.above[w], nabove);
                 }
             }
-            __syncwarp();
-            for (int i = lane; i < wn; i += 32) process_hist(my_list[i]);
+            if (lane == 0 && nabove) atomicAdd(&sm.above[w], nabove);
         }
         __syncthreads();                                                     // S6: tile buffer + column state free
+        if (tid == 0) s_direct = 0;
     }
     cp_async_wait<0>();
 
@@ -581,8 +599,73 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
 }
 
 static inline size_t auction_pass_smem(int K, int J) {
-    return (size_t)2 * K * J * 2 + (size_t)K * AUC_W * 2 + (size_t)K * 16 + (size_t)J * 4 +
-           (size_t)AUC_NW * AUC_LIST_CAP * 4 + (size_t)J * 4 + (size_t)K * 4 + (size_t)K * 2 + (size_t)J + 64;
+    return (size_t)2 * K * J * 2 + (size_t)K * AUC_W * 2 + (size_t)K * 24 + (size_t)J * 4 +
+           (size_t)AUC_CAPL * AUC_THREADS * 2 + (size_t)J * 4 + (size_t)K * 2 + (size_t)J + 64;
+}
+
+// ------------------------------------------------------------------------------------------
+// sampled windows: instead of a coarse 3-pass radix descent from cold, estimate each worker's
+// threshold from a strided sample of its current values and open a fine window around the
+// estimate (+-4.5 sigma of the order statistic).  A wrong guess only costs a slide / coarse restart.
+// Grid = K CTAs x 1024 threads, 4096 samples.
+// ------------------------------------------------------------------------------------------
+constexpr int AUC_SAMPLE = 4096;
+
+__global__ void __launch_bounds__(1024, 1)
+auction_sample_kernel(const __half* __restrict__ S, long long ld, long long N, int K, long long jpw, AuctionPtrs p) {
+    const AuctionState st = *p.st;
+    if (st.mode != MODE_HIST || !st.need_sample) return;
+    __shared__ unsigned short keys[AUC_SAMPLE];
+    const int w = blockIdx.x, tid = threadIdx.x;
+    const long long ns = N < AUC_SAMPLE ? N : AUC_SAMPLE;
+    const __half eps = bits2h(st.eps_bits);
+    for (int i = tid; i < AUC_SAMPLE; i += 1024) {
+        unsigned short key = 0;                                            // padding sorts last
+        if (i < ns) {
+            const long long stride = N / ns;                               // evenly strided over the jobs
+            const long long col = (long long)i * stride + stride / 2;
+            __half c = p.cost[col];
+            const short o = p.owner[col];
+            if (st.ff_pending > 0 && o >= 0)
+                for (int r = 0; r < st.ff_pending; ++r) c = __hadd(c, eps);
+            const __half s = S[(size_t)w * ld + col];
+            const __half v = (o == w) ? s : __hsub(s, c);
+            key = (unsigned short)h2key(h2bits(v));
+        }
+        keys[i] = key;
+    }
+    __syncthreads();
+    // bitonic sort, descending
+    for (int k = 2; k <= AUC_SAMPLE; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < AUC_SAMPLE; i += 1024) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned short a = keys[i], b2 = keys[ixj];
+                    const bool desc = (i & k) == 0;
+                    if (desc ? (a < b2) : (a > b2)) { keys[i] = b2; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (tid == 0) {
+        // rank (0-based, descending) of the (jpw+1)-th largest of N inside the sample, +- its spread
+        const double r = (double)(jpw + 1) * (double)ns / (double)N - 0.5;
+        const double sg = sqrt(r > 1.0 ? r : 1.0);
+        long long r_hi = (long long)floor(r - 4.5 * sg - 2.0), r_lo = (long long)ceil(r + 4.5 * sg + 2.0);
+        if (r_hi < 0) r_hi = 0;
+        if (r_lo > ns - 1) r_lo = ns - 1;
+        int lo = (int)keys[r_lo] - 1, hi = (int)keys[r_hi] + 1;
+        if (r_hi == 0) hi += 64;                                            // the sample's maximum is no bound
+        if (lo < AUC_MIN_KEY) lo = AUC_MIN_KEY;
+        if (hi < lo + 8) hi = lo + 8;
+        int span = hi - lo + 1, shift = 0;
+        while ((span >> shift) > AUC_W) ++shift;
+        if (shift == 0 && lo > 65536 - AUC_W) lo = 65536 - AUC_W;
+        p.win_base[w] = lo;
+        p.win_shift[w] = shift;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -710,6 +793,7 @@ auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
         s.window_misses += s_miss;
         if (was_bid) s.counter += 1;                                     // :125
         s.ff_pending = 0;
+        s.need_sample = jump ? 1 : 0;
         if (jump) {
             // frozen at counter c (already incremented to c+1): rounds c+1..99 add eps each
             s.ff_pending = 100 - s.counter;
@@ -747,12 +831,14 @@ auction_tieprefix_kernel(AuctionPtrs p, int K, int G) {
     if (tid == AUC_MAX_CTAS - 1) p.tie_total[w] = cnt[AUC_MAX_CTAS - 1];
     __syncthreads();
     if (tid == 0) {
-        // Every held job's cost rises by >= eps per round, so thresholds sink by about eps:
-        // window = [T - 2.4 eps, T + 0.4 eps], capped at 128 keys (coarser bins + a refine pass beyond).
+        // Every held job's cost rises by >= eps per round, so thresholds sink by about eps (never more
+        // than ~2 eps in practice): window = [T - 2.15 eps, T + 0.15 eps]; eps is 27..55 fp16 keys at
+        // the threshold for data whose nearest centre is at distance ~0, so this fits 128 one-key bins
+        // (coarser bins + one cheap refine pass otherwise).
         const float T = __half2float(bits2h(key2h((unsigned)tk)));
         const float e = __half2float(bits2h(p.st->eps_bits));
-        int lo = (int)h2key(h2bits(__float2half_rn(T - 2.4f * e)));
-        int hi = (int)h2key(h2bits(__float2half_rn(T + 0.4f * e)));
+        int lo = (int)h2key(h2bits(__float2half_rn(T - 2.15f * e)));
+        int hi = (int)h2key(h2bits(__float2half_rn(T + 0.15f * e)));
         if (hi < tk + 2) hi = tk + 2;
         if (lo > tk - 8) lo = tk - 8;
         if (lo < AUC_MIN_KEY) lo = AUC_MIN_KEY;
@@ -875,6 +961,8 @@ int rqk_auction_pass(const void* scores_t, int64_t ld, int64_t n, int32_t k, int
         RQK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem));
         cur = a.smem;
     }
+    if (n_global == n)   // sampled windows need the whole job set on this GPU (ranks must agree on the windows)
+        auction_sample_kernel<<<k, 1024, 0, (cudaStream_t)stream_>>>((const __half*)scores_t, ld, n, k, n_global / k, a.p);
     kern<<<a.G, AUC_THREADS, a.smem, (cudaStream_t)stream_>>>((const __half*)scores_t, ld, n, k, n_global / k, a.p);
     RQK_LAUNCH_OK();
     return 0;

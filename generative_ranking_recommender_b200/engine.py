@@ -18,7 +18,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, sharding
 from ._lib import AuctionInfo, AuctionLayout, check, lib
 
 
@@ -56,9 +56,9 @@ class ShardGroup:
     def all_gather(self, t: torch.Tensor) -> torch.Tensor:
         if not self.active:
             return t.unsqueeze(0)
-        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-        self.dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
-        return out
+        parts = [torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(parts, t.contiguous(), group=self.group)
+        return torch.stack(parts)
 
 
 _NO_SHARD = None
@@ -198,7 +198,7 @@ def auction(scores_t: torch.Tensor, n: int, minmax: torch.Tensor,
             shard.all_reduce(sess.reduce_block, "sum")
             sess.resolve()
             totals = shard.all_gather(sess.tie_total)                 # [world, k]
-            sess.tie_offset(totals[: shard.rank].sum(dim=0, dtype=torch.int32) if shard.rank > 0 else None)
+            sess.tie_offset(sharding.rank_tie_offsets(totals, shard.rank) if shard.rank > 0 else None)
         info = sess.poll()
         if info.done:
             break
