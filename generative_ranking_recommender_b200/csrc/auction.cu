@@ -280,9 +280,9 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
         const int base = p.win_base[i], shift = p.win_shift[i];
         sm.r_base[i] = base;
         sm.r_shift[i] = (unsigned char)shift;
-        // fine rows are filtered at the window's low edge; coarse rows (cold start, refinement) are
-        // histogrammed by the direct path, so their sweep only has to find bidders
-        const unsigned int lob = (shift == 0) ? key2h((unsigned)base) : (do_bid ? Tb : 0x7c00u /* +inf: nothing */);
+        // BID pass: the sweep finds bidders (v >= T).  HIST pass: fine rows are filtered at the window's
+        // low edge; coarse rows (cold start, refinement) are histogrammed by the direct path
+        const unsigned int lob = do_bid ? Tb : ((shift == 0) ? key2h((unsigned)base) : 0x7c00u /* +inf: nothing */);
         sm.r_lo2[i] = lob | (lob << 16);
         sm.row_flag[i] = 0;
     }
@@ -520,6 +520,11 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
             for (int i = tid; i < K; i += AUC_THREADS) sm.row_flag[i] = 0;
         }
         __syncthreads();                                                     // S4: new column state + overflow flag visible
+        if (do_bid) {                                                        // bids only: the histogram of the new
+            __syncthreads();                                                 // state is a separate, sampled-window pass
+            if (tid == 0) s_direct = 0;
+            continue;
+        }
         const bool direct = s_direct != 0;
 
         // ---------------- stage B: histogram of the values the next selection will see ----------------
@@ -582,6 +587,13 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
     }
     cp_async_wait<0>();
 
+    if (do_bid) {
+        if (tid == 0) {
+            if (s_nwith) atomicAdd(p.n_with, s_nwith);
+            if (s_nviol) atomicAdd(p.n_viol, s_nviol);
+        }
+        return;
+    }
     // ---- publish: per-CTA dump (for the tie prefix) + merge of non-empty bins ----
     unsigned int* dump = reinterpret_cast<unsigned int*>(p.hist_cta + (size_t)b * K * AUC_W);
     for (int i = tid; i < K * AUC_W / 2; i += AUC_THREADS) {
@@ -592,10 +604,6 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
     }
     for (int i = tid; i < K; i += AUC_THREADS)
         if (sm.above[i]) atomicAdd(&p.above_g[i], sm.above[i]);
-    if (tid == 0 && do_bid) {
-        if (s_nwith) atomicAdd(p.n_with, s_nwith);
-        if (s_nviol) atomicAdd(p.n_viol, s_nviol);
-    }
 }
 
 static inline size_t auction_pass_smem(int K, int J) {
@@ -622,8 +630,10 @@ auction_sample_kernel(const __half* __restrict__ S, long long ld, long long N, i
     for (int i = tid; i < AUC_SAMPLE; i += 1024) {
         unsigned short key = 0;                                            // padding sorts last
         if (i < ns) {
-            const long long stride = N / ns;                               // evenly strided over the jobs
-            const long long col = (long long)i * stride + stride / 2;
+            // 16 consecutive jobs = one 32-byte sector of the row; chunks evenly strided over the jobs
+            const long long nchunks = (ns + 15) / 16, chunk = i >> 4;
+            long long col = (N / nchunks) * chunk + (i & 15);
+            if (col >= N) col = N - 1;
             __half c = p.cost[col];
             const short o = p.owner[col];
             if (st.ff_pending > 0 && o >= 0)
@@ -707,8 +717,18 @@ auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
     }
 
     // ---- 2. thresholds from the histogram (of the values the next selection sees) ----
+    // A BID pass leaves no histogram: the next pass is a HIST pass over the new state with windows
+    // placed by the sample kernel.
     const long long need = jpw + 1;
-    if (!jump) {
+    if (was_bid) {
+        for (int w = tid; w < K; w += 1024) {
+            p.win_base[w] = 0;
+            p.win_shift[w] = AUC_COLD_SHIFT;
+            p.tkey[w] = -1;
+            p.miss_run[w] = 0;
+        }
+        if (tid == 0) s_unresolved = 1;
+    } else if (!jump) {
         for (int w = warp; w < K; w += 32) {
             const int base = p.win_base[w], shift = p.win_shift[w];
             unsigned int h[4];
@@ -775,13 +795,6 @@ auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
                 if (shift == 0) atomicAdd(&s_miss, 1);
             }
         }
-    } else {
-        for (int w = tid; w < K; w += 1024) {
-            p.win_base[w] = 0;
-            p.win_shift[w] = AUC_COLD_SHIFT;
-            p.tkey[w] = -1;
-            p.miss_run[w] = 0;
-        }
     }
     __syncthreads();
     // ---- 3. zero the merged histograms for the next pass ----
@@ -793,7 +806,7 @@ auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
         s.window_misses += s_miss;
         if (was_bid) s.counter += 1;                                     // :125
         s.ff_pending = 0;
-        s.need_sample = jump ? 1 : 0;
+        s.need_sample = was_bid ? 1 : 0;
         if (jump) {
             // frozen at counter c (already incremented to c+1): rounds c+1..99 add eps each
             s.ff_pending = 100 - s.counter;
@@ -829,25 +842,6 @@ auction_tieprefix_kernel(AuctionPtrs p, int K, int G) {
     }
     if (tid < G) p.tieprefix[(size_t)tid * K + w] = cnt[tid] - c;
     if (tid == AUC_MAX_CTAS - 1) p.tie_total[w] = cnt[AUC_MAX_CTAS - 1];
-    __syncthreads();
-    if (tid == 0) {
-        // Every held job's cost rises by >= eps per round, so thresholds sink by about eps (never more
-        // than ~2 eps in practice): window = [T - 2.15 eps, T + 0.15 eps]; eps is 27..55 fp16 keys at
-        // the threshold for data whose nearest centre is at distance ~0, so this fits 128 one-key bins
-        // (coarser bins + one cheap refine pass otherwise).
-        const float T = __half2float(bits2h(key2h((unsigned)tk)));
-        const float e = __half2float(bits2h(p.st->eps_bits));
-        int lo = (int)h2key(h2bits(__float2half_rn(T - 2.15f * e)));
-        int hi = (int)h2key(h2bits(__float2half_rn(T + 0.15f * e)));
-        if (hi < tk + 2) hi = tk + 2;
-        if (lo > tk - 8) lo = tk - 8;
-        if (lo < AUC_MIN_KEY) lo = AUC_MIN_KEY;
-        int span = hi - lo + 1, shift = 0;
-        while ((span >> shift) > AUC_W) ++shift;
-        if (shift == 0 && lo > 65536 - AUC_W) lo = 65536 - AUC_W;
-        p.win_base[w] = lo;
-        p.win_shift[w] = shift;
-    }
 }
 
 // sharded jobs: ranks are ordered, so a rank's CTAs come after all ties of lower ranks

@@ -71,9 +71,10 @@ def test_score_pass_matches_oracle(dev, engine, n, k, dim, simt):
     # fp16 scores: compared where the distance is well conditioned (d^2 >= 5 % of |x|^2+|c|^2); in the
     # cancellation regime (x almost on a centre) the absolute d^2 bound above is the contract
     well = (d64 ** 2 >= 0.05 * scale).T
-    assert (s[:, :n] == s_ref)[well].mean() >= 0.999
-    ulp_off = np.abs(s[:, :n].astype(np.int32) - s_ref.astype(np.int32))
-    assert ulp_off[well].max(initial=0) <= 1
+    if well.any():
+        assert (s[:, :n] == s_ref)[well].mean() >= 0.999
+        ulp_off = np.abs(s[:, :n].astype(np.int32) - s_ref.astype(np.int32))
+        assert ulp_off[well].max(initial=0) <= 1
     am = r.argmin.cpu().numpy()
     near = O.top2_relative_gap(d64) < NEAR_TIE if k > 1 else np.zeros(n, bool)
     bad = (am != np.argmin(d, axis=1)) & ~near
