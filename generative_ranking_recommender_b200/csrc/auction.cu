@@ -220,15 +220,39 @@ __device__ __forceinline__ void hist_add(unsigned int* hist, int w, int bin, uns
     atomicAdd(&hist[(w * AUC_W + bin) >> 1], n << ((bin & 1) * 16));
 }
 
-// One pass.  Per tile: ONE half2 sweep filters S - cost_old against the low edge of each worker's
-// window (a superset of both the bidders, v >= T, and of the next round's in-window values, because
-// costs only grow); survivors go to lane-private lists and are visited twice: stage A turns them
-// into bids with the old costs, stage B histograms them with the new costs.
+// ---- mbarrier + bulk-copy (UBLKCP) tile loads: one 16-byte-aligned row per instruction ----
+__device__ __forceinline__ unsigned s_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mb_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(s_addr(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(s_addr(dst)), "l"(src), "r"(bytes), "r"(s_addr(bar)) : "memory");
+}
+
+// One pass.  BID pass: the sweep filters S - cost against each worker's threshold T_w; the ~1 %
+// survivors (lane-private lists) become bids.  HIST pass: the sweep filters S - cost against the low
+// edge of each worker's (sampled) window; survivors are histogrammed.  Both are streaming passes whose
+// per-element work is one HSUB2 + one HSET2 per two elements.
 template <int J>
 __global__ void __launch_bounds__(AUC_THREADS, (J == 128 ? 2 : 1))
 auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int K, long long jpw, AuctionPtrs p) {
-    constexpr int CPL = J / 32;      // columns per lane
-    constexpr int NH2 = CPL / 2;     // half2 words per lane
+    constexpr int CPL = J / 32;           // columns per lane
+    constexpr int NH2 = CPL / 2;          // half2 words per lane
+    constexpr int MAXR = 256 / AUC_NW * (J == 128 ? 1 : 2) / 2;   // rows per warp: 8 (K<=128) / 16 (K<=256)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const AuctionState st = *p.st;
     if (st.mode == MODE_DONE) return;
@@ -261,6 +285,7 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
         sm.colviol = (unsigned char*)q;      q += (size_t)J;
     }
     __shared__ unsigned int s_nwith, s_nviol, s_direct;
+    __shared__ __align__(8) unsigned long long tile_bar[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned int lt = (1u << lane) - 1u;
@@ -280,29 +305,40 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
         const int base = p.win_base[i], shift = p.win_shift[i];
         sm.r_base[i] = base;
         sm.r_shift[i] = (unsigned char)shift;
-        // BID pass: the sweep finds bidders (v >= T).  HIST pass: fine rows are filtered at the window's
-        // low edge; coarse rows (cold start, refinement) are histogrammed by the direct path
-        const unsigned int lob = do_bid ? Tb : ((shift == 0) ? key2h((unsigned)base) : 0x7c00u /* +inf: nothing */);
+        // BID pass: the sweep finds bidders (v >= T).  HIST pass: rows with a placed window (sampled, slid,
+        // refined: base > 0) are filtered at its low edge; cold rows (base == 0: all 65536 keys in 128 coarse
+        // bins) take the direct path, their filter passes nothing (+inf)
+        const unsigned int lob = do_bid ? Tb : (base > 0 ? key2h((unsigned)base) : 0x7c00u);
         sm.r_lo2[i] = lob | (lob << 16);
         sm.row_flag[i] = 0;
     }
     for (int i = tid; i < J; i += AUC_THREADS) { sm.colmax[i] = 0; sm.colviol[i] = 0; }
-    if (tid == 0) { s_nwith = 0; s_nviol = 0; s_direct = 0; }
+    if (tid == 0) {
+        s_nwith = 0; s_nviol = 0; s_direct = 0;
+        mb_init(&tile_bar[0], 1);
+        mb_init(&tile_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // per-row sweep filter in registers (the rows of a warp are w = warp + 16 i)
+    unsigned int f2r[MAXR];
+    bool any_cold = false;
+#pragma unroll
+    for (int i = 0; i < MAXR; ++i) {
+        const int w = warp + AUC_NW * i;
+        f2r[i] = (w < K) ? sm.r_lo2[w] : 0x7c007c00u;
+        if (w < K && !do_bid && sm.r_base[w] == 0) any_cold = true;
+    }
 
     auto issue_tile = [&](long long t, int buf) {
-        constexpr int CHUNKS_PER_ROW = J * 2 / 16;
-        const int total = K * CHUNKS_PER_ROW;
-        __half* dst = sm.tile0 + (size_t)buf * K * J;
-        const __half* src = S + t * J;
-        for (int c = tid; c < total; c += AUC_THREADS) {
-            int row = c / CHUNKS_PER_ROW, ch = c % CHUNKS_PER_ROW;
-            cp_async16(dst + (size_t)row * J + ch * 8, src + (size_t)row * ld + ch * 8);
-        }
+        if (tid == 0) mb_expect_tx(&tile_bar[buf], (unsigned)(K * J * 2));
+        if (tid < K)
+            bulk_g2s(sm.tile0 + (size_t)buf * K * J + (size_t)tid * J, S + (size_t)tid * ld + t * J, J * 2, &tile_bar[buf]);
     };
+    unsigned int bar_phase = 0;                         // bit buf = parity to wait for
 
     if (t_begin < t_end) issue_tile(t_begin, 0);
-    cp_async_commit();
-    __syncthreads();
 
     for (long long t = t_begin; t < t_end; ++t) {
         const int buf = (int)((t - t_begin) & 1);
@@ -329,14 +365,15 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
         // prefetch the next tile into the other buffer (its last readers finished before the
         // barrier that closed the previous iteration)
         if (t + 1 < t_end) issue_tile(t + 1, buf ^ 1);
-        cp_async_commit();
-        cp_async_wait<1>();
+        mb_wait(&tile_bar[buf], (bar_phase >> buf) & 1u);
+        bar_phase ^= 1u << buf;
         __syncthreads();                                                     // S0: tile + column state visible
 
         __half2 c2[NH2];
 #pragma unroll
         for (int h = 0; h < NH2; ++h) c2[h] = u2h2(reinterpret_cast<const unsigned*>(sm.colcost)[lane * NH2 + h]);
 
+        unsigned int flagmask = 0;                                           // bit i: row warp+16i has an owner tie
         if (do_bid) {
             // ---------------- owner entries: one per job, handled by the job's column thread ----------------
             if (tid < ncols) {
@@ -356,21 +393,28 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
                 if (init) atomicMax(&sm.colmax[tid], init);
             }
             __syncthreads();                                                 // S1: row flags visible
+            const int wf = warp + AUC_NW * lane;
+            flagmask = __ballot_sync(0xffffffffu, lane < MAXR && wf < K && sm.row_flag[wf] != 0);
         }
 
-        // ---------------- the sweep: filter S - cost against the window's low edge, compact ----------------
+        // ---------------- the sweep: half2 filter, survivors to the lane-private list ----------------
         int cnt = 0;
-        for (int w = warp; w < K; w += AUC_NW) {
-            const __half2 lo2 = u2h2(sm.r_lo2[w]);
-            const unsigned* row = reinterpret_cast<const unsigned*>(tile + (size_t)w * J) + lane * NH2;
-            const bool flagged = do_bid && sm.row_flag[w] != 0;
+        const unsigned* tile_u = reinterpret_cast<const unsigned*>(tile) + lane * NH2;
+#pragma unroll
+        for (int i = 0; i < MAXR; ++i) {
+            const int w = warp + AUC_NW * i;
+            if (w >= K) break;
+            const __half2 f2 = u2h2(f2r[i]);
+            const unsigned* row = tile_u + (size_t)w * (J / 2);
+            const bool flagged = (flagmask >> i) & 1u;
             __half2 v2[NH2];
-            unsigned int m[NH2];
+            unsigned int m[NH2], anym = 0;
             if (!flagged) {
 #pragma unroll
                 for (int h = 0; h < NH2; ++h) {
                     v2[h] = __hsub2(u2h2(row[h]), c2[h]);                    // ownership ignored: the owner's S is only larger
-                    m[h] = __hge2_mask(v2[h], lo2);
+                    m[h] = __hge2_mask(v2[h], f2);
+                    anym |= m[h];
                 }
             } else {
 #pragma unroll
@@ -379,15 +423,15 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
                     if (sm.colown[lane * CPL + 2 * h] == w) cr &= 0xffff0000u;
                     if (sm.colown[lane * CPL + 2 * h + 1] == w) cr &= 0x0000ffffu;
                     v2[h] = __hsub2(u2h2(row[h]), u2h2(cr));
-                    m[h] = __hge2_mask(v2[h], lo2);
+                    m[h] = __hge2_mask(v2[h], f2);
+                    anym |= m[h];
                 }
             }
             unsigned int rej = 0;                                            // bit e: tie at T_w that gets no bid
-            if (do_bid) {
-                const __half2 T2 = u2h2(sm.r_T2[w]);
+            if (do_bid) {                                                    // f2 == T_w in a BID pass
                 unsigned int anye = 0, em[NH2];
 #pragma unroll
-                for (int h = 0; h < NH2; ++h) { em[h] = __heq2_mask(v2[h], T2); anye |= em[h]; }
+                for (int h = 0; h < NH2; ++h) { em[h] = __heq2_mask(v2[h], f2); anye |= em[h]; }
                 if (__any_sync(0xffffffffu, anye != 0)) {
                     // canonical tie rule: lowest job index first, globally (tieprefix + tiles so far).
                     // In unflagged rows owner entries cannot tie (the column thread would have flagged the row).
@@ -416,24 +460,29 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
                     __syncwarp();
                 }
             }
-#pragma unroll
-            for (int e = 0; e < CPL; ++e) {
-                if ((m[e >> 1] >> ((e & 1) * 16)) & 1u) {
-                    const unsigned int entry = ((unsigned)w << 8) | ((unsigned)(lane * CPL + e) << 1) | ((rej >> e) & 1u);
+            if (anym) {
+                // one bit per surviving column of this lane
+                unsigned int bits = (m[0] & 1u) | ((m[0] >> 15) & 2u);
+                if (NH2 > 1) bits |= ((m[NH2 - 1] << 2) & 4u) | ((m[NH2 - 1] >> 13) & 8u);
+                do {
+                    const int e = __ffs(bits) - 1;
+                    bits &= bits - 1;
                     if (cnt < AUC_CAPL) {
-                        my_list[cnt * AUC_THREADS] = (unsigned short)entry;
+                        my_list[cnt * AUC_THREADS] =
+                            (unsigned short)(((unsigned)w << 8) | ((unsigned)(lane * CPL + e) << 1) | ((rej >> e) & 1u));
                         ++cnt;
                     } else {
-                        cnt = AUC_CAPL + 1;                                  // overflow: handled by the direct path
+                        cnt = AUC_CAPL + 1;                                  // overflow: the tile takes the direct path
                     }
-                }
+                } while (bits);
             }
         }
         if (cnt > AUC_CAPL) s_direct = 1;
+        __syncthreads();                                                     // S2: overflow flag visible
+        const bool direct = s_direct != 0;
+
         if (do_bid) {
-            __syncthreads();                                                 // S1b: overflow flag visible
-            const bool direct = s_direct != 0;
-            // ---------------- stage A: survivors -> bids (old costs / owners) ----------------
+            // ---------------- stage A: survivors -> bids ----------------
             auto bid_one = [&](int w, int col, bool rejected, bool flagged_row) {
                 const int o = sm.colown[col];
                 const bool own = (o == w);
@@ -441,7 +490,7 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
                 const __half s = tile[(size_t)w * J + col];
                 const __half v = own ? s : __hsub(s, __ushort_as_half(sm.colcost[col]));
                 const __half T = bits2h(sm.r_T2[w] & 0xffffu);
-                if (!(__hgt(v, T) || (__heq(v, T) && !rejected))) return;    // a histogram-only survivor
+                if (!(__hgt(v, T) || (__heq(v, T) && !rejected))) return;
                 if (fallback && w == 0 && o < 0) return;                     // :89 overrides worker 0's own bid
                 unsigned int bid = h2bits(__hadd(__hsub(v, T), eps));        // :76, two roundings
                 if (retain && own) bid = eps_bits;                           // :87
@@ -472,7 +521,7 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
                         before += __popc(mm & lt);
                         total += __popc(mm);
                     }
-                    // this row's ties were already ranked by the sweep: undo and redo from the tile's start state
+                    // this row's ties were already counted by the sweep: rank again from the tile's start state
                     const unsigned int seen = sm.tie_seen[w] - total;
                     const long long quota = sm.r_take[w];
 #pragma unroll
@@ -484,7 +533,7 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
                     }
                 }
             }
-            __syncthreads();                                                 // S2: all bids in colmax
+            __syncthreads();                                                 // S3: all bids in colmax
 
             // ---------------- highest bid per job, cost/owner update (:104, :118-123) ----------------
             if (tid < J) {
@@ -497,13 +546,9 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
                     if (pk) {
                         has = true;
                         const short wnr = (short)(0xffffu - (pk & 0xffffu));
-                        const __half nc = __hadd(__ushort_as_half(sm.colcost[tid]), bits2h(pk >> 16));
-                        sm.colcost[tid] = __half_as_ushort(nc);
-                        sm.colown[tid] = wnr;
-                        p.cost[col] = nc;
+                        p.cost[col] = __hadd(__ushort_as_half(sm.colcost[tid]), bits2h(pk >> 16));
                         p.owner[col] = wnr;
                     } else {
-                        sm.colown[tid] = -1;
                         p.owner[col] = -1;
                         if (old_owner >= 0) vv = true;                       // an owned job lost its bidder
                     }
@@ -518,74 +563,74 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
                 }
             }
             for (int i = tid; i < K; i += AUC_THREADS) sm.row_flag[i] = 0;
-        }
-        __syncthreads();                                                     // S4: new column state + overflow flag visible
-        if (do_bid) {                                                        // bids only: the histogram of the new
-            __syncthreads();                                                 // state is a separate, sampled-window pass
-            if (tid == 0) s_direct = 0;
-            continue;
-        }
-        const bool direct = s_direct != 0;
-
-        // ---------------- stage B: histogram of the values the next selection will see ----------------
-        // owner entries (value = S) of fine-window rows: one per job, by the column thread
-        if (tid < ncols && !direct) {
-            const int o = sm.colown[tid];
-            if (o >= 0 && sm.r_shift[o] == 0) {
-                const int rel = (int)h2key(h2bits(tile[(size_t)o * J + tid])) - sm.r_base[o];
-                if (rel >= AUC_W) atomicAdd(&sm.above[o], 1u);
-                else if (rel >= 0) hist_add(sm.hist, o, rel);
-            }
-        }
-        if (!direct) {
-            const int n = cnt;
-            for (int i = 0; i < n; ++i) {
-                const unsigned int e = my_list[i * AUC_THREADS];
-                const int w = e >> 8, col = (e >> 1) & 127;
-                if (sm.r_shift[w] != 0 || sm.colown[col] == w) continue;     // coarse row / owner entry: done elsewhere
-                const __half v = __hsub(tile[(size_t)w * J + col], __ushort_as_half(sm.colcost[col]));
-                const int rel = (int)h2key(h2bits(v)) - sm.r_base[w];
-                if (rel >= AUC_W) atomicAdd(&sm.above[w], 1u);
-                else if (rel >= 0) hist_add(sm.hist, w, rel);
-            }
-        }
-        // coarse / refining windows (cold start, slide) and overflowed tiles: exact values, every element
-        for (int w = warp; w < K; w += AUC_NW) {
-            const int shift = sm.r_shift[w];
-            if (shift == 0 && !direct) continue;
-            const unsigned* row = reinterpret_cast<const unsigned*>(tile + (size_t)w * J) + lane * NH2;
-            const int base = sm.r_base[w];
-            unsigned int nabove = 0;
-#pragma unroll
-            for (int e = 0; e < CPL; ++e) {
-                const int cidx = lane * CPL + e;
-                const unsigned int sr = (row[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
-                const __half v = (sm.colown[cidx] == w) ? bits2h(sr)
-                                                       : __hsub(bits2h(sr), __ushort_as_half(sm.colcost[cidx]));
-                const int key = (int)h2key(h2bits(v));
-                const bool in = cidx < ncols && key >= base;
-                const int bin = (key - base) >> shift;
-                const bool ab = in && bin >= AUC_W;
-                const bool hb = in && bin < AUC_W;
-                nabove += __popc(__ballot_sync(0xffffffffu, ab));
-                unsigned int act = __ballot_sync(0xffffffffu, hb);
-                if (act) {
-                    int lead = __ffs(act) - 1;
-                    int lbin = __shfl_sync(0xffffffffu, bin, lead);
-                    unsigned int same = __ballot_sync(0xffffffffu, hb && bin == lbin);
-                    if (same == act) {
-                        if (lane == lead) hist_add(sm.hist, w, lbin, __popc(act));
-                    } else if (hb) {
-                        hist_add(sm.hist, w, bin);
+        } else {
+            // ---------------- stage B: survivors -> histogram ----------------
+            // owner entries (value = S) of rows with a placed window: one per job, by the column thread
+            if (tid < ncols && !direct) {
+                const int o = sm.colown[tid];
+                if (o >= 0 && sm.r_base[o] > 0) {
+                    const int rel = (int)h2key(h2bits(tile[(size_t)o * J + tid])) - sm.r_base[o];
+                    const int bin = rel >> sm.r_shift[o];
+                    if (rel >= 0) {
+                        if (bin >= AUC_W) atomicAdd(&sm.above[o], 1u);
+                        else hist_add(sm.hist, o, bin);
                     }
                 }
             }
-            if (lane == 0 && nabove) atomicAdd(&sm.above[w], nabove);
+            if (!direct) {
+                const int n = cnt;
+                for (int i = 0; i < n; ++i) {
+                    const unsigned int e = my_list[i * AUC_THREADS];
+                    const int w = e >> 8, col = (e >> 1) & 127;
+                    if (sm.colown[col] == w) continue;                       // owner entry: done by the column thread
+                    const __half v = __hsub(tile[(size_t)w * J + col], __ushort_as_half(sm.colcost[col]));
+                    const int rel = (int)h2key(h2bits(v)) - sm.r_base[w];
+                    const int bin = rel >> sm.r_shift[w];
+                    if (rel >= 0) {
+                        if (bin >= AUC_W) atomicAdd(&sm.above[w], 1u);
+                        else hist_add(sm.hist, w, bin);
+                    }
+                }
+            }
+            // cold rows (all keys in 128 coarse bins) and overflowed tiles: exact values, every element
+            if (any_cold || direct) {
+                for (int w = warp; w < K; w += AUC_NW) {
+                    const int base = sm.r_base[w];
+                    if (base > 0 && !direct) continue;
+                    const int shift = sm.r_shift[w];
+                    const unsigned* row = reinterpret_cast<const unsigned*>(tile + (size_t)w * J) + lane * NH2;
+                    unsigned int nabove = 0;
+#pragma unroll
+                    for (int e = 0; e < CPL; ++e) {
+                        const int cidx = lane * CPL + e;
+                        const unsigned int sr = (row[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+                        const __half v = (sm.colown[cidx] == w) ? bits2h(sr)
+                                                               : __hsub(bits2h(sr), __ushort_as_half(sm.colcost[cidx]));
+                        const int key = (int)h2key(h2bits(v));
+                        const bool in = cidx < ncols && key >= base;
+                        const int bin = (key - base) >> shift;
+                        const bool ab = in && bin >= AUC_W;
+                        const bool hb = in && bin < AUC_W;
+                        nabove += __popc(__ballot_sync(0xffffffffu, ab));
+                        unsigned int act = __ballot_sync(0xffffffffu, hb);
+                        if (act) {
+                            int lead = __ffs(act) - 1;
+                            int lbin = __shfl_sync(0xffffffffu, bin, lead);
+                            unsigned int same = __ballot_sync(0xffffffffu, hb && bin == lbin);
+                            if (same == act) {
+                                if (lane == lead) hist_add(sm.hist, w, lbin, __popc(act));
+                            } else if (hb) {
+                                hist_add(sm.hist, w, bin);
+                            }
+                        }
+                    }
+                    if (lane == 0 && nabove) atomicAdd(&sm.above[w], nabove);
+                }
+            }
         }
-        __syncthreads();                                                     // S6: tile buffer + column state free
+        __syncthreads();                                                     // S4: tile buffer + column state free
         if (tid == 0) s_direct = 0;
     }
-    cp_async_wait<0>();
 
     if (do_bid) {
         if (tid == 0) {
