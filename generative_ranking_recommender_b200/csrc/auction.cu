@@ -55,7 +55,6 @@ constexpr int AUC_MAX_CTAS = 1024; // tie-prefix kernel limit
 constexpr int AUC_MAX_JOBS_PER_CTA = 65024;   // 16-bit per-CTA counters
 constexpr int AUC_MIN_TILES_PER_CTA = 2;
 constexpr int AUC_COLD_SHIFT = 9;  // 128 bins x 512 keys cover all 65536 fp16 keys
-constexpr int AUC_CAPL = 10;       // lane-private survivor slots per tile (overflow -> direct path for that tile)
 constexpr int AUC_MIN_KEY = 0x0400; // key of the most negative finite half: fine windows never reach -inf
 
 enum { MODE_HIST = 0, MODE_BID = 1, MODE_DONE = 2 };
@@ -213,7 +212,6 @@ struct PassSmem {
     unsigned short* colcost;   // [J]
     short* colown;             // [J]
     unsigned char* colviol;    // [J]
-    unsigned short* llist;     // [CAPL][THREADS] lane-private survivors: (worker << 8) | (column << 1) | rejected_tie
 };
 
 __device__ __forceinline__ void hist_add(unsigned int* hist, int w, int bin, unsigned int n = 1) {
@@ -277,14 +275,13 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
         sm.r_T2 = (unsigned int*)q;          q += (size_t)K * 4;
         sm.r_lo2 = (unsigned int*)q;         q += (size_t)K * 4;
         sm.colmax = (unsigned int*)q;        q += (size_t)J * 4;
-        sm.llist = (unsigned short*)q;       q += (size_t)AUC_CAPL * AUC_THREADS * 2;
         sm.colcost = (unsigned short*)q;     q += (size_t)J * 2;
         sm.colown = (short*)q;               q += (size_t)J * 2;
         sm.r_shift = (unsigned char*)q;      q += (size_t)K;
         sm.row_flag = (unsigned char*)q;     q += (size_t)K;
         sm.colviol = (unsigned char*)q;      q += (size_t)J;
     }
-    __shared__ unsigned int s_nwith, s_nviol, s_direct;
+    __shared__ unsigned int s_nwith, s_nviol;
     __shared__ __align__(8) unsigned long long tile_bar[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -292,7 +289,6 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
     const int G = gridDim.x, b = blockIdx.x;
     const long long tiles_total = (N + J - 1) / J;
     const long long t_begin = tiles_total * b / G, t_end = tiles_total * (b + 1) / G;
-    unsigned short* my_list = sm.llist + tid;           // slot i at my_list[i * AUC_THREADS]
 
     for (int i = tid; i < K * AUC_W / 2; i += AUC_THREADS) sm.hist[i] = 0;
     for (int i = tid; i < K; i += AUC_THREADS) {
@@ -314,7 +310,7 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
     }
     for (int i = tid; i < J; i += AUC_THREADS) { sm.colmax[i] = 0; sm.colviol[i] = 0; }
     if (tid == 0) {
-        s_nwith = 0; s_nviol = 0; s_direct = 0;
+        s_nwith = 0; s_nviol = 0;
         mb_init(&tile_bar[0], 1);
         mb_init(&tile_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -397,8 +393,12 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
             flagmask = __ballot_sync(0xffffffffu, lane < MAXR && wf < K && sm.row_flag[wf] != 0);
         }
 
-        // ---------------- the sweep: half2 filter, survivors to the lane-private list ----------------
-        int cnt = 0;
+        // ---------------- the sweep: half2 filter; survivors recorded as register bitmasks ----------------
+        // acc[h] bit i      : column 2h   of row warp+16i survives
+        // acc[h] bit 16 + i : column 2h+1 of row warp+16i survives        (rej[h]: same layout, rejected ties)
+        unsigned int acc[NH2], rej[NH2];
+#pragma unroll
+        for (int h = 0; h < NH2; ++h) { acc[h] = 0; rej[h] = 0; }
         const unsigned* tile_u = reinterpret_cast<const unsigned*>(tile) + lane * NH2;
 #pragma unroll
         for (int i = 0; i < MAXR; ++i) {
@@ -407,14 +407,13 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
             const __half2 f2 = u2h2(f2r[i]);
             const unsigned* row = tile_u + (size_t)w * (J / 2);
             const bool flagged = (flagmask >> i) & 1u;
+            const unsigned int rowbits = (1u << i) | (1u << (16 + i));
             __half2 v2[NH2];
-            unsigned int m[NH2], anym = 0;
             if (!flagged) {
 #pragma unroll
                 for (int h = 0; h < NH2; ++h) {
                     v2[h] = __hsub2(u2h2(row[h]), c2[h]);                    // ownership ignored: the owner's S is only larger
-                    m[h] = __hge2_mask(v2[h], f2);
-                    anym |= m[h];
+                    acc[h] |= __hge2_mask(v2[h], f2) & rowbits;
                 }
             } else {
 #pragma unroll
@@ -423,11 +422,9 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
                     if (sm.colown[lane * CPL + 2 * h] == w) cr &= 0xffff0000u;
                     if (sm.colown[lane * CPL + 2 * h + 1] == w) cr &= 0x0000ffffu;
                     v2[h] = __hsub2(u2h2(row[h]), u2h2(cr));
-                    m[h] = __hge2_mask(v2[h], f2);
-                    anym |= m[h];
+                    acc[h] |= __hge2_mask(v2[h], f2) & rowbits;
                 }
             }
-            unsigned int rej = 0;                                            // bit e: tie at T_w that gets no bid
             if (do_bid) {                                                    // f2 == T_w in a BID pass
                 unsigned int anye = 0, em[NH2];
 #pragma unroll
@@ -451,7 +448,7 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
 #pragma unroll
                     for (int e = 0; e < CPL; ++e) {
                         if (eq[e]) {
-                            if (!((long long)(seen + before + mine) < quota)) rej |= 1u << e;
+                            if (!((long long)(seen + before + mine) < quota)) rej[e >> 1] |= 1u << ((e & 1) * 16 + i);
                             mine++;
                         }
                     }
@@ -460,77 +457,33 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
                     __syncwarp();
                 }
             }
-            if (anym) {
-                // one bit per surviving column of this lane
-                unsigned int bits = (m[0] & 1u) | ((m[0] >> 15) & 2u);
-                if (NH2 > 1) bits |= ((m[NH2 - 1] << 2) & 4u) | ((m[NH2 - 1] >> 13) & 8u);
-                do {
-                    const int e = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    if (cnt < AUC_CAPL) {
-                        my_list[cnt * AUC_THREADS] =
-                            (unsigned short)(((unsigned)w << 8) | ((unsigned)(lane * CPL + e) << 1) | ((rej >> e) & 1u));
-                        ++cnt;
-                    } else {
-                        cnt = AUC_CAPL + 1;                                  // overflow: the tile takes the direct path
-                    }
-                } while (bits);
-            }
         }
-        if (cnt > AUC_CAPL) s_direct = 1;
-        __syncthreads();                                                     // S2: overflow flag visible
-        const bool direct = s_direct != 0;
 
         if (do_bid) {
             // ---------------- stage A: survivors -> bids ----------------
-            auto bid_one = [&](int w, int col, bool rejected, bool flagged_row) {
-                const int o = sm.colown[col];
-                const bool own = (o == w);
-                if (own && !flagged_row) return;                             // the column thread did it
-                const __half s = tile[(size_t)w * J + col];
-                const __half v = own ? s : __hsub(s, __ushort_as_half(sm.colcost[col]));
-                const __half T = bits2h(sm.r_T2[w] & 0xffffu);
-                if (!(__hgt(v, T) || (__heq(v, T) && !rejected))) return;
-                if (fallback && w == 0 && o < 0) return;                     // :89 overrides worker 0's own bid
-                unsigned int bid = h2bits(__hadd(__hsub(v, T), eps));        // :76, two roundings
-                if (retain && own) bid = eps_bits;                           // :87
-                if (!own) sm.colviol[col] = 1;                               // fresh bid on a job the bidder does not own
-                atomicMax(&sm.colmax[col], (bid << 16) | (0xffffu - (unsigned)w));   // :104
-            };
-            if (!direct) {
-                const int n = cnt;
-                for (int i = 0; i < n; ++i) {
-                    const unsigned int e = my_list[i * AUC_THREADS];
-                    bid_one(e >> 8, (e >> 1) & 127, (e & 1u) != 0, sm.row_flag[e >> 8] != 0);
-                }
-            } else {
-                // a lane's list overflowed (degenerate / tie-heavy data): redo the tile without lists
-                for (int w = warp; w < K; w += AUC_NW) {
-                    const bool flagged = sm.row_flag[w] != 0;
+#pragma unroll
+            for (int h = 0; h < NH2; ++h) {
+                unsigned int a = acc[h];
+                while (a) {
+                    const int bpos = __ffs(a) - 1;
+                    a &= a - 1;
+                    const int i = bpos & 15;
+                    const int w = warp + AUC_NW * i, col = lane * CPL + 2 * h + (bpos >> 4);
+                    if (col >= ncols) continue;
+                    const int o = sm.colown[col];
+                    const bool own = (o == w);
+                    const bool flagged_row = (flagmask >> i) & 1u;
+                    if (own && !flagged_row) continue;                       // the column thread did it
+                    const __half sv = tile[(size_t)w * J + col];
+                    const __half v = own ? sv : __hsub(sv, __ushort_as_half(sm.colcost[col]));
                     const __half T = bits2h(sm.r_T2[w] & 0xffffu);
-                    bool eq[CPL];
-                    unsigned int before = 0, total = 0, mine = 0;
-#pragma unroll
-                    for (int e = 0; e < CPL; ++e) {
-                        const int cidx = lane * CPL + e;
-                        const bool own = sm.colown[cidx] == w;
-                        const __half s = tile[(size_t)w * J + cidx];
-                        const __half v = own ? s : __hsub(s, __ushort_as_half(sm.colcost[cidx]));
-                        eq[e] = cidx < ncols && __heq(v, T) && (flagged || !own);
-                        unsigned int mm = __ballot_sync(0xffffffffu, eq[e]);
-                        before += __popc(mm & lt);
-                        total += __popc(mm);
-                    }
-                    // this row's ties were already counted by the sweep: rank again from the tile's start state
-                    const unsigned int seen = sm.tie_seen[w] - total;
-                    const long long quota = sm.r_take[w];
-#pragma unroll
-                    for (int e = 0; e < CPL; ++e) {
-                        const int cidx = lane * CPL + e;
-                        bool rejected = false;
-                        if (eq[e]) { rejected = !((long long)(seen + before + mine) < quota); mine++; }
-                        if (cidx < ncols) bid_one(w, cidx, rejected, flagged);
-                    }
+                    const bool rejected = (rej[h] >> bpos) & 1u;
+                    if (!(__hgt(v, T) || (__heq(v, T) && !rejected))) continue;
+                    if (fallback && w == 0 && o < 0) continue;               // :89 overrides worker 0's own bid
+                    unsigned int bid = h2bits(__hadd(__hsub(v, T), eps));    // :76, two roundings
+                    if (retain && own) bid = eps_bits;                       // :87
+                    if (!own) sm.colviol[col] = 1;                           // fresh bid on a job the bidder does not own
+                    atomicMax(&sm.colmax[col], (bid << 16) | (0xffffu - (unsigned)w));   // :104
                 }
             }
             __syncthreads();                                                 // S3: all bids in colmax
@@ -566,7 +519,7 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
         } else {
             // ---------------- stage B: survivors -> histogram ----------------
             // owner entries (value = S) of rows with a placed window: one per job, by the column thread
-            if (tid < ncols && !direct) {
+            if (tid < ncols) {
                 const int o = sm.colown[tid];
                 if (o >= 0 && sm.r_base[o] > 0) {
                     const int rel = (int)h2key(h2bits(tile[(size_t)o * J + tid])) - sm.r_base[o];
@@ -577,12 +530,14 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
                     }
                 }
             }
-            if (!direct) {
-                const int n = cnt;
-                for (int i = 0; i < n; ++i) {
-                    const unsigned int e = my_list[i * AUC_THREADS];
-                    const int w = e >> 8, col = (e >> 1) & 127;
-                    if (sm.colown[col] == w) continue;                       // owner entry: done by the column thread
+#pragma unroll
+            for (int h = 0; h < NH2; ++h) {
+                unsigned int a = acc[h];
+                while (a) {
+                    const int bpos = __ffs(a) - 1;
+                    a &= a - 1;
+                    const int w = warp + AUC_NW * (bpos & 15), col = lane * CPL + 2 * h + (bpos >> 4);
+                    if (col >= ncols || sm.colown[col] == w) continue;       // owner entry: done by the column thread
                     const __half v = __hsub(tile[(size_t)w * J + col], __ushort_as_half(sm.colcost[col]));
                     const int rel = (int)h2key(h2bits(v)) - sm.r_base[w];
                     const int bin = rel >> sm.r_shift[w];
@@ -592,11 +547,11 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
                     }
                 }
             }
-            // cold rows (all keys in 128 coarse bins) and overflowed tiles: exact values, every element
-            if (any_cold || direct) {
+            // cold rows (all 65536 keys in 128 coarse bins): exact values, every element
+            if (any_cold) {
                 for (int w = warp; w < K; w += AUC_NW) {
                     const int base = sm.r_base[w];
-                    if (base > 0 && !direct) continue;
+                    if (base > 0) continue;
                     const int shift = sm.r_shift[w];
                     const unsigned* row = reinterpret_cast<const unsigned*>(tile + (size_t)w * J) + lane * NH2;
                     unsigned int nabove = 0;
@@ -629,7 +584,6 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
             }
         }
         __syncthreads();                                                     // S4: tile buffer + column state free
-        if (tid == 0) s_direct = 0;
     }
 
     if (do_bid) {
@@ -653,7 +607,7 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
 
 static inline size_t auction_pass_smem(int K, int J) {
     return (size_t)2 * K * J * 2 + (size_t)K * AUC_W * 2 + (size_t)K * 24 + (size_t)J * 4 +
-           (size_t)AUC_CAPL * AUC_THREADS * 2 + (size_t)J * 4 + (size_t)K * 2 + (size_t)J + 64;
+           (size_t)J * 4 + (size_t)K * 2 + (size_t)J + 64;
 }
 
 // ------------------------------------------------------------------------------------------
