@@ -80,14 +80,16 @@ struct AuctionPtrs {
     AuctionState* st;
     __half* cost;
     short* owner;
-    // "reduce block": contiguous int32 [K*W + K + 2]; the only per-pass data ranks must sum when the
-    // jobs are sharded over GPUs (hist_g | above_g | n_with | n_viol)
+    // "reduce block": contiguous int32 [K*W + 2K + 2]; the only per-pass data ranks must sum when the
+    // jobs are sharded over GPUs (hist_g | above_g | gap_g | n_with | n_viol)
     unsigned int* hist_g;     // [K][W]
-    unsigned int* above_g;    // [K]
+    unsigned int* above_g;    // [K] values above the window
+    unsigned int* gap_g;      // [K] values between the two halves of a split window
     unsigned int* n_with;     // [1] jobs with a bidder in the last BID pass
     unsigned int* n_viol;     // [1] frozen-condition violations in the last BID pass
     unsigned int* tie_total;  // [K] local number of values equal to the threshold (for the cross-rank prefix)
     int* win_base;            // [K] key of bin 0
+    int* win_hbase;           // [K] key of bin 64 (fine windows may be split in two 64-key halves; base+64 = contiguous)
     int* win_shift;           // [K] log2 keys per bin
     int* tkey;                // [K] resolved threshold key, -1 = unresolved
     int* take;                // [K] ties at the threshold that still get a bid
@@ -116,9 +118,10 @@ static inline size_t auction_ws_layout(long long N, long long ld, int K, Auction
     size_t o_st = take_(sizeof(AuctionState));
     size_t o_cost = take_((size_t)ld * 2);
     size_t o_own = take_((size_t)ld * 2);
-    size_t o_hist = take_(((size_t)K * AUC_W + K + 2) * 4);
+    size_t o_hist = take_(((size_t)K * AUC_W + 2 * K + 2) * 4);
     size_t o_tt = take_((size_t)K * 4);
     size_t o_wb = take_((size_t)K * 4);
+    size_t o_whb = take_((size_t)K * 4);
     size_t o_ws = take_((size_t)K * 4);
     size_t o_tk = take_((size_t)K * 4);
     size_t o_take = take_((size_t)K * 4);
@@ -133,10 +136,12 @@ static inline size_t auction_ws_layout(long long N, long long ld, int K, Auction
         p->owner = (short*)(base + o_own);
         p->hist_g = (unsigned int*)(base + o_hist);
         p->above_g = p->hist_g + (size_t)K * AUC_W;
-        p->n_with = p->above_g + K;
+        p->gap_g = p->above_g + K;
+        p->n_with = p->gap_g + K;
         p->n_viol = p->n_with + 1;
         p->tie_total = (unsigned int*)(base + o_tt);
         p->win_base = (int*)(base + o_wb);
+        p->win_hbase = (int*)(base + o_whb);
         p->win_shift = (int*)(base + o_ws);
         p->tkey = (int*)(base + o_tk);
         p->take = (int*)(base + o_take);
@@ -157,9 +162,10 @@ __global__ void auction_init_kernel(AuctionPtrs p, long long ld, int K, const un
         p.cost[j] = __ushort_as_half(0);
         p.owner[j] = -1;
     }
-    for (long long j = i; j < (long long)K * AUC_W + K + 2; j += stride) p.hist_g[j] = 0;
+    for (long long j = i; j < (long long)K * AUC_W + 2 * K + 2; j += stride) p.hist_g[j] = 0;
     for (long long j = i; j < K; j += stride) {
         p.win_base[j] = 0;
+        p.win_hbase[j] = 64;
         p.win_shift[j] = AUC_COLD_SHIFT;
         p.tkey[j] = -1;
         p.take[j] = 0;
@@ -204,6 +210,8 @@ struct PassSmem {
     unsigned int* tie_seen;    // [K]
     int* r_take;               // [K]
     int* r_base;               // [K]
+    int* r_hbase;              // [K]
+    unsigned int* gap;         // [K]
     unsigned int* r_T2;        // [K] threshold as a duplicated half2
     unsigned int* r_lo2;       // [K] sweep filter as a duplicated half2 (window low value; T for coarse rows)
     unsigned char* r_shift;    // [K]
@@ -216,6 +224,30 @@ struct PassSmem {
 
 __device__ __forceinline__ void hist_add(unsigned int* hist, int w, int bin, unsigned int n = 1) {
     atomicAdd(&hist[(w * AUC_W + bin) >> 1], n << ((bin & 1) * 16));
+}
+
+// Window geometry.  shift > 0: 128 contiguous bins of 2^shift keys from `base`.  shift == 0: one-key bins,
+// bins 0..63 = [base, base+64), bins 64..127 = [hbase, hbase+64), hbase >= base+64; keys in between are
+// counted in `gap`, keys above in `above`, keys below `base` are ignored.
+__device__ __forceinline__ void window_count(const PassSmem& sm, int w, int key) {
+    const int base = sm.r_base[w];
+    const int shift = sm.r_shift[w];
+    if (key < base) return;
+    if (shift == 0) {
+        const int hb = sm.r_hbase[w];
+        if (key >= hb) {
+            if (key - hb >= 64) atomicAdd(&sm.above[w], 1u);
+            else hist_add(sm.hist, w, 64 + key - hb);
+        } else if (key >= base + 64) {
+            atomicAdd(&sm.gap[w], 1u);
+        } else {
+            hist_add(sm.hist, w, key - base);
+        }
+    } else {
+        const int bin = (key - base) >> shift;
+        if (bin >= AUC_W) atomicAdd(&sm.above[w], 1u);
+        else hist_add(sm.hist, w, bin);
+    }
 }
 
 // ---- mbarrier + bulk-copy (UBLKCP) tile loads: one 16-byte-aligned row per instruction ----
@@ -272,6 +304,8 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
         sm.tie_seen = (unsigned int*)q;      q += (size_t)K * 4;
         sm.r_take = (int*)q;                 q += (size_t)K * 4;
         sm.r_base = (int*)q;                 q += (size_t)K * 4;
+        sm.r_hbase = (int*)q;                q += (size_t)K * 4;
+        sm.gap = (unsigned int*)q;           q += (size_t)K * 4;
         sm.r_T2 = (unsigned int*)q;          q += (size_t)K * 4;
         sm.r_lo2 = (unsigned int*)q;         q += (size_t)K * 4;
         sm.colmax = (unsigned int*)q;        q += (size_t)J * 4;
@@ -300,6 +334,8 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
         sm.r_take[i] = p.take[i];
         const int base = p.win_base[i], shift = p.win_shift[i];
         sm.r_base[i] = base;
+        sm.r_hbase[i] = p.win_hbase[i];
+        sm.gap[i] = 0;
         sm.r_shift[i] = (unsigned char)shift;
         // BID pass: the sweep finds bidders (v >= T).  HIST pass: rows with a placed window (sampled, slid,
         // refined: base > 0) are filtered at its low edge; cold rows (base == 0: all 65536 keys in 128 coarse
@@ -521,14 +557,7 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
             // owner entries (value = S) of rows with a placed window: one per job, by the column thread
             if (tid < ncols) {
                 const int o = sm.colown[tid];
-                if (o >= 0 && sm.r_base[o] > 0) {
-                    const int rel = (int)h2key(h2bits(tile[(size_t)o * J + tid])) - sm.r_base[o];
-                    const int bin = rel >> sm.r_shift[o];
-                    if (rel >= 0) {
-                        if (bin >= AUC_W) atomicAdd(&sm.above[o], 1u);
-                        else hist_add(sm.hist, o, bin);
-                    }
-                }
+                if (o >= 0 && sm.r_base[o] > 0) window_count(sm, o, (int)h2key(h2bits(tile[(size_t)o * J + tid])));
             }
 #pragma unroll
             for (int h = 0; h < NH2; ++h) {
@@ -539,12 +568,7 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
                     const int w = warp + AUC_NW * (bpos & 15), col = lane * CPL + 2 * h + (bpos >> 4);
                     if (col >= ncols || sm.colown[col] == w) continue;       // owner entry: done by the column thread
                     const __half v = __hsub(tile[(size_t)w * J + col], __ushort_as_half(sm.colcost[col]));
-                    const int rel = (int)h2key(h2bits(v)) - sm.r_base[w];
-                    const int bin = rel >> sm.r_shift[w];
-                    if (rel >= 0) {
-                        if (bin >= AUC_W) atomicAdd(&sm.above[w], 1u);
-                        else hist_add(sm.hist, w, bin);
-                    }
+                    window_count(sm, w, (int)h2key(h2bits(v)));
                 }
             }
             // cold rows (all 65536 keys in 128 coarse bins): exact values, every element
@@ -601,12 +625,14 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
         if (h & 0xffffu) atomicAdd(&p.hist_g[2 * i], h & 0xffffu);
         if (h >> 16) atomicAdd(&p.hist_g[2 * i + 1], h >> 16);
     }
-    for (int i = tid; i < K; i += AUC_THREADS)
+    for (int i = tid; i < K; i += AUC_THREADS) {
         if (sm.above[i]) atomicAdd(&p.above_g[i], sm.above[i]);
+        if (sm.gap[i]) atomicAdd(&p.gap_g[i], sm.gap[i]);
+    }
 }
 
 static inline size_t auction_pass_smem(int K, int J) {
-    return (size_t)2 * K * J * 2 + (size_t)K * AUC_W * 2 + (size_t)K * 24 + (size_t)J * 4 +
+    return (size_t)2 * K * J * 2 + (size_t)K * AUC_W * 2 + (size_t)K * 32 + (size_t)J * 4 +
            (size_t)J * 4 + (size_t)K * 2 + (size_t)J + 64;
 }
 
@@ -666,13 +692,29 @@ auction_sample_kernel(const __half* __restrict__ S, long long ld, long long N, i
         if (r_hi < 0) r_hi = 0;
         if (r_lo > ns - 1) r_lo = ns - 1;
         int lo = (int)keys[r_lo] - 1, hi = (int)keys[r_hi] + 1;
-        if (r_hi == 0) hi += 64;                                            // the sample's maximum is no bound
+        if (r_hi == 0) hi += 32;                                            // the sample's maximum is no bound
         if (lo < AUC_MIN_KEY) lo = AUC_MIN_KEY;
         if (hi < lo + 8) hi = lo + 8;
-        int span = hi - lo + 1, shift = 0;
-        while ((span >> shift) > AUC_W) ++shift;
-        if (shift == 0 && lo > 65536 - AUC_W) lo = 65536 - AUC_W;
+        if (hi > 65535) hi = 65535;
+        int span = hi - lo + 1, shift = 0, hb = lo + 64;
+        if (span > AUC_W) {
+            // the candidates usually form two clumps (the worker's owned jobs at their full score, everything
+            // else one or more cost steps lower): put 64 one-key bins on each, provided no sampled candidate
+            // falls in between; otherwise coarser bins and a refine pass
+            const int hb2 = hi - 63;
+            bool clean = true;
+            for (long long q = r_hi; q <= r_lo; ++q) {
+                const int kq = keys[q];
+                if (kq >= lo + 64 && kq < hb2) { clean = false; break; }
+            }
+            if (clean) hb = hb2;
+            else {
+                while ((span >> shift) > AUC_W) ++shift;
+            }
+        }
+        if (shift == 0 && hb == lo + 64 && lo > 65536 - AUC_W) { lo = 65536 - AUC_W; hb = lo + 64; }
         p.win_base[w] = lo;
+        p.win_hbase[w] = hb;
         p.win_shift[w] = shift;
     }
 }
@@ -722,6 +764,7 @@ auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
     if (was_bid) {
         for (int w = tid; w < K; w += 1024) {
             p.win_base[w] = 0;
+            p.win_hbase[w] = 64;
             p.win_shift[w] = AUC_COLD_SHIFT;
             p.tkey[w] = -1;
             p.miss_run[w] = 0;
@@ -730,6 +773,8 @@ auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
     } else if (!jump) {
         for (int w = warp; w < K; w += 32) {
             const int base = p.win_base[w], shift = p.win_shift[w];
+            const int hbase = p.win_hbase[w];
+            const unsigned long long gap = (shift == 0) ? p.gap_g[w] : 0ull;
             unsigned int h[4];
             unsigned int lsum = 0;
 #pragma unroll
@@ -742,11 +787,14 @@ auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
                 if (lane + d < 32) suf += o;
             }
             const unsigned long long ab = p.above_g[w];
-            unsigned long long cum_excl = ab + (suf - lsum);      // strictly above my 4 bins
-            const unsigned long long total = ab + __shfl_sync(0xffffffffu, suf, 0);
+            // strictly above my 4 bins (the gap of a split window sits between bins 63 and 64)
+            unsigned long long cum_excl = ab + (suf - lsum) + (lane < 16 ? gap : 0ull);
+            const unsigned long long total = ab + __shfl_sync(0xffffffffu, suf, 0) + gap;
+            const unsigned long long c_hi = ab + __shfl_sync(0xffffffffu, suf, 16);   // everything >= hbase
+            const bool in_gap = gap > 0 && c_hi < (unsigned long long)need && c_hi + gap >= (unsigned long long)need;
             int found_bin = -1;
             unsigned long long g_above = 0;
-            if (ab < (unsigned long long)need && total >= (unsigned long long)need) {
+            if (!in_gap && ab < (unsigned long long)need && total >= (unsigned long long)need) {
                 unsigned long long c = cum_excl;
 #pragma unroll
                 for (int i = 3; i >= 0; --i) {
@@ -765,28 +813,42 @@ auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
                 if (lane == 0) {
                     p.miss_run[w] = 0;
                     if (shift == 0) {
-                        p.tkey[w] = base + found_bin;
+                        p.tkey[w] = found_bin >= 64 ? hbase + found_bin - 64 : base + found_bin;
                         p.take[w] = (int)(jpw - (long long)g_above);
                     } else {   // refine inside the bin that holds the threshold
                         int nshift = shift >= 7 ? shift - 7 : 0;
-                        p.win_base[w] = base + (found_bin << shift);
+                        const int nb2 = base + (found_bin << shift);
+                        p.win_base[w] = nb2;
+                        p.win_hbase[w] = nb2 + 64;
                         p.win_shift[w] = nshift;
                         p.tkey[w] = -1;
                         atomicAdd(&s_unresolved, 1);
                     }
                 }
+            } else if (lane == 0 && in_gap) {
+                // the threshold lies between the two halves of a split window: histogram just that range
+                int nb2 = base + 64, span = hbase - nb2, nshift = 0;
+                while ((span >> nshift) > AUC_W) ++nshift;
+                p.win_base[w] = nb2;
+                p.win_hbase[w] = nb2 + 64;
+                p.win_shift[w] = nshift;
+                p.tkey[w] = -1;
+                atomicAdd(&s_unresolved, 1);
+                atomicAdd(&s_miss, 1);
             } else if (lane == 0) {
                 // the window missed the threshold: slide one window up / down, restart coarse if that
                 // keeps failing (or if the window was a refinement, which cannot miss by construction)
                 const int run = p.miss_run[w];
                 const bool is_above = ab >= (unsigned long long)need;
-                int nb = is_above ? base + (AUC_W << shift) : base - (AUC_W << shift);
+                int nb = is_above ? (shift == 0 ? hbase + 64 : base + (AUC_W << shift)) : base - (AUC_W << shift);
                 if (shift != 0 || run >= 2 || nb < AUC_MIN_KEY || nb > 65536 - AUC_W) {
                     p.win_base[w] = 0;
+                    p.win_hbase[w] = 64;
                     p.win_shift[w] = AUC_COLD_SHIFT;
                     p.miss_run[w] = 0;
                 } else {
                     p.win_base[w] = nb;
+                    p.win_hbase[w] = nb + 64;
                     p.miss_run[w] = run + 1;
                 }
                 p.tkey[w] = -1;
@@ -797,7 +859,7 @@ auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
     }
     __syncthreads();
     // ---- 3. zero the merged histograms for the next pass ----
-    for (int i = tid; i < K * AUC_W + K + 2; i += 1024) p.hist_g[i] = 0;
+    for (int i = tid; i < K * AUC_W + 2 * K + 2; i += 1024) p.hist_g[i] = 0;
     __syncthreads();
     if (tid == 0) {
         s.passes += 1;
@@ -826,9 +888,9 @@ auction_tieprefix_kernel(AuctionPtrs p, int K, int G) {
     if (p.st->mode != MODE_BID) return;
     const int w = blockIdx.x, tid = threadIdx.x;
     __shared__ unsigned int cnt[AUC_MAX_CTAS];
-    const int base = p.win_base[w];
+    const int base = p.win_base[w], hbase = p.win_hbase[w];
     const int tk = p.tkey[w];
-    const int bin = tk - base;   // shift is 0 when resolved
+    const int bin = tk >= hbase ? 64 + tk - hbase : tk - base;   // shift is 0 when resolved
     unsigned int c = 0;
     if (tid < G) c = p.hist_cta[((size_t)tid * K + w) * AUC_W + bin];
     cnt[tid] = c;
@@ -890,7 +952,7 @@ extern "C" {
 struct rqk_auction_layout {
     int64_t total_bytes;        // workspace size
     int64_t reduce_offset;      // byte offset of the int32 reduce block (sum over ranks after every pass)
-    int64_t reduce_count;       // its length in int32 elements: k*128 + k + 2
+    int64_t reduce_count;       // its length in int32 elements: k*128 + 2k + 2
     int64_t tie_total_offset;   // byte offset of int32[k]: local ties at the threshold (allgather after resolve)
 };
 
@@ -913,7 +975,7 @@ int rqk_auction_layout_query(int64_t n, int32_t k, rqk_auction_layout* out) {
     size_t ro = 0, to = 0;
     out->total_bytes = (int64_t)auction_ws_layout(n, ld, k, nullptr, nullptr, &ro, &to);
     out->reduce_offset = (int64_t)ro;
-    out->reduce_count = (int64_t)k * AUC_W + k + 2;
+    out->reduce_count = (int64_t)k * AUC_W + 2 * k + 2;
     out->tie_total_offset = (int64_t)to;
     return 0;
 }
