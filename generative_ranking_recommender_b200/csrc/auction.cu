@@ -89,7 +89,8 @@ struct AuctionPtrs {
     unsigned int* n_viol;     // [1] frozen-condition violations in the last BID pass
     unsigned int* tie_total;  // [K] local number of values equal to the threshold (for the cross-rank prefix)
     int* win_base;            // [K] key of bin 0
-    int* win_hbase;           // [K] key of bin 64 (fine windows may be split in two 64-key halves; base+64 = contiguous)
+    int* win_hbase;           // [K] fine windows may be split in two runs of one-key bins: [base, base+nlo) and
+    int* win_nlo;             // [K] [hbase, hbase+128-nlo); contiguous = (base, base+64, 64)
     int* win_shift;           // [K] log2 keys per bin
     int* tkey;                // [K] resolved threshold key, -1 = unresolved
     int* take;                // [K] ties at the threshold that still get a bid
@@ -122,6 +123,7 @@ static inline size_t auction_ws_layout(long long N, long long ld, int K, Auction
     size_t o_tt = take_((size_t)K * 4);
     size_t o_wb = take_((size_t)K * 4);
     size_t o_whb = take_((size_t)K * 4);
+    size_t o_wnl = take_((size_t)K * 4);
     size_t o_ws = take_((size_t)K * 4);
     size_t o_tk = take_((size_t)K * 4);
     size_t o_take = take_((size_t)K * 4);
@@ -142,6 +144,7 @@ static inline size_t auction_ws_layout(long long N, long long ld, int K, Auction
         p->tie_total = (unsigned int*)(base + o_tt);
         p->win_base = (int*)(base + o_wb);
         p->win_hbase = (int*)(base + o_whb);
+        p->win_nlo = (int*)(base + o_wnl);
         p->win_shift = (int*)(base + o_ws);
         p->tkey = (int*)(base + o_tk);
         p->take = (int*)(base + o_take);
@@ -166,6 +169,7 @@ __global__ void auction_init_kernel(AuctionPtrs p, long long ld, int K, const un
     for (long long j = i; j < K; j += stride) {
         p.win_base[j] = 0;
         p.win_hbase[j] = 64;
+        p.win_nlo[j] = 64;
         p.win_shift[j] = AUC_COLD_SHIFT;
         p.tkey[j] = -1;
         p.take[j] = 0;
@@ -211,6 +215,7 @@ struct PassSmem {
     int* r_take;               // [K]
     int* r_base;               // [K]
     int* r_hbase;              // [K]
+    int* r_nlo;                // [K]
     unsigned int* gap;         // [K]
     unsigned int* r_T2;        // [K] threshold as a duplicated half2
     unsigned int* r_lo2;       // [K] sweep filter as a duplicated half2 (window low value; T for coarse rows)
@@ -227,18 +232,18 @@ __device__ __forceinline__ void hist_add(unsigned int* hist, int w, int bin, uns
 }
 
 // Window geometry.  shift > 0: 128 contiguous bins of 2^shift keys from `base`.  shift == 0: one-key bins,
-// bins 0..63 = [base, base+64), bins 64..127 = [hbase, hbase+64), hbase >= base+64; keys in between are
-// counted in `gap`, keys above in `above`, keys below `base` are ignored.
+// bins 0..nlo-1 = [base, base+nlo), bins nlo..127 = [hbase, hbase+128-nlo), hbase >= base+nlo; keys in
+// between are counted in `gap`, keys above in `above`, keys below `base` are ignored.
 __device__ __forceinline__ void window_count(const PassSmem& sm, int w, int key) {
     const int base = sm.r_base[w];
     const int shift = sm.r_shift[w];
     if (key < base) return;
     if (shift == 0) {
-        const int hb = sm.r_hbase[w];
+        const int hb = sm.r_hbase[w], nlo = sm.r_nlo[w];
         if (key >= hb) {
-            if (key - hb >= 64) atomicAdd(&sm.above[w], 1u);
-            else hist_add(sm.hist, w, 64 + key - hb);
-        } else if (key >= base + 64) {
+            if (key - hb >= AUC_W - nlo) atomicAdd(&sm.above[w], 1u);
+            else hist_add(sm.hist, w, nlo + key - hb);
+        } else if (key >= base + nlo) {
             atomicAdd(&sm.gap[w], 1u);
         } else {
             hist_add(sm.hist, w, key - base);
@@ -285,9 +290,9 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
     constexpr int MAXR = 256 / AUC_NW * (J == 128 ? 1 : 2) / 2;   // rows per warp: 8 (K<=128) / 16 (K<=256)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const AuctionState st = *p.st;
-    if (st.mode == MODE_DONE) return;
-    const bool do_bid = (st.mode == MODE_BID);
-    const int ff = do_bid ? 0 : st.ff_pending;
+    if (st.mode != MODE_BID) return;                   // HIST passes run in auction_hist_kernel
+    const bool do_bid = true;
+    const int ff = 0;
     const int counter = st.counter;
     const __half eps = bits2h(st.eps_bits);
     const unsigned int eps_bits = st.eps_bits;
@@ -305,6 +310,7 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
         sm.r_take = (int*)q;                 q += (size_t)K * 4;
         sm.r_base = (int*)q;                 q += (size_t)K * 4;
         sm.r_hbase = (int*)q;                q += (size_t)K * 4;
+        sm.r_nlo = (int*)q;                  q += (size_t)K * 4;
         sm.gap = (unsigned int*)q;           q += (size_t)K * 4;
         sm.r_T2 = (unsigned int*)q;          q += (size_t)K * 4;
         sm.r_lo2 = (unsigned int*)q;         q += (size_t)K * 4;
@@ -335,6 +341,7 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
         const int base = p.win_base[i], shift = p.win_shift[i];
         sm.r_base[i] = base;
         sm.r_hbase[i] = p.win_hbase[i];
+        sm.r_nlo[i] = p.win_nlo[i];
         sm.gap[i] = 0;
         sm.r_shift[i] = (unsigned char)shift;
         // BID pass: the sweep finds bidders (v >= T).  HIST pass: rows with a placed window (sampled, slid,
@@ -631,8 +638,182 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// HIST pass as a tile-free streaming kernel.  A HIST pass needs no column maximum, so nothing forces
+// the K rows of a job through shared memory together: every warp streams row segments straight from
+// global memory with 16-byte loads, four in flight per lane, which hides HBM latency far better than a
+// double-buffered tile.  Per 8 jobs of a row: 1 LDG.128, 1 LDS.128 (costs), 4 HSUB2, 4 HSET2, 4 LOP3.
+// Survivors are recorded as register bitmasks and histogrammed afterwards.
+// CTA b owns exactly the job range CTA b of the tiled BID kernel owns (the per-CTA dumps feed its tie prefix).
+// ------------------------------------------------------------------------------------------
+constexpr int HS_SUB = 4096;      // jobs staged (cost, owner) per sub-range
+
+__device__ __forceinline__ uint4 ldg_stream128(const void* ptr) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(ptr));
+    return r;
+}
+
+__global__ void __launch_bounds__(AUC_THREADS, 2)
+auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int K, int J, AuctionPtrs p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const AuctionState st = *p.st;
+    if (st.mode != MODE_HIST) return;
+    const int ff = st.ff_pending;
+    const __half eps = bits2h(st.eps_bits);
+
+    PassSmem sm;
+    unsigned short* cost_s;
+    short* own_s;
+    {
+        unsigned char* q = smem_raw;
+        sm.hist = (unsigned int*)q;          q += (size_t)K * AUC_W * 2;
+        cost_s = (unsigned short*)q;         q += (size_t)HS_SUB * 2;
+        own_s = (short*)q;                   q += (size_t)HS_SUB * 2;
+        sm.above = (unsigned int*)q;         q += (size_t)K * 4;
+        sm.gap = (unsigned int*)q;           q += (size_t)K * 4;
+        sm.r_base = (int*)q;                 q += (size_t)K * 4;
+        sm.r_hbase = (int*)q;                q += (size_t)K * 4;
+        sm.r_nlo = (int*)q;                  q += (size_t)K * 4;
+        sm.r_lo2 = (unsigned int*)q;         q += (size_t)K * 4;
+        sm.r_shift = (unsigned char*)q;      q += (size_t)K;
+    }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, b = blockIdx.x;
+    const long long tiles_total = (N + J - 1) / J;
+    const long long c_begin = (tiles_total * b / G) * J;
+    long long c_end = (tiles_total * (b + 1) / G) * J;
+    if (c_end > N) c_end = N;
+
+    for (int i = tid; i < K * AUC_W / 2; i += AUC_THREADS) sm.hist[i] = 0;
+    for (int i = tid; i < K; i += AUC_THREADS) {
+        sm.above[i] = 0;
+        sm.gap[i] = 0;
+        const int base = p.win_base[i];
+        sm.r_base[i] = base;
+        sm.r_hbase[i] = p.win_hbase[i];
+        sm.r_nlo[i] = p.win_nlo[i];
+        sm.r_shift[i] = (unsigned char)p.win_shift[i];
+        const unsigned int lob = base > 0 ? key2h((unsigned)base) : 0x7c00u;   // cold rows: direct path below
+        sm.r_lo2[i] = lob | (lob << 16);
+    }
+    __syncthreads();
+
+    for (long long sub = c_begin; sub < c_end; sub += HS_SUB) {
+        const int sublen = (int)((c_end - sub) < HS_SUB ? (c_end - sub) : HS_SUB);
+        // ---- stage costs / owners of the sub-range (retain fast-forward applied here, once) ----
+        for (int i = tid; i < HS_SUB; i += AUC_THREADS) {
+            unsigned short c = 0;
+            short o = -1;
+            if (i < sublen) {
+                __half ch = p.cost[sub + i];
+                o = p.owner[sub + i];
+                if (ff > 0 && o >= 0) {
+                    for (int r = 0; r < ff; ++r) ch = __hadd(ch, eps);
+                    p.cost[sub + i] = ch;
+                }
+                c = __half_as_ushort(ch);
+            }
+            cost_s[i] = c;
+            own_s[i] = o;
+        }
+        __syncthreads();
+        // ---- owner entries (value = S): one per job ----
+        for (int i = tid; i < sublen; i += AUC_THREADS) {
+            const int o = own_s[i];
+            if (o >= 0 && sm.r_base[o] > 0)
+                window_count(sm, o, (int)h2key(h2bits(S[(size_t)o * ld + sub + i])));
+        }
+        // ---- the sweep: rows of this warp, 4 x 256 jobs per step ----
+        for (int w = warp; w < K; w += AUC_NW) {
+            const __half* srow = S + (size_t)w * ld + sub;
+            if (sm.r_base[w] > 0) {
+                const __half2 f2 = u2h2(sm.r_lo2[w]);
+                for (int c0 = 0; c0 < sublen; c0 += 1024) {
+                    uint4 sv[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int cc = c0 + q * 256 + lane * 8;
+                        if (cc < sublen) sv[q] = ldg_stream128(srow + cc);       // ld is a multiple of 128: in bounds
+                        else sv[q] = make_uint4(0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u);
+                    }
+                    unsigned int acc = 0;   // low half bit 4q+h: job 2h of load q survives; high half: job 2h+1
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int cc = c0 + q * 256 + lane * 8;
+                        const uint4 cv = (cc < HS_SUB) ? *reinterpret_cast<const uint4*>(cost_s + cc) : make_uint4(0, 0, 0, 0);
+                        const unsigned int sw[4] = {sv[q].x, sv[q].y, sv[q].z, sv[q].w};
+                        const unsigned int cw[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            const __half2 v2 = __hsub2(u2h2(sw[h]), u2h2(cw[h]));
+                            acc |= __hge2_mask(v2, f2) & ((1u << (4 * q + h)) | (1u << (16 + 4 * q + h)));
+                        }
+                    }
+                    while (acc) {
+                        const int bpos = __ffs(acc) - 1;
+                        acc &= acc - 1;
+                        const int pq = bpos & 15;
+                        const int cc = c0 + (pq >> 2) * 256 + lane * 8 + 2 * (pq & 3) + (bpos >> 4);
+                        if (cc >= sublen || own_s[cc] == w) continue;            // owner entry: counted above
+                        const __half v = __hsub(srow[cc], __ushort_as_half(cost_s[cc]));
+                        window_count(sm, w, (int)h2key(h2bits(v)));
+                    }
+                }
+            } else {
+                // cold row (all 65536 keys in 128 coarse bins): exact values, every element
+                const int shift = sm.r_shift[w];
+                for (int c0 = 0; c0 < sublen; c0 += 32) {
+                    const int cc = c0 + lane;
+                    const bool valid = cc < sublen;
+                    __half v = __ushort_as_half(0xfc00);
+                    if (valid) {
+                        const __half sx = srow[cc];
+                        v = (own_s[cc] == w) ? sx : __hsub(sx, __ushort_as_half(cost_s[cc]));
+                    }
+                    const int bin = (int)h2key(h2bits(v)) >> shift;
+                    const bool hb = valid && bin < AUC_W;
+                    const bool ab = valid && bin >= AUC_W;
+                    unsigned int na = __popc(__ballot_sync(0xffffffffu, ab));
+                    if (lane == 0 && na) atomicAdd(&sm.above[w], na);
+                    unsigned int act = __ballot_sync(0xffffffffu, hb);
+                    if (act) {
+                        int lead = __ffs(act) - 1;
+                        int lbin = __shfl_sync(0xffffffffu, bin, lead);
+                        unsigned int same = __ballot_sync(0xffffffffu, hb && bin == lbin);
+                        if (same == act) {
+                            if (lane == lead) hist_add(sm.hist, w, lbin, __popc(act));
+                        } else if (hb) {
+                            hist_add(sm.hist, w, bin);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- publish: per-CTA dump (for the tie prefix) + merge of non-empty bins ----
+    unsigned int* dump = reinterpret_cast<unsigned int*>(p.hist_cta + (size_t)b * K * AUC_W);
+    for (int i = tid; i < K * AUC_W / 2; i += AUC_THREADS) {
+        unsigned int h = sm.hist[i];
+        dump[i] = h;
+        if (h & 0xffffu) atomicAdd(&p.hist_g[2 * i], h & 0xffffu);
+        if (h >> 16) atomicAdd(&p.hist_g[2 * i + 1], h >> 16);
+    }
+    for (int i = tid; i < K; i += AUC_THREADS) {
+        if (sm.above[i]) atomicAdd(&p.above_g[i], sm.above[i]);
+        if (sm.gap[i]) atomicAdd(&p.gap_g[i], sm.gap[i]);
+    }
+}
+
+static inline size_t auction_hist_smem(int K) {
+    return (size_t)K * AUC_W * 2 + (size_t)HS_SUB * 4 + (size_t)K * 25 + 64;
+}
+
 static inline size_t auction_pass_smem(int K, int J) {
-    return (size_t)2 * K * J * 2 + (size_t)K * AUC_W * 2 + (size_t)K * 32 + (size_t)J * 4 +
+    return (size_t)2 * K * J * 2 + (size_t)K * AUC_W * 2 + (size_t)K * 36 + (size_t)J * 4 +
            (size_t)J * 4 + (size_t)K * 2 + (size_t)J + 64;
 }
 
@@ -696,25 +877,42 @@ auction_sample_kernel(const __half* __restrict__ S, long long ld, long long N, i
         if (lo < AUC_MIN_KEY) lo = AUC_MIN_KEY;
         if (hi < lo + 8) hi = lo + 8;
         if (hi > 65535) hi = 65535;
-        int span = hi - lo + 1, shift = 0, hb = lo + 64;
+        int span = hi - lo + 1, shift = 0, hb = lo + 64, nlo = 64;
         if (span > AUC_W) {
             // the candidates usually form two clumps (the worker's owned jobs at their full score, everything
-            // else one or more cost steps lower): put 64 one-key bins on each, provided no sampled candidate
-            // falls in between; otherwise coarser bins and a refine pass
-            const int hb2 = hi - 63;
-            bool clean = true;
-            for (long long q = r_hi; q <= r_lo; ++q) {
-                const int kq = keys[q];
-                if (kq >= lo + 64 && kq < hb2) { clean = false; break; }
+            // else one or more cost steps lower): cut the window at the widest hole between consecutive
+            // sampled candidates and spend the 128 one-key bins on the two sides; keys inside the hole are
+            // counted in `gap`.  If the two sides do not fit: coarser bins and a refine pass.
+            long long cut = -1;
+            int hole = 0;
+            for (long long q = r_hi; q < r_lo; ++q) {
+                const int d = (int)keys[q] - (int)keys[q + 1];
+                if (d > hole) { hole = d; cut = q; }
             }
-            if (clean) hb = hb2;
-            else {
+            bool ok = false;
+            if (cut >= 0) {
+                const int up_lo = keys[cut], dn_hi = keys[cut + 1];       // hole = (dn_hi, up_lo)
+                const int need_up = hi - up_lo + 1, need_dn = dn_hi - lo + 1;
+                if (need_up + need_dn <= AUC_W && need_up >= 1 && need_dn >= 1) {
+                    int spare = AUC_W - need_up - need_dn;
+                    const int room = up_lo - dn_hi - 1;                    // keys strictly inside the hole
+                    if (spare > room) spare = room;
+                    const int ext_dn = spare / 2, ext_up = spare - ext_dn; // margins into the hole
+                    nlo = need_dn + ext_dn;
+                    hb = up_lo - ext_up;
+                    ok = true;
+                }
+            }
+            if (!ok) {
                 while ((span >> shift) > AUC_W) ++shift;
+                hb = lo + 64;
+                nlo = 64;
             }
         }
-        if (shift == 0 && hb == lo + 64 && lo > 65536 - AUC_W) { lo = 65536 - AUC_W; hb = lo + 64; }
+        if (shift == 0 && nlo == 64 && hb == lo + 64 && lo > 65536 - AUC_W) { lo = 65536 - AUC_W; hb = lo + 64; }
         p.win_base[w] = lo;
         p.win_hbase[w] = hb;
+        p.win_nlo[w] = nlo;
         p.win_shift[w] = shift;
     }
 }
@@ -765,6 +963,7 @@ auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
         for (int w = tid; w < K; w += 1024) {
             p.win_base[w] = 0;
             p.win_hbase[w] = 64;
+            p.win_nlo[w] = 64;
             p.win_shift[w] = AUC_COLD_SHIFT;
             p.tkey[w] = -1;
             p.miss_run[w] = 0;
@@ -773,7 +972,7 @@ auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
     } else if (!jump) {
         for (int w = warp; w < K; w += 32) {
             const int base = p.win_base[w], shift = p.win_shift[w];
-            const int hbase = p.win_hbase[w];
+            const int hbase = p.win_hbase[w], nlo = (shift == 0) ? p.win_nlo[w] : 0;
             const unsigned long long gap = (shift == 0) ? p.gap_g[w] : 0ull;
             unsigned int h[4];
             unsigned int lsum = 0;
@@ -787,10 +986,15 @@ auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
                 if (lane + d < 32) suf += o;
             }
             const unsigned long long ab = p.above_g[w];
-            // strictly above my 4 bins (the gap of a split window sits between bins 63 and 64)
-            unsigned long long cum_excl = ab + (suf - lsum) + (lane < 16 ? gap : 0ull);
+            // strictly above my 4 bins (the gap of a split window sits between bins nlo-1 and nlo)
+            unsigned long long cum_excl = ab + (suf - lsum) + ((4 * lane + 3) < nlo ? gap : 0ull);
             const unsigned long long total = ab + __shfl_sync(0xffffffffu, suf, 0) + gap;
-            const unsigned long long c_hi = ab + __shfl_sync(0xffffffffu, suf, 16);   // everything >= hbase
+            unsigned int hsum = 0;                                    // my bins of the upper run
+#pragma unroll
+            for (int i = 0; i < 4; ++i) hsum += (4 * lane + i >= nlo) ? h[i] : 0u;
+#pragma unroll
+            for (int d = 16; d; d >>= 1) hsum += __shfl_xor_sync(0xffffffffu, hsum, d);
+            const unsigned long long c_hi = ab + hsum;               // everything >= hbase
             const bool in_gap = gap > 0 && c_hi < (unsigned long long)need && c_hi + gap >= (unsigned long long)need;
             int found_bin = -1;
             unsigned long long g_above = 0;
@@ -798,6 +1002,7 @@ auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
                 unsigned long long c = cum_excl;
 #pragma unroll
                 for (int i = 3; i >= 0; --i) {
+                    if (i != 3 && 4 * lane + i == nlo - 1) c += gap;      // stepping over the gap inside my 4 bins
                     if (found_bin < 0 && c < (unsigned long long)need && c + h[i] >= (unsigned long long)need) {
                         found_bin = lane * 4 + i;
                         g_above = c;
@@ -813,13 +1018,15 @@ auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
                 if (lane == 0) {
                     p.miss_run[w] = 0;
                     if (shift == 0) {
-                        p.tkey[w] = found_bin >= 64 ? hbase + found_bin - 64 : base + found_bin;
+                        p.tkey[w] = found_bin >= nlo ? hbase + found_bin - nlo : base + found_bin;
                         p.take[w] = (int)(jpw - (long long)g_above);
                     } else {   // refine inside the bin that holds the threshold
                         int nshift = shift >= 7 ? shift - 7 : 0;
                         const int nb2 = base + (found_bin << shift);
                         p.win_base[w] = nb2;
                         p.win_hbase[w] = nb2 + 64;
+                p.win_nlo[w] = 64;
+                        p.win_nlo[w] = 64;
                         p.win_shift[w] = nshift;
                         p.tkey[w] = -1;
                         atomicAdd(&s_unresolved, 1);
@@ -827,10 +1034,11 @@ auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
                 }
             } else if (lane == 0 && in_gap) {
                 // the threshold lies between the two halves of a split window: histogram just that range
-                int nb2 = base + 64, span = hbase - nb2, nshift = 0;
+                int nb2 = base + nlo, span = hbase - nb2, nshift = 0;
                 while ((span >> nshift) > AUC_W) ++nshift;
                 p.win_base[w] = nb2;
                 p.win_hbase[w] = nb2 + 64;
+                p.win_nlo[w] = 64;
                 p.win_shift[w] = nshift;
                 p.tkey[w] = -1;
                 atomicAdd(&s_unresolved, 1);
@@ -840,15 +1048,18 @@ auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
                 // keeps failing (or if the window was a refinement, which cannot miss by construction)
                 const int run = p.miss_run[w];
                 const bool is_above = ab >= (unsigned long long)need;
-                int nb = is_above ? (shift == 0 ? hbase + 64 : base + (AUC_W << shift)) : base - (AUC_W << shift);
+                int nb = is_above ? (shift == 0 ? hbase + (AUC_W - nlo) : base + (AUC_W << shift)) : base - (AUC_W << shift);
                 if (shift != 0 || run >= 2 || nb < AUC_MIN_KEY || nb > 65536 - AUC_W) {
                     p.win_base[w] = 0;
                     p.win_hbase[w] = 64;
+                    p.win_nlo[w] = 64;
+            p.win_nlo[w] = 64;
                     p.win_shift[w] = AUC_COLD_SHIFT;
                     p.miss_run[w] = 0;
                 } else {
                     p.win_base[w] = nb;
                     p.win_hbase[w] = nb + 64;
+                    p.win_nlo[w] = 64;
                     p.miss_run[w] = run + 1;
                 }
                 p.tkey[w] = -1;
@@ -890,7 +1101,8 @@ auction_tieprefix_kernel(AuctionPtrs p, int K, int G) {
     __shared__ unsigned int cnt[AUC_MAX_CTAS];
     const int base = p.win_base[w], hbase = p.win_hbase[w];
     const int tk = p.tkey[w];
-    const int bin = tk >= hbase ? 64 + tk - hbase : tk - base;   // shift is 0 when resolved
+    const int nlo = p.win_nlo[w];
+    const int bin = tk >= hbase ? nlo + tk - hbase : tk - base;   // shift is 0 when resolved
     unsigned int c = 0;
     if (tid < G) c = p.hist_cta[((size_t)tid * K + w) * AUC_W + bin];
     cnt[tid] = c;
@@ -1018,6 +1230,15 @@ int rqk_auction_pass(const void* scores_t, int64_t ld, int64_t n, int32_t k, int
     }
     if (n_global == n)   // sampled windows need the whole job set on this GPU (ranks must agree on the windows)
         auction_sample_kernel<<<k, 1024, 0, (cudaStream_t)stream_>>>((const __half*)scores_t, ld, n, k, n_global / k, a.p);
+    {
+        static size_t hs_set = 0;
+        const size_t hs = auction_hist_smem(k);
+        if (hs > hs_set) {
+            RQK_CUDA_OK(cudaFuncSetAttribute(auction_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
+            hs_set = hs;
+        }
+        auction_hist_kernel<<<a.G, AUC_THREADS, hs, (cudaStream_t)stream_>>>((const __half*)scores_t, ld, n, k, a.J, a.p);
+    }
     kern<<<a.G, AUC_THREADS, a.smem, (cudaStream_t)stream_>>>((const __half*)scores_t, ld, n, k, n_global / k, a.p);
     RQK_LAUNCH_OK();
     return 0;
