@@ -47,14 +47,17 @@
 
 namespace rqk {
 
-constexpr int AUC_W = 128;         // histogram bins per worker
+constexpr int AUC_W = 256;         // histogram bins per worker
+constexpr int AUC_HALF = AUC_W / 2;
+constexpr int AUC_NBUF = 3;        // tile buffers of the BID kernel
+constexpr int AUC_BPL = AUC_W / 32; // bins per lane in the resolve kernel
 constexpr int AUC_NW = 16;         // warps per CTA
 constexpr int AUC_THREADS = AUC_NW * 32;
 constexpr int AUC_BASE_CTAS = 296; // 2 per SM
 constexpr int AUC_MAX_CTAS = 1024; // tie-prefix kernel limit
 constexpr int AUC_MAX_JOBS_PER_CTA = 65024;   // 16-bit per-CTA counters
 constexpr int AUC_MIN_TILES_PER_CTA = 2;
-constexpr int AUC_COLD_SHIFT = 9;  // 128 bins x 512 keys cover all 65536 fp16 keys
+constexpr int AUC_COLD_SHIFT = 8;  // 256 bins x 256 keys cover all 65536 fp16 keys
 constexpr int AUC_MIN_KEY = 0x0400; // key of the most negative finite half: fine windows never reach -inf
 
 enum { MODE_HIST = 0, MODE_BID = 1, MODE_DONE = 2 };
@@ -168,8 +171,8 @@ __global__ void auction_init_kernel(AuctionPtrs p, long long ld, int K, const un
     for (long long j = i; j < (long long)K * AUC_W + 2 * K + 2; j += stride) p.hist_g[j] = 0;
     for (long long j = i; j < K; j += stride) {
         p.win_base[j] = 0;
-        p.win_hbase[j] = 64;
-        p.win_nlo[j] = 64;
+        p.win_hbase[j] = AUC_HALF;
+        p.win_nlo[j] = AUC_HALF;
         p.win_shift[j] = AUC_COLD_SHIFT;
         p.tkey[j] = -1;
         p.take[j] = 0;
@@ -208,7 +211,7 @@ __device__ __forceinline__ __half2 u2h2(unsigned u) { return *reinterpret_cast<_
 __device__ __forceinline__ unsigned h22u(__half2 h) { return *reinterpret_cast<unsigned*>(&h); }
 
 struct PassSmem {
-    __half* tile0;             // [2][K][J]
+    __half* tile0;             // [NBUF][K][J]
     unsigned int* hist;        // [K][W/2] two 16-bit counters per word
     unsigned int* above;       // [K]
     unsigned int* tie_seen;    // [K]
@@ -278,10 +281,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                  ::"r"(s_addr(dst)), "l"(src), "r"(bytes), "r"(s_addr(bar)) : "memory");
 }
 
-// One pass.  BID pass: the sweep filters S - cost against each worker's threshold T_w; the ~1 %
-// survivors (lane-private lists) become bids.  HIST pass: the sweep filters S - cost against the low
-// edge of each worker's (sampled) window; survivors are histogrammed.  Both are streaming passes whose
-// per-element work is one HSUB2 + one HSET2 per two elements.
+// The BID pass.  Per tile (all K workers x J jobs in shared memory, bulk-copied, double buffered): the sweep
+// filters S - cost against each worker's threshold T_w (one HSUB2 + one HSET2 per two elements); the ~1 %
+// survivors, kept as register bitmasks, become bids; column maximum; cost / owner update.
 template <int J>
 __global__ void __launch_bounds__(AUC_THREADS, (J == 128 ? 2 : 1))
 auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int K, long long jpw, AuctionPtrs p) {
@@ -303,15 +305,9 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
     PassSmem sm;
     {
         unsigned char* q = smem_raw;
-        sm.tile0 = (__half*)q;               q += (size_t)2 * K * J * 2;
-        sm.hist = (unsigned int*)q;          q += (size_t)K * AUC_W * 2;
-        sm.above = (unsigned int*)q;         q += (size_t)K * 4;
+        sm.tile0 = (__half*)q;               q += (size_t)AUC_NBUF * K * J * 2;
         sm.tie_seen = (unsigned int*)q;      q += (size_t)K * 4;
         sm.r_take = (int*)q;                 q += (size_t)K * 4;
-        sm.r_base = (int*)q;                 q += (size_t)K * 4;
-        sm.r_hbase = (int*)q;                q += (size_t)K * 4;
-        sm.r_nlo = (int*)q;                  q += (size_t)K * 4;
-        sm.gap = (unsigned int*)q;           q += (size_t)K * 4;
         sm.r_T2 = (unsigned int*)q;          q += (size_t)K * 4;
         sm.r_lo2 = (unsigned int*)q;         q += (size_t)K * 4;
         sm.colmax = (unsigned int*)q;        q += (size_t)J * 4;
@@ -322,7 +318,7 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
         sm.colviol = (unsigned char*)q;      q += (size_t)J;
     }
     __shared__ unsigned int s_nwith, s_nviol;
-    __shared__ __align__(8) unsigned long long tile_bar[2];
+    __shared__ __align__(8) unsigned long long tile_bar[AUC_NBUF];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned int lt = (1u << lane) - 1u;
@@ -330,44 +326,29 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
     const long long tiles_total = (N + J - 1) / J;
     const long long t_begin = tiles_total * b / G, t_end = tiles_total * (b + 1) / G;
 
-    for (int i = tid; i < K * AUC_W / 2; i += AUC_THREADS) sm.hist[i] = 0;
     for (int i = tid; i < K; i += AUC_THREADS) {
-        sm.above[i] = 0;
         sm.tie_seen[i] = p.tieprefix[(size_t)b * K + i];
         const int tk = p.tkey[i];
         const unsigned int Tb = key2h((unsigned)(tk < 0 ? 0 : tk));
         sm.r_T2[i] = Tb | (Tb << 16);
         sm.r_take[i] = p.take[i];
-        const int base = p.win_base[i], shift = p.win_shift[i];
-        sm.r_base[i] = base;
-        sm.r_hbase[i] = p.win_hbase[i];
-        sm.r_nlo[i] = p.win_nlo[i];
-        sm.gap[i] = 0;
-        sm.r_shift[i] = (unsigned char)shift;
-        // BID pass: the sweep finds bidders (v >= T).  HIST pass: rows with a placed window (sampled, slid,
-        // refined: base > 0) are filtered at its low edge; cold rows (base == 0: all 65536 keys in 128 coarse
-        // bins) take the direct path, their filter passes nothing (+inf)
-        const unsigned int lob = do_bid ? Tb : (base > 0 ? key2h((unsigned)base) : 0x7c00u);
-        sm.r_lo2[i] = lob | (lob << 16);
+        sm.r_lo2[i] = Tb | (Tb << 16);                     // the sweep finds bidders: v >= T_w
         sm.row_flag[i] = 0;
     }
     for (int i = tid; i < J; i += AUC_THREADS) { sm.colmax[i] = 0; sm.colviol[i] = 0; }
     if (tid == 0) {
         s_nwith = 0; s_nviol = 0;
-        mb_init(&tile_bar[0], 1);
-        mb_init(&tile_bar[1], 1);
+        for (int i = 0; i < AUC_NBUF; ++i) mb_init(&tile_bar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     // per-row sweep filter in registers (the rows of a warp are w = warp + 16 i)
     unsigned int f2r[MAXR];
-    bool any_cold = false;
 #pragma unroll
     for (int i = 0; i < MAXR; ++i) {
         const int w = warp + AUC_NW * i;
         f2r[i] = (w < K) ? sm.r_lo2[w] : 0x7c007c00u;
-        if (w < K && !do_bid && sm.r_base[w] == 0) any_cold = true;
     }
 
     auto issue_tile = [&](long long t, int buf) {
@@ -375,12 +356,13 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
         if (tid < K)
             bulk_g2s(sm.tile0 + (size_t)buf * K * J + (size_t)tid * J, S + (size_t)tid * ld + t * J, J * 2, &tile_bar[buf]);
     };
-    unsigned int bar_phase = 0;                         // bit buf = parity to wait for
-
-    if (t_begin < t_end) issue_tile(t_begin, 0);
+    // AUC_NBUF-deep ring: tiles t+1 .. t+NBUF-1 are in flight while tile t is processed
+    for (int i = 0; i < AUC_NBUF - 1; ++i)
+        if (t_begin + i < t_end) issue_tile(t_begin + i, i);
 
     for (long long t = t_begin; t < t_end; ++t) {
-        const int buf = (int)((t - t_begin) & 1);
+        const int it = (int)(t - t_begin);
+        const int buf = it % AUC_NBUF;
         const __half* tile = sm.tile0 + (size_t)buf * K * J;
         const long long col0 = t * J;
         const int ncols = (int)((N - col0) < J ? (N - col0) : J);   // valid columns of this tile
@@ -401,11 +383,10 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
             sm.colcost[tid] = c;
             sm.colown[tid] = o;
         }
-        // prefetch the next tile into the other buffer (its last readers finished before the
-        // barrier that closed the previous iteration)
-        if (t + 1 < t_end) issue_tile(t + 1, buf ^ 1);
-        mb_wait(&tile_bar[buf], (bar_phase >> buf) & 1u);
-        bar_phase ^= 1u << buf;
+        // prefetch into the buffer whose last readers finished before the barrier that closed the
+        // previous iteration
+        if (t + AUC_NBUF - 1 < t_end) issue_tile(t + AUC_NBUF - 1, (it + AUC_NBUF - 1) % AUC_NBUF);
+        mb_wait(&tile_bar[buf], (unsigned)(it / AUC_NBUF) & 1u);
         __syncthreads();                                                     // S0: tile + column state visible
 
         __half2 c2[NH2];
@@ -559,82 +540,13 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
                 }
             }
             for (int i = tid; i < K; i += AUC_THREADS) sm.row_flag[i] = 0;
-        } else {
-            // ---------------- stage B: survivors -> histogram ----------------
-            // owner entries (value = S) of rows with a placed window: one per job, by the column thread
-            if (tid < ncols) {
-                const int o = sm.colown[tid];
-                if (o >= 0 && sm.r_base[o] > 0) window_count(sm, o, (int)h2key(h2bits(tile[(size_t)o * J + tid])));
-            }
-#pragma unroll
-            for (int h = 0; h < NH2; ++h) {
-                unsigned int a = acc[h];
-                while (a) {
-                    const int bpos = __ffs(a) - 1;
-                    a &= a - 1;
-                    const int w = warp + AUC_NW * (bpos & 15), col = lane * CPL + 2 * h + (bpos >> 4);
-                    if (col >= ncols || sm.colown[col] == w) continue;       // owner entry: done by the column thread
-                    const __half v = __hsub(tile[(size_t)w * J + col], __ushort_as_half(sm.colcost[col]));
-                    window_count(sm, w, (int)h2key(h2bits(v)));
-                }
-            }
-            // cold rows (all 65536 keys in 128 coarse bins): exact values, every element
-            if (any_cold) {
-                for (int w = warp; w < K; w += AUC_NW) {
-                    const int base = sm.r_base[w];
-                    if (base > 0) continue;
-                    const int shift = sm.r_shift[w];
-                    const unsigned* row = reinterpret_cast<const unsigned*>(tile + (size_t)w * J) + lane * NH2;
-                    unsigned int nabove = 0;
-#pragma unroll
-                    for (int e = 0; e < CPL; ++e) {
-                        const int cidx = lane * CPL + e;
-                        const unsigned int sr = (row[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
-                        const __half v = (sm.colown[cidx] == w) ? bits2h(sr)
-                                                               : __hsub(bits2h(sr), __ushort_as_half(sm.colcost[cidx]));
-                        const int key = (int)h2key(h2bits(v));
-                        const bool in = cidx < ncols && key >= base;
-                        const int bin = (key - base) >> shift;
-                        const bool ab = in && bin >= AUC_W;
-                        const bool hb = in && bin < AUC_W;
-                        nabove += __popc(__ballot_sync(0xffffffffu, ab));
-                        unsigned int act = __ballot_sync(0xffffffffu, hb);
-                        if (act) {
-                            int lead = __ffs(act) - 1;
-                            int lbin = __shfl_sync(0xffffffffu, bin, lead);
-                            unsigned int same = __ballot_sync(0xffffffffu, hb && bin == lbin);
-                            if (same == act) {
-                                if (lane == lead) hist_add(sm.hist, w, lbin, __popc(act));
-                            } else if (hb) {
-                                hist_add(sm.hist, w, bin);
-                            }
-                        }
-                    }
-                    if (lane == 0 && nabove) atomicAdd(&sm.above[w], nabove);
-                }
-            }
         }
         __syncthreads();                                                     // S4: tile buffer + column state free
     }
 
-    if (do_bid) {
-        if (tid == 0) {
-            if (s_nwith) atomicAdd(p.n_with, s_nwith);
-            if (s_nviol) atomicAdd(p.n_viol, s_nviol);
-        }
-        return;
-    }
-    // ---- publish: per-CTA dump (for the tie prefix) + merge of non-empty bins ----
-    unsigned int* dump = reinterpret_cast<unsigned int*>(p.hist_cta + (size_t)b * K * AUC_W);
-    for (int i = tid; i < K * AUC_W / 2; i += AUC_THREADS) {
-        unsigned int h = sm.hist[i];
-        dump[i] = h;
-        if (h & 0xffffu) atomicAdd(&p.hist_g[2 * i], h & 0xffffu);
-        if (h >> 16) atomicAdd(&p.hist_g[2 * i + 1], h >> 16);
-    }
-    for (int i = tid; i < K; i += AUC_THREADS) {
-        if (sm.above[i]) atomicAdd(&p.above_g[i], sm.above[i]);
-        if (sm.gap[i]) atomicAdd(&p.gap_g[i], sm.gap[i]);
+    if (tid == 0) {
+        if (s_nwith) atomicAdd(p.n_with, s_nwith);
+        if (s_nviol) atomicAdd(p.n_viol, s_nviol);
     }
 }
 
@@ -813,7 +725,7 @@ static inline size_t auction_hist_smem(int K) {
 }
 
 static inline size_t auction_pass_smem(int K, int J) {
-    return (size_t)2 * K * J * 2 + (size_t)K * AUC_W * 2 + (size_t)K * 36 + (size_t)J * 4 +
+    return (size_t)AUC_NBUF * K * J * 2 + (size_t)K * 16 + (size_t)J * 4 +
            (size_t)J * 4 + (size_t)K * 2 + (size_t)J + 64;
 }
 
@@ -877,7 +789,7 @@ auction_sample_kernel(const __half* __restrict__ S, long long ld, long long N, i
         if (lo < AUC_MIN_KEY) lo = AUC_MIN_KEY;
         if (hi < lo + 8) hi = lo + 8;
         if (hi > 65535) hi = 65535;
-        int span = hi - lo + 1, shift = 0, hb = lo + 64, nlo = 64;
+        int span = hi - lo + 1, shift = 0, hb = lo + AUC_HALF, nlo = AUC_HALF;
         if (span > AUC_W) {
             // the candidates usually form two clumps (the worker's owned jobs at their full score, everything
             // else one or more cost steps lower): cut the window at the widest hole between consecutive
@@ -905,11 +817,11 @@ auction_sample_kernel(const __half* __restrict__ S, long long ld, long long N, i
             }
             if (!ok) {
                 while ((span >> shift) > AUC_W) ++shift;
-                hb = lo + 64;
-                nlo = 64;
+                hb = lo + AUC_HALF;
+                nlo = AUC_HALF;
             }
         }
-        if (shift == 0 && nlo == 64 && hb == lo + 64 && lo > 65536 - AUC_W) { lo = 65536 - AUC_W; hb = lo + 64; }
+        if (shift == 0 && nlo == AUC_HALF && hb == lo + AUC_HALF && lo > 65536 - AUC_W) { lo = 65536 - AUC_W; hb = lo + AUC_HALF; }
         p.win_base[w] = lo;
         p.win_hbase[w] = hb;
         p.win_nlo[w] = nlo;
@@ -962,8 +874,8 @@ auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
     if (was_bid) {
         for (int w = tid; w < K; w += 1024) {
             p.win_base[w] = 0;
-            p.win_hbase[w] = 64;
-            p.win_nlo[w] = 64;
+            p.win_hbase[w] = AUC_HALF;
+            p.win_nlo[w] = AUC_HALF;
             p.win_shift[w] = AUC_COLD_SHIFT;
             p.tkey[w] = -1;
             p.miss_run[w] = 0;
@@ -974,10 +886,10 @@ auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
             const int base = p.win_base[w], shift = p.win_shift[w];
             const int hbase = p.win_hbase[w], nlo = (shift == 0) ? p.win_nlo[w] : 0;
             const unsigned long long gap = (shift == 0) ? p.gap_g[w] : 0ull;
-            unsigned int h[4];
+            unsigned int h[AUC_BPL];
             unsigned int lsum = 0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { h[i] = p.hist_g[w * AUC_W + lane * 4 + i]; lsum += h[i]; }
+            for (int i = 0; i < AUC_BPL; ++i) { h[i] = p.hist_g[w * AUC_W + lane * AUC_BPL + i]; lsum += h[i]; }
             // suffix sums over lanes (bins above mine)
             unsigned int suf = lsum;
 #pragma unroll
@@ -986,12 +898,12 @@ auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
                 if (lane + d < 32) suf += o;
             }
             const unsigned long long ab = p.above_g[w];
-            // strictly above my 4 bins (the gap of a split window sits between bins nlo-1 and nlo)
-            unsigned long long cum_excl = ab + (suf - lsum) + ((4 * lane + 3) < nlo ? gap : 0ull);
+            // strictly above my bins (the gap of a split window sits between bins nlo-1 and nlo)
+            unsigned long long cum_excl = ab + (suf - lsum) + ((AUC_BPL * lane + AUC_BPL - 1) < nlo ? gap : 0ull);
             const unsigned long long total = ab + __shfl_sync(0xffffffffu, suf, 0) + gap;
             unsigned int hsum = 0;                                    // my bins of the upper run
 #pragma unroll
-            for (int i = 0; i < 4; ++i) hsum += (4 * lane + i >= nlo) ? h[i] : 0u;
+            for (int i = 0; i < AUC_BPL; ++i) hsum += (AUC_BPL * lane + i >= nlo) ? h[i] : 0u;
 #pragma unroll
             for (int d = 16; d; d >>= 1) hsum += __shfl_xor_sync(0xffffffffu, hsum, d);
             const unsigned long long c_hi = ab + hsum;               // everything >= hbase
@@ -1001,10 +913,10 @@ auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
             if (!in_gap && ab < (unsigned long long)need && total >= (unsigned long long)need) {
                 unsigned long long c = cum_excl;
 #pragma unroll
-                for (int i = 3; i >= 0; --i) {
-                    if (i != 3 && 4 * lane + i == nlo - 1) c += gap;      // stepping over the gap inside my 4 bins
+                for (int i = AUC_BPL - 1; i >= 0; --i) {
+                    if (i != AUC_BPL - 1 && AUC_BPL * lane + i == nlo - 1) c += gap;   // stepping over the gap inside my bins
                     if (found_bin < 0 && c < (unsigned long long)need && c + h[i] >= (unsigned long long)need) {
-                        found_bin = lane * 4 + i;
+                        found_bin = lane * AUC_BPL + i;
                         g_above = c;
                     }
                     c += h[i];
@@ -1021,12 +933,12 @@ auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
                         p.tkey[w] = found_bin >= nlo ? hbase + found_bin - nlo : base + found_bin;
                         p.take[w] = (int)(jpw - (long long)g_above);
                     } else {   // refine inside the bin that holds the threshold
-                        int nshift = shift >= 7 ? shift - 7 : 0;
+                        int nshift = shift >= 8 ? shift - 8 : 0;
                         const int nb2 = base + (found_bin << shift);
                         p.win_base[w] = nb2;
-                        p.win_hbase[w] = nb2 + 64;
-                p.win_nlo[w] = 64;
-                        p.win_nlo[w] = 64;
+                        p.win_hbase[w] = nb2 + AUC_HALF;
+                p.win_nlo[w] = AUC_HALF;
+                        p.win_nlo[w] = AUC_HALF;
                         p.win_shift[w] = nshift;
                         p.tkey[w] = -1;
                         atomicAdd(&s_unresolved, 1);
@@ -1037,8 +949,8 @@ auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
                 int nb2 = base + nlo, span = hbase - nb2, nshift = 0;
                 while ((span >> nshift) > AUC_W) ++nshift;
                 p.win_base[w] = nb2;
-                p.win_hbase[w] = nb2 + 64;
-                p.win_nlo[w] = 64;
+                p.win_hbase[w] = nb2 + AUC_HALF;
+                p.win_nlo[w] = AUC_HALF;
                 p.win_shift[w] = nshift;
                 p.tkey[w] = -1;
                 atomicAdd(&s_unresolved, 1);
@@ -1051,15 +963,15 @@ auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
                 int nb = is_above ? (shift == 0 ? hbase + (AUC_W - nlo) : base + (AUC_W << shift)) : base - (AUC_W << shift);
                 if (shift != 0 || run >= 2 || nb < AUC_MIN_KEY || nb > 65536 - AUC_W) {
                     p.win_base[w] = 0;
-                    p.win_hbase[w] = 64;
-                    p.win_nlo[w] = 64;
-            p.win_nlo[w] = 64;
+                    p.win_hbase[w] = AUC_HALF;
+                    p.win_nlo[w] = AUC_HALF;
+            p.win_nlo[w] = AUC_HALF;
                     p.win_shift[w] = AUC_COLD_SHIFT;
                     p.miss_run[w] = 0;
                 } else {
                     p.win_base[w] = nb;
-                    p.win_hbase[w] = nb + 64;
-                    p.win_nlo[w] = 64;
+                    p.win_hbase[w] = nb + AUC_HALF;
+                    p.win_nlo[w] = AUC_HALF;
                     p.miss_run[w] = run + 1;
                 }
                 p.tkey[w] = -1;
@@ -1164,7 +1076,7 @@ extern "C" {
 struct rqk_auction_layout {
     int64_t total_bytes;        // workspace size
     int64_t reduce_offset;      // byte offset of the int32 reduce block (sum over ranks after every pass)
-    int64_t reduce_count;       // its length in int32 elements: k*128 + 2k + 2
+    int64_t reduce_count;       // its length in int32 elements: k*256 + 2k + 2
     int64_t tie_total_offset;   // byte offset of int32[k]: local ties at the threshold (allgather after resolve)
 };
 

@@ -6,7 +6,7 @@ Row sharding: when a `ShardGroup` with world_size > 1 is 
 contiguous row block.  The only data exchanged per iteration are
   * K x D partial sums + K counts            (centroid update, one all_reduce)
   * K argmin counts, 2 fp16 extrema           (loss / eps, tiny all_reduces)
-  * K*128 + K + 2 int32 per auction pass      (threshold histograms, one all_reduce)
+  * K*256 + 2K + 2 int32 per auction pass     (threshold histograms, one all_reduce)
   * K int32 per auction pass                  (tie totals, one all_gather)
 """
 from __future__ import annotations

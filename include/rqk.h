@@ -75,7 +75,7 @@ typedef struct rqk_auction_info {
 typedef struct rqk_auction_layout {
     int64_t total_bytes;       /* workspace size */
     int64_t reduce_offset;     /* byte offset of the int32 reduce block */
-    int64_t reduce_count;      /* its length: k*128 + 2k + 2 */
+    int64_t reduce_count;      /* its length: k*256 + 2k + 2 */
     int64_t tie_total_offset;  /* byte offset of int32[k]: local number of values equal to the threshold */
 } rqk_auction_layout;
 

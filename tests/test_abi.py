@@ -50,7 +50,7 @@ def test_sizes_only_entry_points_work_on_cpu():
     assert L.rqk_encode_workspace_bytes(100000, 512, 256) > 0
     lay = _lib.AuctionLayout()
     assert L.rqk_auction_layout_query(100000, 128, ctypes.byref(lay)) == 0
-    assert lay.reduce_count == 128 * 128 + 2 * 128 + 2
+    assert lay.reduce_count == 128 * 256 + 2 * 128 + 2
     assert lay.total_bytes == L.rqk_auction_workspace_bytes(100000, 128)
     # argument errors come back as codes + message, never as exceptions or crashes
     assert L.rqk_auction_layout_query(0, 128, ctypes.byref(lay)) < 0
