@@ -97,6 +97,7 @@ struct AuctionPtrs {
     int* win_shift;           // [K] log2 keys per bin
     int* tkey;                // [K] resolved threshold key, -1 = unresolved
     int* take;                // [K] ties at the threshold that still get a bid
+    int* tprev;               // [K] threshold of the previous round (-1 = none): thresholds only sink within an auction
     int* miss_run;            // [K] consecutive window slides
     unsigned int* tieprefix;  // [G][K]
     unsigned short* hist_cta; // [G][K][W] per-CTA histograms (16-bit: a CTA owns < 65536 jobs)
@@ -130,6 +131,7 @@ static inline size_t auction_ws_layout(long long N, long long ld, int K, Auction
     size_t o_ws = take_((size_t)K * 4);
     size_t o_tk = take_((size_t)K * 4);
     size_t o_take = take_((size_t)K * 4);
+    size_t o_tprev = take_((size_t)K * 4);
     size_t o_mr = take_((size_t)K * 4);
     size_t o_tp = take_((size_t)G * K * 4);
     size_t o_hc = take_((size_t)G * K * AUC_W * 2);
@@ -151,6 +153,7 @@ static inline size_t auction_ws_layout(long long N, long long ld, int K, Auction
         p->win_shift = (int*)(base + o_ws);
         p->tkey = (int*)(base + o_tk);
         p->take = (int*)(base + o_take);
+        p->tprev = (int*)(base + o_tprev);
         p->miss_run = (int*)(base + o_mr);
         p->tieprefix = (unsigned int*)(base + o_tp);
         p->hist_cta = (unsigned short*)(base + o_hc);
@@ -176,6 +179,7 @@ __global__ void auction_init_kernel(AuctionPtrs p, long long ld, int K, const un
         p.win_shift[j] = AUC_COLD_SHIFT;
         p.tkey[j] = -1;
         p.take[j] = 0;
+        p.tprev[j] = -1;
         p.miss_run[j] = 0;
     }
     if (i == 0) {
@@ -786,6 +790,10 @@ auction_sample_kernel(const __half* __restrict__ S, long long ld, long long N, i
         if (r_lo > ns - 1) r_lo = ns - 1;
         int lo = (int)keys[r_lo] - 1, hi = (int)keys[r_hi] + 1;
         if (r_hi == 0) hi += 32;                                            // the sample's maximum is no bound
+        // costs only grow, so a worker's threshold never rises from one round to the next (up to a rare
+        // tie corner case, which the slide-up path catches): the window need not reach above the last one
+        const int tp = p.tprev[w];
+        if (tp >= 0 && hi > tp + 2) hi = tp + 2;
         if (lo < AUC_MIN_KEY) lo = AUC_MIN_KEY;
         if (hi < lo + 8) hi = lo + 8;
         if (hi > 65535) hi = 65535;
@@ -873,6 +881,7 @@ auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
     const long long need = jpw + 1;
     if (was_bid) {
         for (int w = tid; w < K; w += 1024) {
+            p.tprev[w] = p.tkey[w];
             p.win_base[w] = 0;
             p.win_hbase[w] = AUC_HALF;
             p.win_nlo[w] = AUC_HALF;

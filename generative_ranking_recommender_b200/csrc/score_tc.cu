@@ -23,6 +23,7 @@
 // The lo.lo product is dropped (<= 2^-22 |x||c| per term), which leaves the dot products at fp32
 // accuracy (~1e-7 relative on d): far below the fp16 rounding of the scores and the 1e-5 near-tie gate.
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace rqk {
@@ -121,6 +122,7 @@ struct ScoreTcParams {
     int stages;
     const float* c2;         // [K] |c|^2
     ScoreOut o;
+    int debug;               // timing attribution only (RQK_SCORE_DEBUG): 1 = skip epilogue math, 2 = hi.hi MMA only, 4 = no transform
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -219,9 +221,13 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < TC_BK / 8; ++k) {
                         const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);   // +32 B along K inside the swizzle row
-                        umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
-                        umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
-                        umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+                        if (!(P.debug & 2)) {
+                            umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+                            umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+                            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+                        } else {
+                            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
+                        }
                     }
                     umma_commit(&empty_bar[s]);      // frees the ring slot when these MMAs retire
                     if (kb == kblocks - 1) umma_commit(&tmem_full[a]);
@@ -239,6 +245,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             float nrm = 0.f;
             for (int kb = 0; kb < kblocks; ++kb) {
                 mbar_wait(&full_bar[s], ph);
+                if (P.debug & 4) {
+                    fence_proxy_async();
+                    mbar_arrive(&xf_bar[s]);
+                    if (++s == stages) { s = 0; ph ^= 1; }
+                    continue;
+                }
                 unsigned char* st = smem + (size_t)s * stage_bytes;
                 float4* hi = reinterpret_cast<float4*>(st + (size_t)r * 128);
                 float4* lo = reinterpret_cast<float4*>(st + a_bytes + (size_t)r * 128);
@@ -282,6 +294,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             float b1 = INFINITY, b2 = INFINITY;
             int bi = 0;
             for (int c0 = 0; c0 < KC; c0 += 32) {
+                if (P.debug & 1) break;
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * P.tmem_cols + c0), v);
                 tmem_ld_wait();
@@ -402,6 +415,10 @@ int score_pass_tc(const float* x, long long n, int dim, const float* c, int K, f
     ScoreTcParams P;
     P.n = n; P.dim = dim; P.K = K; P.KC = KC; P.tmem_cols = tcols;
     P.c2 = c2; P.o = o;
+    {
+        const char* dbg = getenv("RQK_SCORE_DEBUG");
+        P.debug = dbg ? atoi(dbg) : 0;
+    }
     const size_t stage_bytes = 2 * (size_t)TC_BM * TC_BK * 4 + 2 * (size_t)KC * TC_BK * 4;
     const size_t tail = 8 * 8 * 3 + 2 * 8 * 3 + 16 + 2 * TC_BM * 4 + 256 * 4 + 256 * 4 + 64;
     int stages = (int)((225 * 1024 - tail - 1024) / stage_bytes);
