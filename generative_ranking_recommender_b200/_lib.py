@@ -39,7 +39,7 @@ SIGNATURES = {
     "rqk_auction_workspace_bytes": (c_sz, [c_i64, c_i32]),
     "rqk_auction_layout_query": (ctypes.c_int, [c_i64, c_i32, ctypes.POINTER(AuctionLayout)]),
     "rqk_auction_init": (ctypes.c_int, [c_i64, c_i64, c_i32, c_p, c_p, c_sz, c_p]),
-    "rqk_auction_pass": (ctypes.c_int, [c_p, c_i64, c_i64, c_i32, c_i64, c_p, c_sz, c_p]),
+    "rqk_auction_pass": (ctypes.c_int, [c_p, c_i64, c_i64, c_i32, c_i64, c_i32, c_p, c_sz, c_p]),
     "rqk_auction_resolve": (ctypes.c_int, [c_i64, c_i64, c_i32, c_i64, c_p, c_sz, c_p]),
     "rqk_auction_tie_offset": (ctypes.c_int, [c_i64, c_i64, c_i32, c_p, c_p, c_sz, c_p]),
     "rqk_auction_poll": (ctypes.c_int, [c_i64, c_i64, c_i32, c_p, c_sz, ctypes.POINTER(AuctionInfo), c_p]),

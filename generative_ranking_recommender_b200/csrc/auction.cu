@@ -12,26 +12,26 @@
 //          streams through shared memory, and bids are reduced to (highest bid, first highest
 //          bidder) per job on the fly.
 //
-// One PASS = every CTA streams its contiguous range of 128-job (K<=128) or 64-job tiles, all K
-// workers deep, through a double-buffered cp.async pipeline.  Per tile:
-//   sweep    A warp owns a worker row of the tile, so ties are met in job order.  The sweep is a half2
-//            FILTER: v = S - cost (ownership ignored: the owner's true value S is only larger)
-//            against the low edge of the worker's histogram window, which lies below its threshold
-//            T_w, the (N/K+1)-th largest value (:66).  Because costs only grow, the survivors are a
-//            superset of BOTH this round's bidders (v >= T_w) and the next round's in-window values.
-//            The few-percent survivors go to lane-private 16-bit lists in shared memory.
-//   stage A  (BID) survivors with v >= T_w become bids ((v - T_w) + eps, :76); ties at T_w are taken
-//            lowest job index first up to the worker's quota.  The one owner entry of every job is
-//            handled by the job's column thread (retain hack :86-87, counter>1000 fallback :88-89).
-//            The column max with first-argmax (:104) is an atomicMax on (bid << 16 | ~worker) in
-//            shared memory; then cost/owner update (:118-123).
-//   stage B  (HIST) the same survivors, re-valued with the NEW costs, are histogrammed into the
-//            <=128-key window predicted just below each threshold (16-bit packed counters), plus an
-//            "above the window" count: the input of the next round's threshold selection.
-// A 1-CTA RESOLVE kernel turns the merged histograms into exact thresholds (16-bit radix select:
-// window hit -> exact; miss -> slide; cold start -> coarse 128-bin pass over all keys, then refine),
-// and a K-CTA kernel prefix-sums per-CTA tie counts so the canonical tie rule is global.  So a
-// steady-state round reads S exactly once.
+// A ROUND of the reference is two streaming passes over S (2*K bytes per job each):
+//   HIST pass  (auction_hist_kernel) each worker's threshold T_w, the (N/K+1)-th largest value (:66), by an
+//            exact 16-bit radix select.  A strided 4096-job sample of the worker's current values brackets the
+//            threshold's rank (+-4.5 sigma of the order statistic, capped by the previous threshold: costs only
+//            grow, so thresholds only sink); 256 one-key bins are laid over that bracket (split in two runs
+//            around the widest sampled hole if it is wider than 256 keys) plus "above" / "gap" counters.
+//            Warps stream row segments straight from global memory (16-byte loads, four in flight per lane):
+//            per 8 jobs 1 LDG.128 + 1 LDS.128 + 4 HSUB2 + 4 HSET2 + 4 LOP3; the ~1.5 % survivors (values at or
+//            above the bracket's low edge) are kept as register bitmasks and histogrammed afterwards (16-bit
+//            packed shared-memory counters).  A 1-CTA resolve kernel turns the merged histograms into exact
+//            thresholds (hit -> exact; miss -> slide / refine / coarse restart); a K-CTA kernel prefix-sums
+//            per-CTA tie counts so the canonical tie rule is global.
+//   BID pass   (auction_pass_kernel) tiles of all K workers x 128 (K<=128) or 64 jobs in shared memory through a
+//            3-deep bulk-copy (UBLKCP + mbarrier) ring.  A warp owns a worker row of the tile, so ties are met
+//            in job order.  The sweep is a half2 FILTER: v = S - cost (ownership ignored: the owner's true value
+//            S is only larger) against T_w; survivors (~0.8 %) are register bitmasks and become bids
+//            ((v - T_w) + eps, :76); ties at T_w are taken lowest job index first up to the worker's quota.
+//            The one owner entry of every job is handled by the job's column thread (retain hack :86-87,
+//            counter>1000 fallback :88-89).  The column max with first-argmax (:104) is an atomicMax on
+//            (bid << 16 | ~worker) in shared memory; then cost/owner update (:118-123).
 //
 // Exact fast-forward.  With N % K != 0 the reference cannot terminate before its counter>1000
 // fallback and runs 1002 rounds.  But once a round's fresh bids all land on jobs
@@ -767,18 +767,91 @@ auction_sample_kernel(const __half* __restrict__ S, long long ld, long long N, i
         keys[i] = key;
     }
     __syncthreads();
-    // bitonic sort, descending
-    for (int k = 2; k <= AUC_SAMPLE; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
+    // Only ranks r_hi .. r_lo of the descending order are needed (a few dozen for K >= 64): find the key at
+    // rank r_lo by a two-level radix select, collect everything >= it and rank that short list by counting.
+    // Full bitonic sort as the fallback (small K, or many duplicates).
+    __shared__ unsigned int shist[256];
+    __shared__ unsigned short top[1024], sorted[1024];
+    __shared__ int s_b1, s_above1, s_vlo, s_cnt;
+    bool need_full_sort = true;
+    {
+        const double r = (double)(jpw + 1) * (double)ns / (double)N - 0.5;
+        const double sg = sqrt(r > 1.0 ? r : 1.0);
+        long long r_lo = (long long)ceil(r + 4.5 * sg + 2.0);
+        if (r_lo > ns - 1) r_lo = ns - 1;
+        const int need_n = (int)r_lo + 1;
+        if (need_n <= 512) {
+            if (tid < 256) shist[tid] = 0;
+            if (tid == 0) s_cnt = 0;
+            __syncthreads();
+            for (int i = tid; i < AUC_SAMPLE; i += 1024) atomicAdd(&shist[keys[i] >> 8], 1u);
+            __syncthreads();
+            if (tid == 0) {
+                int cum = 0, bsel = 0;
+                for (int bb = 255; bb >= 0; --bb) {
+                    if (cum + (int)shist[bb] >= need_n) { bsel = bb; break; }
+                    cum += shist[bb];
+                }
+                s_b1 = bsel;
+                s_above1 = cum;
+            }
+            __syncthreads();
+            const int b1 = s_b1;
+            if (tid < 256) shist[tid] = 0;
+            __syncthreads();
+            for (int i = tid; i < AUC_SAMPLE; i += 1024)
+                if ((keys[i] >> 8) == b1) atomicAdd(&shist[keys[i] & 255], 1u);
+            __syncthreads();
+            if (tid == 0) {
+                int cum = s_above1, bsel = 0;
+                for (int bb = 255; bb >= 0; --bb) {
+                    if (cum + (int)shist[bb] >= need_n) { bsel = bb; break; }
+                    cum += shist[bb];
+                }
+                s_vlo = (b1 << 8) | bsel;
+            }
+            __syncthreads();
+            const int vlo = s_vlo;
             for (int i = tid; i < AUC_SAMPLE; i += 1024) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const unsigned short a = keys[i], b2 = keys[ixj];
-                    const bool desc = (i & k) == 0;
-                    if (desc ? (a < b2) : (a > b2)) { keys[i] = b2; keys[ixj] = a; }
+                const unsigned short kk = keys[i];
+                if ((int)kk >= vlo) {
+                    const int slot = atomicAdd(&s_cnt, 1);
+                    if (slot < 1024) top[slot] = kk;
                 }
             }
             __syncthreads();
+            const int cnt = s_cnt;
+            if (cnt <= 1024) {
+                need_full_sort = false;
+                for (int i = tid; i < cnt; i += 1024) {
+                    const unsigned short kk = top[i];
+                    int rank = 0;
+                    for (int j = 0; j < cnt; ++j) {
+                        const unsigned short kj = top[j];
+                        rank += (kj > kk) || (kj == kk && j < i);
+                    }
+                    sorted[rank] = kk;
+                }
+                __syncthreads();
+                for (int i = tid; i < cnt; i += 1024) keys[i] = sorted[i];   // ranks 0 .. cnt-1 (>= r_lo) are exact
+                __syncthreads();
+            }
+        }
+    }
+    if (need_full_sort) {
+        // bitonic sort, descending
+        for (int k = 2; k <= AUC_SAMPLE; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < AUC_SAMPLE; i += 1024) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const unsigned short a = keys[i], b2 = keys[ixj];
+                        const bool desc = (i & k) == 0;
+                        if (desc ? (a < b2) : (a > b2)) { keys[i] = b2; keys[ixj] = a; }
+                    }
+                }
+                __syncthreads();
+            }
         }
     }
     if (tid == 0) {
@@ -1134,8 +1207,12 @@ int rqk_auction_init(int64_t n, int64_t ld, int32_t k, const void* minmax_keys, 
 }
 
 // One pass over this rank's [k][ld] score shard (n local jobs).  jobs_per_worker = n_global / k.
-int rqk_auction_pass(const void* scores_t, int64_t ld, int64_t n, int32_t k, int64_t n_global, void* workspace,
-                     size_t workspace_bytes, void* stream_) {
+// The device-side state machine decides what the pass is: three kernels are enqueued and two of them
+// return at once - window sampling (only when windows are cold and the jobs are not sharded), the
+// streaming HIST kernel, the tiled BID kernel.  `which` (0 = all) restricts the launch to a subset
+// (bit 0 sample, bit 1 HIST, bit 2 BID) so that a caller can time one kernel alone.
+int rqk_auction_pass(const void* scores_t, int64_t ld, int64_t n, int32_t k, int64_t n_global, int32_t which,
+                     void* workspace, size_t workspace_bytes, void* stream_) {
     using namespace rqk;
     AuctionArgs a;
     int rc = auction_prepare(n, ld, k, workspace, workspace_bytes, &a, "rqk_auction_pass");
@@ -1149,9 +1226,10 @@ int rqk_auction_pass(const void* scores_t, int64_t ld, int64_t n, int32_t k, int
         RQK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem));
         cur = a.smem;
     }
-    if (n_global == n)   // sampled windows need the whole job set on this GPU (ranks must agree on the windows)
+    if (which == 0) which = 7;
+    if (n_global == n && (which & 1))   // sampled windows need the whole job set on this GPU (ranks must agree on the windows)
         auction_sample_kernel<<<k, 1024, 0, (cudaStream_t)stream_>>>((const __half*)scores_t, ld, n, k, n_global / k, a.p);
-    {
+    if (which & 2) {
         static size_t hs_set = 0;
         const size_t hs = auction_hist_smem(k);
         if (hs > hs_set) {
@@ -1160,7 +1238,8 @@ int rqk_auction_pass(const void* scores_t, int64_t ld, int64_t n, int32_t k, int
         }
         auction_hist_kernel<<<a.G, AUC_THREADS, hs, (cudaStream_t)stream_>>>((const __half*)scores_t, ld, n, k, a.J, a.p);
     }
-    kern<<<a.G, AUC_THREADS, a.smem, (cudaStream_t)stream_>>>((const __half*)scores_t, ld, n, k, n_global / k, a.p);
+    if (which & 4)
+        kern<<<a.G, AUC_THREADS, a.smem, (cudaStream_t)stream_>>>((const __half*)scores_t, ld, n, k, n_global / k, a.p);
     RQK_LAUNCH_OK();
     return 0;
 }
@@ -1245,7 +1324,7 @@ int rqk_auction(const void* scores_t, int64_t ld, int64_t n, int32_t k, const vo
     // hard stop: the reference itself cannot exceed 1002 rounds; each round is a handful of passes at most
     for (int it = 0; it < 8000 && !st.done; it += batch) {
         for (int q = 0; q < batch; ++q) {
-            if ((rc = rqk_auction_pass(scores_t, ld, n, k, n, workspace, workspace_bytes, stream_))) return rc;
+            if ((rc = rqk_auction_pass(scores_t, ld, n, k, n, 0, workspace, workspace_bytes, stream_))) return rc;
             if ((rc = rqk_auction_resolve(n, ld, k, n, workspace, workspace_bytes, stream_))) return rc;
         }
         if ((rc = rqk_auction_poll(n, ld, k, workspace, workspace_bytes, &st, stream_))) return rc;

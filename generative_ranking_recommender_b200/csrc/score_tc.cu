@@ -281,54 +281,91 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         const int q = warp;                                  // TMEM lane quarter = warp % 4
         const int r = q * 32 + lane;
         int a = 0; uint32_t aph = 0;
-        unsigned int kmax = 0, kmin = 0xffffu;
+        // fast path: no fp32 distance matrix, no predict()-mode masking, nearest (not farthest) centre
+        const bool fast = !P.o.dist && !P.o.mask_ids && !P.o.farthest;
+        unsigned int kmax = 0, kmin = 0xffffu;               // generic path: extrema as fp16 keys
+        float dmin2 = INFINITY, dmax2 = 0.f;                 // fast path: extrema of d^2 over valid rows
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const long long row = tile * TC_BM + r;
             const bool rv = row < P.n;
             mbar_wait(&x2_full[a], aph);
             const float xn = x2s[a * TC_BM + r];
-            const int pid = (rv && P.o.mask_ids) ? P.o.mask_ids[row] : -1;
-            const int mlo = pid * P.o.mask_block, mhi = mlo + P.o.mask_block;
             mbar_wait(&tmem_full[a], aph);
             tc_fence_after();
             float b1 = INFINITY, b2 = INFINITY;
             int bi = 0;
-            for (int c0 = 0; c0 < KC; c0 += 32) {
-                if (P.debug & 1) break;
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * P.tmem_cols + c0), v);
-                tmem_ld_wait();
+            if (fast) {
+                // argmin / runner-up on d^2 (sqrt is monotone; identical d^2 keep the first index like
+                // torch.argmin); sqrt only where the fp16 score is actually stored
+                __half* sp = (P.o.scores_t && rv) ? P.o.scores_t + row : nullptr;
+                const long long ld = P.o.ld;
+                float mx = 0.f;
+                for (int c0 = 0; c0 < KC; c0 += 32) {
+                    if (P.debug & 1) break;
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * P.tmem_cols + c0), v);
+                    tmem_ld_wait();
+                    const bool whole = (c0 + 32 <= P.K);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int k = c0 + j;
-                    if (k < P.K) {
-                        float d2 = fmaf(-2.f, __uint_as_float(v[j]), xn + c2s[k]);
-                        float d = sqrtf(fmaxf(d2, 0.f));
-                        if (P.o.dist && rv) P.o.dist[row * P.K + k] = d;
-                        if (P.o.scores_t && rv) {
-                            __half h = __float2half_rn(-d);
-                            P.o.scores_t[(long long)k * P.o.ld + row] = h;
-                            unsigned int key = h2key(h2bits(h));
-                            kmax = max(kmax, key);
-                            kmin = min(kmin, key);
+                    for (int j = 0; j < 32; ++j) {
+                        const int k = c0 + j;
+                        if (whole || k < P.K) {
+                            const float d2 = fmaxf(fmaf(-2.f, __uint_as_float(v[j]), xn + c2s[k]), 0.f);
+                            if (d2 < b1) { b2 = b1; b1 = d2; bi = k; }
+                            else if (d2 < b2) b2 = d2;
+                            mx = fmaxf(mx, d2);
+                            if (sp) sp[(long long)k * ld] = __float2half_rn(-sqrtf(d2));
                         }
-                        float dd = P.o.farthest ? -d : d;
-                        if (pid >= 0 && (k < mlo || k >= mhi)) dd = d + 10000.0f;
-                        if (dd < b1) { b2 = b1; b1 = dd; bi = k; }
-                        else if (dd < b2) b2 = dd;
                     }
                 }
+                if (rv) { dmin2 = fminf(dmin2, b1); dmax2 = fmaxf(dmax2, mx); }
+                b1 = sqrtf(b1);
+                b2 = sqrtf(b2);
+            } else {
+                const int pid = (rv && P.o.mask_ids) ? P.o.mask_ids[row] : -1;
+                const int mlo = pid * P.o.mask_block, mhi = mlo + P.o.mask_block;
+                for (int c0 = 0; c0 < KC; c0 += 32) {
+                    if (P.debug & 1) break;
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * P.tmem_cols + c0), v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int k = c0 + j;
+                        if (k < P.K) {
+                            float d2 = fmaf(-2.f, __uint_as_float(v[j]), xn + c2s[k]);
+                            float d = sqrtf(fmaxf(d2, 0.f));
+                            if (P.o.dist && rv) P.o.dist[row * P.K + k] = d;
+                            if (P.o.scores_t && rv) {
+                                __half h = __float2half_rn(-d);
+                                P.o.scores_t[(long long)k * P.o.ld + row] = h;
+                                unsigned int key = h2key(h2bits(h));
+                                kmax = max(kmax, key);
+                                kmin = min(kmin, key);
+                            }
+                            float dd = P.o.farthest ? -d : d;
+                            if (pid >= 0 && (k < mlo || k >= mhi)) dd = d + 10000.0f;
+                            if (dd < b1) { b2 = b1; b1 = dd; bi = k; }
+                            else if (dd < b2) b2 = dd;
+                        }
+                    }
+                }
+                if (P.o.farthest) { b1 = -b1; b2 = -b2; }
             }
             tc_fence_before();
             mbar_arrive(&tmem_empty[a]);
             if (rv) {
                 if (P.o.argmin) P.o.argmin[row] = bi;
-                if (P.o.best2) { P.o.best2[row * 2] = P.o.farthest ? -b1 : b1; P.o.best2[row * 2 + 1] = P.o.farthest ? -b2 : b2; }
+                if (P.o.best2) { P.o.best2[row * 2] = b1; P.o.best2[row * 2 + 1] = b2; }
                 if (P.o.counts) atomicAdd(&cnt_s[bi], 1);
             }
             if (++a == 2) { a = 0; aph ^= 1; }
         }
         if (P.o.scores_t && P.o.minmax_keys) {
+            if (fast && dmin2 <= dmax2) {                    // rounding is monotone: extrema of half(-d) from those of d^2
+                kmax = h2key(h2bits(__float2half_rn(-sqrtf(dmin2))));
+                kmin = h2key(h2bits(__float2half_rn(-sqrtf(dmax2))));
+            }
 #pragma unroll
             for (int off = 16; off; off >>= 1) {
                 kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, off));

@@ -232,9 +232,10 @@ class AuctionSession:
         self._mm = minmax_global.contiguous()
         check(self.L.rqk_auction_init(self.n, self.ld, self.k, _ptr(self._mm), *self._args(), _stream(self.dev)))
 
-    def do_pass(self):
-        check(self.L.rqk_auction_pass(_ptr(self.s), self.ld, self.n, self.k, self.n_global, *self._args(),
-                                      _stream(self.dev)))
+    def do_pass(self, which: int = 0):
+        """which: 0 = sample + HIST + BID kernels (the state machine picks), or a subset (1 | 2 | 4)."""
+        check(self.L.rqk_auction_pass(_ptr(self.s), self.ld, self.n, self.k, self.n_global, int(which),
+                                      *self._args(), _stream(self.dev)))
 
     def resolve(self):
         check(self.L.rqk_auction_resolve(self.n, self.ld, self.k, self.n_global, *self._args(), _stream(self.dev)))

@@ -85,8 +85,8 @@ int rqk_auction(const void* scores_t, int64_t ld, int64_t n, int32_t k, const vo
                 void* workspace, size_t workspace_bytes, rqk_auction_info* info /*HOST*/, void* stream);
 int rqk_auction_init(int64_t n, int64_t ld, int32_t k, const void* minmax_keys, void* workspace,
                      size_t workspace_bytes, void* stream);
-int rqk_auction_pass(const void* scores_t, int64_t ld, int64_t n, int32_t k, int64_t n_global, void* workspace,
-                     size_t workspace_bytes, void* stream);
+int rqk_auction_pass(const void* scores_t, int64_t ld, int64_t n, int32_t k, int64_t n_global, int32_t which,
+                     void* workspace, size_t workspace_bytes, void* stream);   /* which: 0 = all; bit0 sample, bit1 HIST, bit2 BID */
 int rqk_auction_resolve(int64_t n, int64_t ld, int32_t k, int64_t n_global, void* workspace, size_t workspace_bytes,
                         void* stream);
 int rqk_auction_tie_offset(int64_t n, int64_t ld, int32_t k, const int32_t* offsets, void* workspace,
