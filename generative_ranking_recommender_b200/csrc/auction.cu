@@ -457,7 +457,14 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
                 unsigned int anye = 0, em[NH2];
 #pragma unroll
                 for (int h = 0; h < NH2; ++h) { em[h] = __heq2_mask(v2[h], f2); anye |= em[h]; }
-                if (__any_sync(0xffffffffu, anye != 0)) {
+                const unsigned int seen0 = sm.tie_seen[w];
+                const long long quota0 = sm.r_take[w];
+                if ((long long)seen0 >= quota0) {
+                    // the worker's quota of ties was used up by lower job indices: every tie here is rejected
+                    // (owner entries and padding columns are skipped in stage A anyway)
+#pragma unroll
+                    for (int h = 0; h < NH2; ++h) rej[h] |= em[h] & rowbits;
+                } else if (__any_sync(0xffffffffu, anye != 0)) {
                     // canonical tie rule: lowest job index first, globally (tieprefix + tiles so far).
                     // In unflagged rows owner entries cannot tie (the column thread would have flagged the row).
                     bool eq[CPL];
@@ -566,7 +573,7 @@ constexpr int HS_SUB = 4096;      // jobs staged (cost, owner) per sub-range
 
 __device__ __forceinline__ uint4 ldg_stream128(const void* ptr) {
     uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(ptr));
     return r;
 }
@@ -644,8 +651,10 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
         // ---- the sweep: rows of this warp, 4 x 256 jobs per step ----
         for (int w = warp; w < K; w += AUC_NW) {
             const __half* srow = S + (size_t)w * ld + sub;
-            if (sm.r_base[w] > 0) {
+            const int wbase = sm.r_base[w];
+            if (wbase > 0) {
                 const __half2 f2 = u2h2(sm.r_lo2[w]);
+                const int whb = sm.r_hbase[w], wnlo = sm.r_nlo[w], wshift = sm.r_shift[w];
                 for (int c0 = 0; c0 < sublen; c0 += 1024) {
                     uint4 sv[4];
 #pragma unroll
@@ -674,7 +683,22 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
                         const int cc = c0 + (pq >> 2) * 256 + lane * 8 + 2 * (pq & 3) + (bpos >> 4);
                         if (cc >= sublen || own_s[cc] == w) continue;            // owner entry: counted above
                         const __half v = __hsub(srow[cc], __ushort_as_half(cost_s[cc]));
-                        window_count(sm, w, (int)h2key(h2bits(v)));
+                        const int key = (int)h2key(h2bits(v));
+                        if (key < wbase) continue;
+                        if (wshift == 0) {
+                            if (key >= whb) {
+                                if (key - whb >= AUC_W - wnlo) atomicAdd(&sm.above[w], 1u);
+                                else hist_add(sm.hist, w, wnlo + key - whb);
+                            } else if (key >= wbase + wnlo) {
+                                atomicAdd(&sm.gap[w], 1u);
+                            } else {
+                                hist_add(sm.hist, w, key - wbase);
+                            }
+                        } else {
+                            const int bin = (key - wbase) >> wshift;
+                            if (bin >= AUC_W) atomicAdd(&sm.above[w], 1u);
+                            else hist_add(sm.hist, w, bin);
+                        }
                     }
                 }
             } else {
