@@ -765,17 +765,26 @@ static inline size_t auction_pass_smem(int K, int J) {
 // ------------------------------------------------------------------------------------------
 constexpr int AUC_SAMPLE = 4096;
 
+// Sharded jobs: every rank samples AUC_SAMPLE / world jobs of its shard (collect_out != null: write the keys
+// and return), the host all-gathers them, and every rank places identical windows from the union
+// (ext_keys != null: [K][ext_n] keys, N = global job count).
 __global__ void __launch_bounds__(1024, 1)
-auction_sample_kernel(const __half* __restrict__ S, long long ld, long long N, int K, long long jpw, AuctionPtrs p) {
+auction_sample_kernel(const __half* __restrict__ S, long long ld, long long N, int K, long long jpw, AuctionPtrs p,
+                      unsigned short* __restrict__ collect_out, int collect_n,
+                      const unsigned short* __restrict__ ext_keys, int ext_n) {
     const AuctionState st = *p.st;
     if (st.mode != MODE_HIST || !st.need_sample) return;
     __shared__ unsigned short keys[AUC_SAMPLE];
     const int w = blockIdx.x, tid = threadIdx.x;
-    const long long ns = N < AUC_SAMPLE ? N : AUC_SAMPLE;
+    long long ns = N < AUC_SAMPLE ? N : AUC_SAMPLE;
+    if (collect_out) ns = collect_n < ns ? collect_n : ns;
+    if (ext_keys) ns = ext_n;
     const __half eps = bits2h(st.eps_bits);
     for (int i = tid; i < AUC_SAMPLE; i += 1024) {
         unsigned short key = 0;                                            // padding sorts last
-        if (i < ns) {
+        if (ext_keys) {
+            if (i < ns) key = ext_keys[(size_t)w * ext_n + i];
+        } else if (i < ns) {
             // 16 consecutive jobs = one 32-byte sector of the row; chunks evenly strided over the jobs
             const long long nchunks = (ns + 15) / 16, chunk = i >> 4;
             long long col = (N / nchunks) * chunk + (i & 15);
@@ -789,7 +798,9 @@ auction_sample_kernel(const __half* __restrict__ S, long long ld, long long N, i
             key = (unsigned short)h2key(h2bits(v));
         }
         keys[i] = key;
+        if (collect_out && i < collect_n) collect_out[(size_t)w * collect_n + i] = key;
     }
+    if (collect_out) return;
     __syncthreads();
     // Only ranks r_hi .. r_lo of the descending order are needed (a few dozen for K >= 64): find the key at
     // rank r_lo by a two-level radix select, collect everything >= it and rank that short list by counting.
@@ -1251,8 +1262,9 @@ int rqk_auction_pass(const void* scores_t, int64_t ld, int64_t n, int32_t k, int
         cur = a.smem;
     }
     if (which == 0) which = 7;
-    if (n_global == n && (which & 1))   // sampled windows need the whole job set on this GPU (ranks must agree on the windows)
-        auction_sample_kernel<<<k, 1024, 0, (cudaStream_t)stream_>>>((const __half*)scores_t, ld, n, k, n_global / k, a.p);
+    if (n_global == n && (which & 1))   // sharded jobs: rqk_auction_sample_collect / _window (ranks must agree on the windows)
+        auction_sample_kernel<<<k, 1024, 0, (cudaStream_t)stream_>>>((const __half*)scores_t, ld, n, k, n_global / k, a.p,
+                                                                      nullptr, 0, nullptr, 0);
     if (which & 2) {
         static size_t hs_set = 0;
         const size_t hs = auction_hist_smem(k);
@@ -1264,6 +1276,36 @@ int rqk_auction_pass(const void* scores_t, int64_t ld, int64_t n, int32_t k, int
     }
     if (which & 4)
         kern<<<a.G, AUC_THREADS, a.smem, (cudaStream_t)stream_>>>((const __half*)scores_t, ld, n, k, n_global / k, a.p);
+    RQK_LAUNCH_OK();
+    return 0;
+}
+
+// Sharded window sampling, step 1: keys of `count` (<= 4096) evenly strided local jobs per worker -> out [k][count]
+// (uint16 fp16 keys).  Writes nothing unless the state machine wants a sample (then `out` is untouched and the
+// window step ignores it), so the host may call both steps unconditionally before every pass.
+int rqk_auction_sample_collect(const void* scores_t, int64_t ld, int64_t n, int32_t k, int64_t n_global, void* out,
+                               int32_t count, void* workspace, size_t workspace_bytes, void* stream_) {
+    using namespace rqk;
+    AuctionArgs a;
+    int rc = auction_prepare(n, ld, k, workspace, workspace_bytes, &a, "rqk_auction_sample_collect");
+    if (rc) return rc;
+    if (!scores_t || !out || count < 1 || count > AUC_SAMPLE) return fail(RQK_ERR_ARG, "rqk_auction_sample_collect: bad argument%s");
+    auction_sample_kernel<<<k, 1024, 0, (cudaStream_t)stream_>>>((const __half*)scores_t, ld, n, k, n_global / k, a.p,
+                                                                  (unsigned short*)out, count, nullptr, 0);
+    RQK_LAUNCH_OK();
+    return 0;
+}
+
+// Sharded window sampling, step 2: keys [k][count] = the all-gathered samples of every rank (count <= 4096).
+int rqk_auction_sample_window(int64_t n, int64_t ld, int32_t k, int64_t n_global, const void* keys, int32_t count,
+                              void* workspace, size_t workspace_bytes, void* stream_) {
+    using namespace rqk;
+    AuctionArgs a;
+    int rc = auction_prepare(n, ld, k, workspace, workspace_bytes, &a, "rqk_auction_sample_window");
+    if (rc) return rc;
+    if (!keys || count < 1 || count > AUC_SAMPLE) return fail(RQK_ERR_ARG, "rqk_auction_sample_window: bad argument%s");
+    auction_sample_kernel<<<k, 1024, 0, (cudaStream_t)stream_>>>(nullptr, ld, n_global, k, n_global / k, a.p, nullptr, 0,
+                                                                  (const unsigned short*)keys, count);
     RQK_LAUNCH_OK();
     return 0;
 }

@@ -194,7 +194,10 @@ def auction(scores_t: torch.Tensor, n: int, minmax: torch.Tensor,
     info = None
     for _ in range(0, 5000, batch):
         for _q in range(batch):
-            sess.do_pass()
+            # identical sampled windows on every rank: 4096 / world local jobs per worker, all-gathered
+            local = sess.sample_collect(max(4096 // shard.world, 1))
+            sess.sample_window(shard.all_gather(local).permute(1, 0, 2).reshape(k, -1))
+            sess.do_pass(6)
             shard.all_reduce(sess.reduce_block, "sum")
             sess.resolve()
             totals = shard.all_gather(sess.tie_total)                 # [world, k]
@@ -236,6 +239,20 @@ class AuctionSession:
         """which: 0 = sample + HIST + BID kernels (the state machine picks), or a subset (1 | 2 | 4)."""
         check(self.L.rqk_auction_pass(_ptr(self.s), self.ld, self.n, self.k, self.n_global, int(which),
                                       *self._args(), _stream(self.dev)))
+
+    def sample_collect(self, count: int) -> torch.Tensor:
+        """Sharded window sampling, step 1: int16 [k, count] fp16 keys of `count` local jobs per worker
+        (all zeros while the state machine does not ask for a sample)."""
+        out = torch.zeros((self.k, count), dtype=torch.int16, device=self.dev)
+        check(self.L.rqk_auction_sample_collect(_ptr(self.s), self.ld, self.n, self.k, self.n_global, _ptr(out),
+                                                int(count), *self._args(), _stream(self.dev)))
+        return out
+
+    def sample_window(self, keys: torch.Tensor):
+        """Step 2: keys int16 [k, total] = every rank's samples side by side (total <= 4096)."""
+        self._keys = keys.contiguous()
+        check(self.L.rqk_auction_sample_window(self.n, self.ld, self.k, self.n_global, _ptr(self._keys),
+                                               int(self._keys.shape[1]), *self._args(), _stream(self.dev)))
 
     def resolve(self):
         check(self.L.rqk_auction_resolve(self.n, self.ld, self.k, self.n_global, *self._args(), _stream(self.dev)))

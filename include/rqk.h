@@ -87,6 +87,12 @@ int rqk_auction_init(int64_t n, int64_t ld, int32_t k, const void* minmax_keys, 
                      size_t workspace_bytes, void* stream);
 int rqk_auction_pass(const void* scores_t, int64_t ld, int64_t n, int32_t k, int64_t n_global, int32_t which,
                      void* workspace, size_t workspace_bytes, void* stream);   /* which: 0 = all; bit0 sample, bit1 HIST, bit2 BID */
+/* sharded jobs: every rank samples `count` of its jobs per worker (uint16 fp16 keys, [k][count]); the host
+ * all-gathers them into [k][world*count] (<= 4096) and every rank places identical windows from the union */
+int rqk_auction_sample_collect(const void* scores_t, int64_t ld, int64_t n, int32_t k, int64_t n_global, void* out,
+                               int32_t count, void* workspace, size_t workspace_bytes, void* stream);
+int rqk_auction_sample_window(int64_t n, int64_t ld, int32_t k, int64_t n_global, const void* keys, int32_t count,
+                              void* workspace, size_t workspace_bytes, void* stream);
 int rqk_auction_resolve(int64_t n, int64_t ld, int32_t k, int64_t n_global, void* workspace, size_t workspace_bytes,
                         void* stream);
 int rqk_auction_tie_offset(int64_t n, int64_t ld, int32_t k, const int32_t* offsets, void* workspace,

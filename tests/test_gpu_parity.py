@@ -173,8 +173,9 @@ def test_auction_constant_matrix(dev, engine):
     assert np.array_equal(a.cpu().numpy().astype(np.int64), ref.assignment) and stats.rounds == ref.rounds
 
 
+@pytest.mark.parametrize("sampled", [True, False])
 @pytest.mark.parametrize("n,k,split", [(4100, 16, 2), (20010, 128, 3), (12900, 256, 2), (4096, 16, 4)])
-def test_sharded_auction_protocol_single_gpu_emulation(dev, engine, n, k, split):
+def test_sharded_auction_protocol_single_gpu_emulation(dev, engine, n, k, split, sampled):
     """The multi-GPU protocol (jobs sharded over ranks; reduce block summed between pass and resolve; tie
     totals gathered) driven for `split` virtual ranks in ONE process with the same C-ABI step functions.
     Must equal the unsharded result bit for bit."""
@@ -195,8 +196,12 @@ def test_sharded_auction_protocol_single_gpu_emulation(dev, engine, n, k, split)
         sess[-1].init(mm)
     done = False
     for _ in range(3000):
+        if sampled:      # identical windows on every rank from the all-gathered per-rank samples
+            allk = torch.cat([q.sample_collect(4096 // split) for q in sess], dim=1)
+            for q in sess:
+                q.sample_window(allk)
         for q in sess:
-            q.do_pass()
+            q.do_pass(6)
         total = sum(q.reduce_block.clone() for q in sess)
         for q in sess:
             q.reduce_block.copy_(total)
