@@ -56,9 +56,11 @@ class ShardGroup:
     def all_gather(self, t: torch.Tensor) -> torch.Tensor:
         if not self.active:
             return t.unsqueeze(0)
-        parts = [torch.empty_like(t) for _ in range(self.world)]
-        self.dist.all_gather(parts, t.contiguous(), group=self.group)
-        return torch.stack(parts)
+        # moved as raw bytes: NCCL has no 16-bit integer type and a gather needs none
+        raw = t.contiguous().reshape(-1).view(torch.uint8)
+        parts = [torch.empty_like(raw) for _ in range(self.world)]
+        self.dist.all_gather(parts, raw, group=self.group)
+        return torch.stack(parts).view(t.dtype).reshape((self.world,) + tuple(t.shape))
 
 
 _NO_SHARD = None
