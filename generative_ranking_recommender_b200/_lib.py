@@ -19,7 +19,7 @@ class AuctionInfo(ctypes.Structure):
     _fields_ = [
         ("done", c_i32), ("rounds", c_i32), ("passes", c_i32), ("cold_passes", c_i32),
         ("window_misses", c_i32), ("frozen_exit", c_i32), ("counter", c_i32),
-        ("eps_bits", ctypes.c_uint16), ("reserved", ctypes.c_uint16),
+        ("eps_bits", ctypes.c_uint16), ("list_passes", ctypes.c_uint16),
     ]
 
 

@@ -59,6 +59,8 @@ constexpr int AUC_MAX_JOBS_PER_CTA = 65024;   // 16-bit per-CTA counters
 constexpr int AUC_MIN_TILES_PER_CTA = 2;
 constexpr int AUC_COLD_SHIFT = 8;  // 256 bins x 256 keys cover all 65536 fp16 keys
 constexpr int AUC_MIN_KEY = 0x0400; // key of the most negative finite half: fine windows never reach -inf
+constexpr int AUC_SUB = 4096;      // jobs whose cost / owner are staged in shared memory at a time
+constexpr int AUC_SEG_CAP = 256;   // survivor-list entries per (sub-range, worker); ~60 expected
 
 enum { MODE_HIST = 0, MODE_BID = 1, MODE_DONE = 2 };
 
@@ -76,7 +78,10 @@ struct AuctionState {
     unsigned int smax_bits, smin_bits;
     int need_sample;    // windows are cold: estimate them from a sample before the next pass
     int error;
-    int pad_[15];
+    int use_list;       // the coming BID pass reads the survivor lists of the HIST pass instead of S
+    int force_scan;     // debugging / tests: never use the lists
+    int list_passes;    // BID passes served from the lists
+    int pad_[12];
 };
 
 struct AuctionPtrs {
@@ -101,6 +106,11 @@ struct AuctionPtrs {
     int* miss_run;            // [K] consecutive window slides
     unsigned int* tieprefix;  // [G][K]
     unsigned short* hist_cta; // [G][K][W] per-CTA histograms (16-bit: a CTA owns < 65536 jobs)
+    // survivor lists of the last HIST pass: every (worker, job) whose value reached the worker's window, i.e. a
+    // superset of the coming round's bidders.  One segment per (4096-job sub-range, worker), unordered.
+    unsigned int* seg_list;   // [G*spc][K][AUC_SEG_CAP]  (job - sub-range start) << 16 | value key
+    unsigned int* seg_cnt;    // [G*spc][K]  entries the HIST pass wanted to write (> AUC_SEG_CAP: overflow)
+    int* list_ok;             // [1] cleared by a HIST CTA whose segment overflowed
 };
 
 static inline int auction_tile_cols(int K) { return K <= 128 ? 128 : 64; }
@@ -113,6 +123,14 @@ static inline int auction_grid(long long N, int K) {
     if (g < g16) g = g16;
     if (g < 1) g = 1;
     return (int)g;
+}
+
+// sub-ranges per CTA (upper bound): CTA b owns tiles [T*b/G, T*(b+1)/G)
+static inline int auction_spc(long long N, int K) {
+    const int J = auction_tile_cols(K), G = auction_grid(N, K);
+    const long long tiles = ceil_div<long long>(N, J);
+    const long long len = ceil_div<long long>(tiles, G) * J;
+    return (int)ceil_div<long long>(len, AUC_SUB);
 }
 
 static inline size_t auction_ws_layout(long long N, long long ld, int K, AuctionPtrs* p, char* base,
@@ -135,6 +153,10 @@ static inline size_t auction_ws_layout(long long N, long long ld, int K, Auction
     size_t o_mr = take_((size_t)K * 4);
     size_t o_tp = take_((size_t)G * K * 4);
     size_t o_hc = take_((size_t)G * K * AUC_W * 2);
+    const size_t nseg = (size_t)G * auction_spc(N, K);
+    size_t o_sl = take_(nseg * K * AUC_SEG_CAP * 4);
+    size_t o_sc = take_(nseg * K * 4);
+    size_t o_lo = take_(4);
     if (reduce_off) *reduce_off = o_hist;
     if (tie_total_off) *tie_total_off = o_tt;
     if (p) {
@@ -157,6 +179,9 @@ static inline size_t auction_ws_layout(long long N, long long ld, int K, Auction
         p->miss_run = (int*)(base + o_mr);
         p->tieprefix = (unsigned int*)(base + o_tp);
         p->hist_cta = (unsigned short*)(base + o_hc);
+        p->seg_list = (unsigned int*)(base + o_sl);
+        p->seg_cnt = (unsigned int*)(base + o_sc);
+        p->list_ok = (int*)(base + o_lo);
     }
     return off;
 }
@@ -164,7 +189,7 @@ static inline size_t auction_ws_layout(long long N, long long ld, int K, Auction
 // ------------------------------------------------------------------------------------------
 // init: cost = 0, owner = -1, eps from the fp16 extrema (:33-34), cold windows
 // ------------------------------------------------------------------------------------------
-__global__ void auction_init_kernel(AuctionPtrs p, long long ld, int K, const unsigned int* minmax_keys) {
+__global__ void auction_init_kernel(AuctionPtrs p, long long ld, int K, const unsigned int* minmax_keys, int force_scan) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long stride = (long long)gridDim.x * blockDim.x;
     for (long long j = i; j < ld; j += stride) {
@@ -187,6 +212,8 @@ __global__ void auction_init_kernel(AuctionPtrs p, long long ld, int K, const un
         memset(&s, 0, sizeof(s));
         s.mode = MODE_HIST;
         s.need_sample = 1;
+        s.force_scan = force_scan;
+        *p.list_ok = 1;
         unsigned int smax = key2h(minmax_keys[0]), smin = key2h(minmax_keys[1]);
         // eps = (max - min) / 50 in fp16 (two roundings), floored at half(1e-4)  (:33-34)
         __half range = __hsub(bits2h(smax), bits2h(smin));
@@ -296,7 +323,7 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
     constexpr int MAXR = 256 / AUC_NW * (J == 128 ? 1 : 2) / 2;   // rows per warp: 8 (K<=128) / 16 (K<=256)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const AuctionState st = *p.st;
-    if (st.mode != MODE_BID) return;                   // HIST passes run in auction_hist_kernel
+    if (st.mode != MODE_BID || st.use_list) return;    // HIST passes run in auction_hist_kernel, list rounds in auction_bidlist_kernel
     const bool do_bid = true;
     const int ff = 0;
     const int counter = st.counter;
@@ -569,7 +596,10 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
 // Survivors are recorded as register bitmasks and histogrammed afterwards.
 // CTA b owns exactly the job range CTA b of the tiled BID kernel owns (the per-CTA dumps feed its tie prefix).
 // ------------------------------------------------------------------------------------------
-constexpr int HS_SUB = 4096;      // jobs staged (cost, owner) per sub-range
+constexpr int HS_SUB = AUC_SUB;   // jobs staged (cost, owner) per sub-range
+__host__ __device__ inline size_t auction_hist_smem_fixed(int K) {
+    return ((size_t)K * AUC_W * 2 + (size_t)HS_SUB * 4 + (size_t)K * 25 + 63) / 16 * 16;
+}
 
 __device__ __forceinline__ uint4 ldg_stream128(const void* ptr) {
     uint4 r;
@@ -579,7 +609,7 @@ __device__ __forceinline__ uint4 ldg_stream128(const void* ptr) {
 }
 
 __global__ void __launch_bounds__(AUC_THREADS, 2)
-auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int K, int J, AuctionPtrs p) {
+auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int K, int J, int spc, AuctionPtrs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const AuctionState st = *p.st;
     if (st.mode != MODE_HIST) return;
@@ -602,7 +632,9 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
         sm.r_lo2 = (unsigned int*)q;         q += (size_t)K * 4;
         sm.r_shift = (unsigned char*)q;      q += (size_t)K;
     }
+    unsigned int* seg_cnt_s = reinterpret_cast<unsigned int*>(smem_raw + auction_hist_smem_fixed(K));   // [K]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned int lt = (1u << lane) - 1u;
     const int G = gridDim.x, b = blockIdx.x;
     const long long tiles_total = (N + J - 1) / J;
     const long long c_begin = (tiles_total * b / G) * J;
@@ -623,8 +655,11 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
     }
     __syncthreads();
 
-    for (long long sub = c_begin; sub < c_end; sub += HS_SUB) {
+    int seg = b * spc;
+    for (long long sub = c_begin; sub < c_end; sub += HS_SUB, ++seg) {
         const int sublen = (int)((c_end - sub) < HS_SUB ? (c_end - sub) : HS_SUB);
+        unsigned int* seg_lists = p.seg_list + (size_t)seg * K * AUC_SEG_CAP;
+        if (tid < K) seg_cnt_s[tid] = 0;
         // ---- stage costs / owners of the sub-range (retain fast-forward applied here, once) ----
         for (int i = tid; i < HS_SUB; i += AUC_THREADS) {
             unsigned short c = 0;
@@ -645,8 +680,14 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
         // ---- owner entries (value = S): one per job ----
         for (int i = tid; i < sublen; i += AUC_THREADS) {
             const int o = own_s[i];
-            if (o >= 0 && sm.r_base[o] > 0)
-                window_count(sm, o, (int)h2key(h2bits(S[(size_t)o * ld + sub + i])));
+            if (o >= 0 && sm.r_base[o] > 0) {
+                const int key = (int)h2key(h2bits(S[(size_t)o * ld + sub + i]));
+                window_count(sm, o, key);
+                if (key >= sm.r_base[o]) {
+                    const unsigned int slot = atomicAdd(&seg_cnt_s[o], 1u);
+                    if (slot < AUC_SEG_CAP) seg_lists[(size_t)o * AUC_SEG_CAP + slot] = ((unsigned)i << 16) | (unsigned)key;
+                }
+            }
         }
         // ---- the sweep: rows of this warp, 4 x 256 jobs per step ----
         for (int w = warp; w < K; w += AUC_NW) {
@@ -685,6 +726,15 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
                         const __half v = __hsub(srow[cc], __ushort_as_half(cost_s[cc]));
                         const int key = (int)h2key(h2bits(v));
                         if (key < wbase) continue;
+                        {   // survivor list for the BID pass (warp-aggregated slot allocation)
+                            const unsigned int act = __activemask();
+                            const int leader = __ffs(act) - 1;
+                            unsigned int slot0 = 0;
+                            if (lane == leader) slot0 = atomicAdd(&seg_cnt_s[w], (unsigned)__popc(act));
+                            slot0 = __shfl_sync(act, slot0, leader);
+                            const unsigned int slot = slot0 + __popc(act & lt);
+                            if (slot < AUC_SEG_CAP) seg_lists[(size_t)w * AUC_SEG_CAP + slot] = ((unsigned)cc << 16) | (unsigned)key;
+                        }
                         if (wshift == 0) {
                             if (key >= whb) {
                                 if (key - whb >= AUC_W - wnlo) atomicAdd(&sm.above[w], 1u);
@@ -732,6 +782,11 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
             }
         }
         __syncthreads();
+        if (tid < K) {
+            const unsigned int c = seg_cnt_s[tid];
+            p.seg_cnt[(size_t)seg * K + tid] = c;
+            if (c > AUC_SEG_CAP) *p.list_ok = 0;
+        }
     }
 
     // ---- publish: per-CTA dump (for the tie prefix) + merge of non-empty bins ----
@@ -748,8 +803,153 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// BID pass from the survivor lists.  The HIST pass that resolved the thresholds already computed
+// S - cost for every entry and kept those at or above each worker's window (a superset of the
+// bidders, ~1.5 % of the matrix), so the bidding round does not have to read S again: CTA b replays
+// its own segments (L2-resident, written microseconds ago), then updates cost / owner of its jobs.
+// Same arithmetic as auction_pass_kernel; ties at the threshold are ranked by job index only in the
+// one segment per worker that straddles the worker's quota.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(AUC_THREADS, 2)
+auction_bidlist_kernel(long long N, int K, int J, int spc, AuctionPtrs p) {
+    const AuctionState st = *p.st;
+    if (st.mode != MODE_BID || !st.use_list) return;
+    constexpr int NCH = AUC_SEG_CAP / 32;
+    __shared__ unsigned int colmax[AUC_SUB];
+    __shared__ unsigned short cost_s[AUC_SUB];
+    __shared__ short own_s[AUC_SUB];
+    __shared__ unsigned char colviol[AUC_SUB];
+    __shared__ unsigned int tie_seen[256];
+    __shared__ int r_take[256], r_tk[256];
+    __shared__ unsigned int s_nwith, s_nviol;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int counter = st.counter;
+    const __half eps = bits2h(st.eps_bits);
+    const unsigned int eps_bits = st.eps_bits;
+    const bool retain = counter >= 1 && counter < 100;      // :86
+    const bool fallback = counter > 1000;                    // :88
+    const int G = gridDim.x, b = blockIdx.x;
+    const long long tiles_total = (N + J - 1) / J;
+    const long long c_begin = (tiles_total * b / G) * J;
+    long long c_end = (tiles_total * (b + 1) / G) * J;
+    if (c_end > N) c_end = N;
+
+    for (int i = tid; i < K; i += AUC_THREADS) {
+        tie_seen[i] = p.tieprefix[(size_t)b * K + i];
+        r_tk[i] = p.tkey[i];
+        r_take[i] = p.take[i];
+    }
+    if (tid == 0) { s_nwith = 0; s_nviol = 0; }
+
+    int seg = b * spc;
+    for (long long sub = c_begin; sub < c_end; sub += AUC_SUB, ++seg) {
+        const int sublen = (int)((c_end - sub) < AUC_SUB ? (c_end - sub) : AUC_SUB);
+        // ---- stage cost / owner; bids that do not depend on S (retain hack :87, fallback :89) ----
+        for (int i = tid; i < sublen; i += AUC_THREADS) {
+            const unsigned short c = __half_as_ushort(p.cost[sub + i]);
+            const short o = p.owner[sub + i];
+            cost_s[i] = c;
+            own_s[i] = o;
+            unsigned int init = 0;
+            if (o >= 0) { if (retain) init = (eps_bits << 16) | (0xffffu - (unsigned)o); }
+            else if (fallback) init = (eps_bits << 16) | 0xffffu;
+            colmax[i] = init;
+            colviol[i] = 0;
+        }
+        __syncthreads();
+        // ---- segments: a warp per worker ----
+        for (int w = warp; w < K; w += AUC_NW) {
+            unsigned int E = p.seg_cnt[(size_t)seg * K + w];
+            if (E > AUC_SEG_CAP) E = AUC_SEG_CAP;            // cannot happen when use_list is set
+            const unsigned int* L = p.seg_list + ((size_t)seg * K + w) * AUC_SEG_CAP;
+            const int tk = r_tk[w];
+            const __half T = bits2h(key2h((unsigned)tk));
+            unsigned int ent[NCH], tmask[NCH];
+            unsigned int n_ties = 0;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const unsigned int idx = c * 32 + lane;
+                ent[c] = (idx < E) ? __ldcg(L + idx) : 0u;   // key 0 is below every threshold: never a bidder
+                tmask[c] = __ballot_sync(0xffffffffu, idx < E && (int)(ent[c] & 0xffffu) == tk);
+                n_ties += __popc(tmask[c]);
+            }
+            const unsigned int seen0 = tie_seen[w];
+            const long long quota = r_take[w];
+            const bool all_rej = (long long)seen0 >= quota;
+            const bool all_acc = (long long)seen0 + n_ties <= quota;
+            unsigned int rank[NCH];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) rank[c] = 0;
+            if (n_ties && !all_rej && !all_acc) {
+                // the segment straddles the quota: rank its ties by job index (lowest first)
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    unsigned int m = tmask[c];
+                    while (m) {
+                        const int src = __ffs(m) - 1;
+                        m &= m - 1;
+                        const unsigned int jsrc = __shfl_sync(0xffffffffu, ent[c], src) >> 16;
+#pragma unroll
+                        for (int c2 = 0; c2 < NCH; ++c2) rank[c2] += ((ent[c2] >> 16) > jsrc) ? 1u : 0u;
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const unsigned int idx = c * 32 + lane;
+                if (idx >= E) continue;
+                const int key = (int)(ent[c] & 0xffffu);
+                const int cc = (int)(ent[c] >> 16);
+                bool bidder = key > tk;
+                if (key == tk) bidder = all_acc || (!all_rej && (long long)seen0 + rank[c] < quota);
+                if (!bidder) continue;
+                const int o = own_s[cc];
+                const bool own = (o == w);
+                if (fallback && w == 0 && o < 0) continue;                       // :89 overrides worker 0's own bid
+                const __half v = bits2h(key2h((unsigned)key));
+                unsigned int bid = h2bits(__hadd(__hsub(v, T), eps));            // :76, two roundings
+                if (retain && own) bid = eps_bits;                               // :87
+                if (!own) colviol[cc] = 1;
+                atomicMax(&colmax[cc], (bid << 16) | (0xffffu - (unsigned)w));   // :104
+            }
+            if (lane == 0) tie_seen[w] = seen0 + n_ties;
+        }
+        __syncthreads();
+        // ---- highest bid per job, cost / owner update (:104, :118-123) ----
+        for (int i0 = 0; i0 < sublen; i0 += AUC_THREADS) {
+            const int i = i0 + tid;
+            bool has = false, vv = false;
+            if (i < sublen) {
+                const unsigned int pk = colmax[i];
+                const short old_owner = own_s[i];
+                vv = colviol[i] != 0;
+                if (pk) {
+                    has = true;
+                    const short wnr = (short)(0xffffu - (pk & 0xffffu));
+                    p.cost[sub + i] = __hadd(__ushort_as_half(cost_s[i]), bits2h(pk >> 16));
+                    if (wnr != old_owner) p.owner[sub + i] = wnr;
+                } else {
+                    if (old_owner >= 0) { p.owner[sub + i] = -1; vv = true; }    // an owned job lost its bidder
+                }
+            }
+            const unsigned int mh = __ballot_sync(0xffffffffu, has);
+            const unsigned int mv = __ballot_sync(0xffffffffu, vv);
+            if (lane == 0) {
+                if (mh) atomicAdd(&s_nwith, __popc(mh));
+                if (mv) atomicAdd(&s_nviol, __popc(mv));
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        if (s_nwith) atomicAdd(p.n_with, s_nwith);
+        if (s_nviol) atomicAdd(p.n_viol, s_nviol);
+    }
+}
+
 static inline size_t auction_hist_smem(int K) {
-    return (size_t)K * AUC_W * 2 + (size_t)HS_SUB * 4 + (size_t)K * 25 + 64;
+    return auction_hist_smem_fixed(K) + (size_t)K * 4;
 }
 
 static inline size_t auction_pass_smem(int K, int J) {
@@ -978,6 +1178,7 @@ auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
             s.mode = MODE_DONE;
             s.done = 1;
             s.passes += 1;
+            if (s.use_list) s.list_passes += 1;
             *p.st = s;
         }
         return;
@@ -1108,6 +1309,11 @@ auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
         if (was_bid) s.counter += 1;                                     // :125
         s.ff_pending = 0;
         s.need_sample = was_bid ? 1 : 0;
+        if (was_bid && s.use_list) s.list_passes += 1;
+        if (!was_bid) {      // lists of the pass that just ran: complete unless a segment overflowed
+            s.use_list = (*p.list_ok != 0 && !s.force_scan) ? 1 : 0;
+            *p.list_ok = 1;
+        }
         if (jump) {
             // frozen at counter c (already incremented to c+1): rounds c+1..99 add eps each
             s.ff_pending = 100 - s.counter;
@@ -1206,7 +1412,7 @@ struct rqk_auction_info {
     int32_t frozen_exit;    // 1 = ended through the frozen-state shortcut
     int32_t counter;        // reference `counter` at exit
     uint16_t eps_bits;
-    uint16_t reserved;
+    uint16_t list_passes;
 };
 
 int rqk_auction_layout_query(int64_t n, int32_t k, rqk_auction_layout* out) {
@@ -1236,7 +1442,8 @@ int rqk_auction_init(int64_t n, int64_t ld, int32_t k, const void* minmax_keys, 
     if (!minmax_keys) return fail(RQK_ERR_ARG, "rqk_auction_init: null minmax_keys%s");
     cudaStream_t stream = (cudaStream_t)stream_;
     RQK_CUDA_OK(cudaMemsetAsync(a.p.tieprefix, 0, (size_t)a.G * k * 4, stream));
-    auction_init_kernel<<<148, 256, 0, stream>>>(a.p, ld, k, (const unsigned int*)minmax_keys);
+    const char* ns = getenv("RQK_AUCTION_NO_LIST");      // tests: force the S-scanning BID kernel
+    auction_init_kernel<<<148, 256, 0, stream>>>(a.p, ld, k, (const unsigned int*)minmax_keys, (ns && ns[0] == '1') ? 1 : 0);
     RQK_LAUNCH_OK();
     return 0;
 }
@@ -1272,10 +1479,13 @@ int rqk_auction_pass(const void* scores_t, int64_t ld, int64_t n, int32_t k, int
             RQK_CUDA_OK(cudaFuncSetAttribute(auction_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
             hs_set = hs;
         }
-        auction_hist_kernel<<<a.G, AUC_THREADS, hs, (cudaStream_t)stream_>>>((const __half*)scores_t, ld, n, k, a.J, a.p);
+        auction_hist_kernel<<<a.G, AUC_THREADS, hs, (cudaStream_t)stream_>>>((const __half*)scores_t, ld, n, k, a.J,
+                                                                              auction_spc(n, k), a.p);
     }
-    if (which & 4)
+    if (which & 4) {
+        auction_bidlist_kernel<<<a.G, AUC_THREADS, 0, (cudaStream_t)stream_>>>(n, k, a.J, auction_spc(n, k), a.p);
         kern<<<a.G, AUC_THREADS, a.smem, (cudaStream_t)stream_>>>((const __half*)scores_t, ld, n, k, n_global / k, a.p);
+    }
     RQK_LAUNCH_OK();
     return 0;
 }
@@ -1357,7 +1567,7 @@ int rqk_auction_poll(int64_t n, int64_t ld, int32_t k, void* workspace, size_t w
     info->frozen_exit = host.frozen_exit;
     info->counter = host.counter;
     info->eps_bits = (uint16_t)host.eps_bits;
-    info->reserved = 0;
+    info->list_passes = (uint16_t)(host.list_passes > 65535 ? 65535 : host.list_passes);
     return 0;
 }
 

@@ -256,7 +256,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 float4* lo = reinterpret_cast<float4*>(st + a_bytes + (size_t)r * 128);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    const int ch = (c + lane) & 7;          // rotate chunks across lanes: no bank conflicts
+                    // logical 16-byte chunk c of the row sits at physical chunk c ^ (row & 7) (SWIZZLE_128B), which
+                    // is also conflict-free; summing in LOGICAL order keeps a row's norm independent of where
+                    // the row lands in a tile, so row-sharded runs reproduce the unsharded scores bit for bit
+                    const int ch = c ^ (lane & 7);
                     float4 v = hi[ch];
                     nrm = fmaf(v.x, v.x, nrm); nrm = fmaf(v.y, v.y, nrm);
                     nrm = fmaf(v.z, v.z, nrm); nrm = fmaf(v.w, v.w, nrm);

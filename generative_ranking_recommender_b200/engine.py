@@ -159,12 +159,13 @@ class AuctionStats:
     window_misses: int
     frozen_exit: bool
     eps: float
+    list_passes: int = 0
 
 
 def _info_to_stats(info: AuctionInfo) -> AuctionStats:
     eps = float(np.array([info.eps_bits], dtype=np.uint16).view(np.float16)[0])
     return AuctionStats(int(info.rounds), int(info.passes), int(info.cold_passes), int(info.window_misses),
-                        bool(info.frozen_exit), eps)
+                        bool(info.frozen_exit), eps, int(info.list_passes))
 
 
 def auction(scores_t: torch.Tensor, n: int, minmax: torch.Tensor,

@@ -69,7 +69,7 @@ typedef struct rqk_auction_info {
     int32_t frozen_exit;   /* 1: finished through the frozen-state fast-forward */
     int32_t counter;
     uint16_t eps_bits;     /* fp16 eps of :33-34 */
-    uint16_t reserved;
+    uint16_t list_passes;    /* bidding rounds served from the HIST pass's survivor lists (no second read of S) */
 } rqk_auction_info;
 
 typedef struct rqk_auction_layout {

@@ -98,6 +98,20 @@ def test_score_pass_farthest_quirk(dev, engine):
     assert (r.argmin.cpu().numpy() == want).mean() > 0.98
 
 
+def test_score_rows_do_not_depend_on_tile_position(dev, engine):
+    """A row's scores must not change with the row's position inside a 128-row tile: a rank's row block of a
+    sharded fit then reproduces its columns of the unsharded score matrix bit for bit."""
+    g = torch.Generator().manual_seed(3)
+    n = 5000
+    x = torch.randn((n, 512), generator=g).to(dev)
+    c = x[torch.arange(0, n, n // 64)[:64]].contiguous()
+    full = engine.score_pass(x, c, scores=True, argmin=True)
+    for off in (3, 59, 1001):
+        part = engine.score_pass(x[off:].contiguous(), c, scores=True, argmin=True)
+        assert torch.equal(part.scores_t[:, :n - off].view(torch.int16), full.scores_t[:, off:n].view(torch.int16)), off
+        assert torch.equal(part.argmin, full.argmin[off:])
+
+
 def test_tensor_core_and_cuda_core_kernels_agree(dev, engine):
     x = torch.from_numpy(O.synth_mix(30000, 512, seed=9)).to(dev)
     c = x[:128].clone() * 1.01
@@ -110,7 +124,18 @@ def test_tensor_core_and_cuda_core_kernels_agree(dev, engine):
 # ------------------------------------------------------------------------------------------------
 # balanced auction
 # ------------------------------------------------------------------------------------------------
-def test_auction_golden_vectors_from_reference(dev, engine, golden_dir):
+@pytest.fixture(params=["lists", "scan"])
+def bid_path(request, monkeypatch):
+    """Both implementations of the bidding round: replaying the HIST pass's survivor lists (default) and
+    re-reading the score matrix (the fallback when a list segment overflows)."""
+    if request.param == "scan":
+        monkeypatch.setenv("RQK_AUCTION_NO_LIST", "1")
+    else:
+        monkeypatch.delenv("RQK_AUCTION_NO_LIST", raising=False)
+    return request.param
+
+
+def test_auction_golden_vectors_from_reference(dev, engine, golden_dir, bid_path):
     g = np.load(os.path.join(golden_dir, "auction.npz"))
     from generative_ranking_recommender_b200.balancekmeans import auction_lap_half
     so = ao = 0
@@ -128,7 +153,7 @@ def test_auction_golden_vectors_from_reference(dev, engine, golden_dir):
 @pytest.mark.parametrize("n,k,dim", [(64, 4, 64), (130, 4, 64), (1000, 8, 64), (4096, 16, 64), (4100, 16, 64),
                                      (6000, 32, 128), (20000, 128, 128), (20010, 128, 128), (12800, 256, 64),
                                      (12900, 256, 64), (256, 256, 64), (300, 256, 64), (16384, 64, 64)])
-def test_auction_bit_exact_vs_oracle(dev, engine, n, k, dim):
+def test_auction_bit_exact_vs_oracle(dev, engine, n, k, dim, bid_path):
     """Identical fp16 matrix in -> identical assignment out, including the 1002-round fallback regime
     (which the GPU reaches through the frozen-state fast-forward while the oracle simulates every round)."""
     rng = np.random.default_rng(n)
@@ -142,6 +167,7 @@ def test_auction_bit_exact_vs_oracle(dev, engine, n, k, dim):
     assert np.array_equal(a, ref.assignment), f"{(a != ref.assignment).sum()} of {n} differ"
     assert stats.rounds == ref.rounds
     assert abs(stats.eps - ref.eps) == 0
+    assert (stats.list_passes > 0) == (bid_path == "lists"), stats
     if n % k:
         assert stats.rounds == 1002 and stats.frozen_exit and stats.passes < 200
         sizes = np.bincount(a, minlength=k)
@@ -150,7 +176,7 @@ def test_auction_bit_exact_vs_oracle(dev, engine, n, k, dim):
         assert (np.bincount(a, minlength=k) == n // k).all()
 
 
-def test_auction_heavy_ties(dev, engine):
+def test_auction_heavy_ties(dev, engine, bid_path):
     """Few distinct fp16 values: the canonical lowest-job-index rule decides almost every round."""
     rng = np.random.default_rng(5)
     n, k = 5000, 16
@@ -164,7 +190,7 @@ def test_auction_heavy_ties(dev, engine):
     assert stats.rounds == ref.rounds
 
 
-def test_auction_constant_matrix(dev, engine):
+def test_auction_constant_matrix(dev, engine, bid_path):
     n, k = 1024, 8
     s = np.full((k, n), np.float16(-1.5)).view(np.uint16)
     ref = O.auction_lap_half_t(s)
@@ -175,7 +201,7 @@ def test_auction_constant_matrix(dev, engine):
 
 @pytest.mark.parametrize("sampled", [True, False])
 @pytest.mark.parametrize("n,k,split", [(4100, 16, 2), (20010, 128, 3), (12900, 256, 2), (4096, 16, 4)])
-def test_sharded_auction_protocol_single_gpu_emulation(dev, engine, n, k, split, sampled):
+def test_sharded_auction_protocol_single_gpu_emulation(dev, engine, n, k, split, sampled, bid_path):
     """The multi-GPU protocol (jobs sharded over ranks; reduce block summed between pass and resolve; tie
     totals gathered) driven for `split` virtual ranks in ONE process with the same C-ABI step functions.
     Must equal the unsharded result bit for bit."""
