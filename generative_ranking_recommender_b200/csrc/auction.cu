@@ -60,6 +60,7 @@ constexpr int AUC_MIN_TILES_PER_CTA = 2;
 constexpr int AUC_COLD_SHIFT = 8;  // 256 bins x 256 keys cover all 65536 fp16 keys
 constexpr int AUC_MIN_KEY = 0x0400; // key of the most negative finite half: fine windows never reach -inf
 constexpr int AUC_SUB = 4096;      // jobs whose cost / owner are staged in shared memory at a time
+constexpr int AUC_QCAP = 128;      // per-warp survivor queue of the HIST kernel
 constexpr int AUC_SEG_CAP = 256;   // survivor-list entries per (sub-range, worker); ~60 expected
 
 enum { MODE_HIST = 0, MODE_BID = 1, MODE_DONE = 2 };
@@ -633,6 +634,7 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
         sm.r_shift = (unsigned char*)q;      q += (size_t)K;
     }
     unsigned int* seg_cnt_s = reinterpret_cast<unsigned int*>(smem_raw + auction_hist_smem_fixed(K));   // [K]
+    unsigned short* hq = reinterpret_cast<unsigned short*>(seg_cnt_s + K);                             // [AUC_NW][AUC_QCAP]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned int lt = (1u << lane) - 1u;
     const int G = gridDim.x, b = blockIdx.x;
@@ -654,6 +656,7 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
         sm.r_lo2[i] = lob | (lob << 16);
     }
     __syncthreads();
+    const int any_cold = __syncthreads_or(tid < K && sm.r_base[tid] <= 0);   // cold rows take the unpipelined path
 
     int seg = b * spc;
     for (long long sub = c_begin; sub < c_end; sub += HS_SUB, ++seg) {
@@ -690,51 +693,108 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
             }
         }
         // ---- the sweep: rows of this warp, 4 x 256 jobs per step ----
-        for (int w = warp; w < K; w += AUC_NW) {
-            const __half* srow = S + (size_t)w * ld + sub;
+        auto load4 = [&](const __half* srow, int c0, uint4 (&sv)[4]) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int cc = c0 + q * 256 + lane * 8;
+                if (cc < sublen) sv[q] = ldg_stream128(srow + cc);               // ld is a multiple of 128: in bounds
+                else sv[q] = make_uint4(0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u);
+            }
+        };
+        auto process = [&](int w, const __half* srow, int c0, const uint4 (&sv)[4]) {
             const int wbase = sm.r_base[w];
-            if (wbase > 0) {
-                const __half2 f2 = u2h2(sm.r_lo2[w]);
-                const int whb = sm.r_hbase[w], wnlo = sm.r_nlo[w], wshift = sm.r_shift[w];
-                for (int c0 = 0; c0 < sublen; c0 += 1024) {
-                    uint4 sv[4];
+            const __half2 f2 = u2h2(sm.r_lo2[w]);
+            unsigned int acc = 0;   // low half bit 4q+h: job 2h of load q survives; high half: job 2h+1
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int cc = c0 + q * 256 + lane * 8;
+                const uint4 cv = (cc < HS_SUB) ? *reinterpret_cast<const uint4*>(cost_s + cc) : make_uint4(0, 0, 0, 0);
+                const unsigned int sw[4] = {sv[q].x, sv[q].y, sv[q].z, sv[q].w};
+                const unsigned int cw[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const __half2 v2 = __hsub2(u2h2(sw[h]), u2h2(cw[h]));
+                    acc |= __hge2_mask(v2, f2) & ((1u << (4 * q + h)) | (1u << (16 + 4 * q + h)));
+                }
+            }
+            if (!__any_sync(0xffffffffu, acc != 0)) return;
+            const int whb = sm.r_hbase[w], wnlo = sm.r_nlo[w], wshift = sm.r_shift[w];
+            while (acc) {
+                const int bpos = __ffs(acc) - 1;
+                acc &= acc - 1;
+                const int pq = bpos & 15;
+                const int cc = c0 + (pq >> 2) * 256 + lane * 8 + 2 * (pq & 3) + (bpos >> 4);
+                if (cc >= sublen || own_s[cc] == w) continue;                    // owner entry: counted above
+                const __half v = __hsub(srow[cc], __ushort_as_half(cost_s[cc]));
+                const int key = (int)h2key(h2bits(v));
+                if (key < wbase) continue;
+                {   // survivor list for the BID pass (warp-aggregated slot allocation)
+                    const unsigned int act = __activemask();
+                    const int leader = __ffs(act) - 1;
+                    unsigned int slot0 = 0;
+                    if (lane == leader) slot0 = atomicAdd(&seg_cnt_s[w], (unsigned)__popc(act));
+                    slot0 = __shfl_sync(act, slot0, leader);
+                    const unsigned int slot = slot0 + __popc(act & lt);
+                    if (slot < AUC_SEG_CAP) seg_lists[(size_t)w * AUC_SEG_CAP + slot] = ((unsigned)cc << 16) | (unsigned)key;
+                }
+                if (wshift == 0) {
+                    if (key >= whb) {
+                        if (key - whb >= AUC_W - wnlo) atomicAdd(&sm.above[w], 1u);
+                        else hist_add(sm.hist, w, wnlo + key - whb);
+                    } else if (key >= wbase + wnlo) {
+                        atomicAdd(&sm.gap[w], 1u);
+                    } else {
+                        hist_add(sm.hist, w, key - wbase);
+                    }
+                } else {
+                    const int bin = (key - wbase) >> wshift;
+                    if (bin >= AUC_W) atomicAdd(&sm.above[w], 1u);
+                    else hist_add(sm.hist, w, bin);
+                }
+            }
+        };
+        if (!any_cold) {
+            // Fast path (every row has a fine window).  Software-pipelined: the next step's four 16-byte loads
+            // are in flight while this step is filtered, across row boundaries too.  Survivors are not
+            // handled by the lane that found them (a divergent loop, ~5 of 32 lanes busy) but pushed as
+            // job offsets into a per-warp queue and handled 32 at a time when the queue fills / the row ends.
+            unsigned short* wq = hq + warp * AUC_QCAP;
+            int qn = 0;
+            const int nfull = sublen >> 10, nsteps = (sublen + 1023) >> 10;
+            auto load_step = [&](int w, int st, uint4 (&sv)[4]) {
+                const uint4* rp = reinterpret_cast<const uint4*>(S + (size_t)w * ld + sub) + (st << 7) + lane;
+                if (st < nfull) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) sv[q] = ldg_stream128(rp + q * 32);
+                } else {   // tail step; columns >= N of S hold -inf and their staged cost is 0: they never survive
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const int cc = c0 + q * 256 + lane * 8;
-                        if (cc < sublen) sv[q] = ldg_stream128(srow + cc);       // ld is a multiple of 128: in bounds
-                        else sv[q] = make_uint4(0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u);
+                        sv[q] = make_uint4(0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u);
+                        if ((st << 10) + q * 256 + lane * 8 < sublen) sv[q] = ldg_stream128(rp + q * 32);
                     }
-                    unsigned int acc = 0;   // low half bit 4q+h: job 2h of load q survives; high half: job 2h+1
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int cc = c0 + q * 256 + lane * 8;
-                        const uint4 cv = (cc < HS_SUB) ? *reinterpret_cast<const uint4*>(cost_s + cc) : make_uint4(0, 0, 0, 0);
-                        const unsigned int sw[4] = {sv[q].x, sv[q].y, sv[q].z, sv[q].w};
-                        const unsigned int cw[4] = {cv.x, cv.y, cv.z, cv.w};
-#pragma unroll
-                        for (int h = 0; h < 4; ++h) {
-                            const __half2 v2 = __hsub2(u2h2(sw[h]), u2h2(cw[h]));
-                            acc |= __hge2_mask(v2, f2) & ((1u << (4 * q + h)) | (1u << (16 + 4 * q + h)));
-                        }
+                }
+            };
+            auto flush = [&](int w) {
+                const __half* srow = S + (size_t)w * ld + sub;
+                const int wbase = sm.r_base[w], whb = sm.r_hbase[w], wnlo = sm.r_nlo[w], wshift = sm.r_shift[w];
+                unsigned int* lw = seg_lists + (size_t)w * AUC_SEG_CAP;
+                __syncwarp();
+                for (int i0 = 0; i0 < qn; i0 += 32) {
+                    const int i = i0 + lane;
+                    bool live = i < qn;
+                    const int cc = live ? (int)wq[i] : 0;
+                    live = live && own_s[cc] != w;                               // owner entry: counted above
+                    int key = 0;
+                    if (live) key = (int)h2key(h2bits(__hsub(srow[cc], __ushort_as_half(cost_s[cc]))));
+                    const unsigned int m = __ballot_sync(0xffffffffu, live);
+                    if (m) {
+                        unsigned int slot0 = 0;
+                        if (lane == 0) slot0 = atomicAdd(&seg_cnt_s[w], (unsigned)__popc(m));
+                        slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+                        const unsigned int slot = slot0 + __popc(m & lt);
+                        if (live && slot < AUC_SEG_CAP) lw[slot] = ((unsigned)cc << 16) | (unsigned)key;
                     }
-                    while (acc) {
-                        const int bpos = __ffs(acc) - 1;
-                        acc &= acc - 1;
-                        const int pq = bpos & 15;
-                        const int cc = c0 + (pq >> 2) * 256 + lane * 8 + 2 * (pq & 3) + (bpos >> 4);
-                        if (cc >= sublen || own_s[cc] == w) continue;            // owner entry: counted above
-                        const __half v = __hsub(srow[cc], __ushort_as_half(cost_s[cc]));
-                        const int key = (int)h2key(h2bits(v));
-                        if (key < wbase) continue;
-                        {   // survivor list for the BID pass (warp-aggregated slot allocation)
-                            const unsigned int act = __activemask();
-                            const int leader = __ffs(act) - 1;
-                            unsigned int slot0 = 0;
-                            if (lane == leader) slot0 = atomicAdd(&seg_cnt_s[w], (unsigned)__popc(act));
-                            slot0 = __shfl_sync(act, slot0, leader);
-                            const unsigned int slot = slot0 + __popc(act & lt);
-                            if (slot < AUC_SEG_CAP) seg_lists[(size_t)w * AUC_SEG_CAP + slot] = ((unsigned)cc << 16) | (unsigned)key;
-                        }
+                    if (live) {
                         if (wshift == 0) {
                             if (key >= whb) {
                                 if (key - whb >= AUC_W - wnlo) atomicAdd(&sm.above[w], 1u);
@@ -750,6 +810,91 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
                             else hist_add(sm.hist, w, bin);
                         }
                     }
+                }
+                qn = 0;
+                __syncwarp();
+            };
+            uint4 cur[4], nxt[4];
+            int w = warp, st = 0;
+            if (w < K) load_step(w, 0, cur);
+            while (w < K) {
+                int wn = w, sn = st + 1;
+                if (sn == nsteps) { wn = w + AUC_NW; sn = 0; }
+                if (wn < K) load_step(wn, sn, nxt);
+                // ---- filter: v = S - cost against the window's low edge ----
+                const __half2 f2 = u2h2(sm.r_lo2[w]);
+                const uint4* cp = reinterpret_cast<const uint4*>(cost_s) + (st << 7) + lane;
+                unsigned int acc = 0;   // low half bit 4q+h: job 2h of load q survives; high half: job 2h+1
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint4 cv = cp[q * 32];
+                    const unsigned int sw[4] = {cur[q].x, cur[q].y, cur[q].z, cur[q].w};
+                    const unsigned int cw[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        const __half2 v2 = __hsub2(u2h2(sw[h]), u2h2(cw[h]));
+                        acc |= __hge2_mask(v2, f2) & ((1u << (4 * q + h)) | (1u << (16 + 4 * q + h)));
+                    }
+                }
+                // ---- push the survivors' job offsets ----
+                const int mine = __popc(acc);
+                int incl = mine;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += o;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                if (total) {
+                    const int cbase = (st << 10) + lane * 8;
+                    if (qn + total > AUC_QCAP) flush(w);
+                    if (total <= AUC_QCAP) {
+                        int pos = qn + incl - mine;
+                        while (acc) {
+                            const int bpos = __ffs(acc) - 1;
+                            acc &= acc - 1;
+                            const int pq = bpos & 15;
+                            wq[pos++] = (unsigned short)(cbase + ((pq >> 2) << 8) + ((pq & 3) << 1) + (bpos >> 4));
+                        }
+                        qn += total;
+                    } else {
+                        // more than a queue's worth in one step (only with very wide windows): 4 per lane per round
+                        while (__any_sync(0xffffffffu, acc != 0)) {
+                            const int pc = __popc(acc);
+                            const int take = pc < 4 ? pc : 4;
+                            int in2 = take;
+#pragma unroll
+                            for (int d = 1; d < 32; d <<= 1) {
+                                const int o = __shfl_up_sync(0xffffffffu, in2, d);
+                                if (lane >= d) in2 += o;
+                            }
+                            int pos = in2 - take;
+                            for (int r = 0; r < take; ++r) {
+                                const int bpos = __ffs(acc) - 1;
+                                acc &= acc - 1;
+                                const int pq = bpos & 15;
+                                wq[pos++] = (unsigned short)(cbase + ((pq >> 2) << 8) + ((pq & 3) << 1) + (bpos >> 4));
+                            }
+                            qn = __shfl_sync(0xffffffffu, in2, 31);
+                            flush(w);
+                        }
+                    }
+                }
+                if (sn == 0 && qn) flush(w);                                     // the queue is per row
+#pragma unroll
+                for (int q = 0; q < 4; ++q) cur[q] = nxt[q];
+                w = wn;
+                st = sn;
+            }
+        } else
+        for (int w = warp; w < K; w += AUC_NW) {
+            const __half* srow = S + (size_t)w * ld + sub;
+            const int wbase = sm.r_base[w];
+            if (wbase > 0) {
+                for (int c0 = 0; c0 < sublen; c0 += 1024) {
+                    uint4 sv[4];
+                    load4(srow, c0, sv);
+                    process(w, srow, c0, sv);
                 }
             } else {
                 // cold row (all 65536 keys in 128 coarse bins): exact values, every element
@@ -949,7 +1094,7 @@ auction_bidlist_kernel(long long N, int K, int J, int spc, AuctionPtrs p) {
 }
 
 static inline size_t auction_hist_smem(int K) {
-    return auction_hist_smem_fixed(K) + (size_t)K * 4;
+    return auction_hist_smem_fixed(K) + (size_t)K * 4 + (size_t)AUC_NW * AUC_QCAP * 2;
 }
 
 static inline size_t auction_pass_smem(int K, int J) {
