@@ -112,6 +112,7 @@ struct AuctionPtrs {
     unsigned int* seg_list;   // [G*spc][K][AUC_SEG_CAP]  (job - sub-range start) << 16 | value key
     unsigned int* seg_cnt;    // [G*spc][K]  entries the HIST pass wanted to write (> AUC_SEG_CAP: overflow)
     int* list_ok;             // [1] cleared by a HIST CTA whose segment overflowed
+    unsigned int* ticket;     // [1] CTAs finished in the running pass kernel (fused resolve)
 };
 
 static inline int auction_tile_cols(int K) { return K <= 128 ? 128 : 64; }
@@ -158,6 +159,7 @@ static inline size_t auction_ws_layout(long long N, long long ld, int K, Auction
     size_t o_sl = take_(nseg * K * AUC_SEG_CAP * 4);
     size_t o_sc = take_(nseg * K * 4);
     size_t o_lo = take_(4);
+    size_t o_tk2 = take_(4);
     if (reduce_off) *reduce_off = o_hist;
     if (tie_total_off) *tie_total_off = o_tt;
     if (p) {
@@ -183,6 +185,7 @@ static inline size_t auction_ws_layout(long long N, long long ld, int K, Auction
         p->seg_list = (unsigned int*)(base + o_sl);
         p->seg_cnt = (unsigned int*)(base + o_sc);
         p->list_ok = (int*)(base + o_lo);
+        p->ticket = (unsigned int*)(base + o_tk2);
     }
     return off;
 }
@@ -215,6 +218,7 @@ __global__ void auction_init_kernel(AuctionPtrs p, long long ld, int K, const un
         s.need_sample = 1;
         s.force_scan = force_scan;
         *p.list_ok = 1;
+        *p.ticket = 0;
         unsigned int smax = key2h(minmax_keys[0]), smin = key2h(minmax_keys[1]);
         // eps = (max - min) / 50 in fp16 (two roundings), floored at half(1e-4)  (:33-34)
         __half range = __hsub(bits2h(smax), bits2h(smin));
@@ -226,6 +230,211 @@ __global__ void auction_init_kernel(AuctionPtrs p, long long ld, int K, const un
         s.smin_bits = smin;
         *p.st = s;
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// resolve: merged histograms -> thresholds / next windows / state machine.  One CTA.
+// ------------------------------------------------------------------------------------------
+// `expect`: -1, or the mode whose pass must have just run (MODE_HIST / MODE_BID) for the call to act.
+__device__ __noinline__ void auction_resolve_body(AuctionPtrs p, long long N, int K, long long jpw, int expect) {
+    __shared__ int s_unresolved, s_miss;
+    __shared__ AuctionState s;
+    __shared__ unsigned long long s_nwith_g, s_nviol_g;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NT = blockDim.x, NWARPS = NT >> 5;
+    if (tid == 0) { s = *p.st; s_unresolved = 0; s_miss = 0; s_nwith_g = *p.n_with; s_nviol_g = *p.n_viol; }
+    __syncthreads();
+    if (s.mode == MODE_DONE || (expect >= 0 && s.mode != expect)) return;
+    const bool was_bid = (s.mode == MODE_BID);
+
+    // ---- 1. outcome of the bidding round that just ran ----
+    bool finished = false, jump = false;
+    if (was_bid) {
+        if (s_nwith_g == (unsigned long long)N) {
+            finished = true;                                  // :113-114
+        } else if (s_nviol_g == 0 && s.counter >= 1) {
+            if (s.counter >= 100 && s.counter <= 1000) finished = true;   // frozen: ends at counter 1001
+            else if (s.counter < 99) jump = true;                        // frozen in the retain phase
+        }
+    }
+    if (finished) {
+        __syncthreads();
+        if (tid == 0) {
+            bool normal = (s_nwith_g == (unsigned long long)N);
+            s.rounds = normal ? s.counter + 1 : 1002;
+            s.frozen_exit = normal ? 0 : 1;
+            s.mode = MODE_DONE;
+            s.done = 1;
+            s.passes += 1;
+            if (s.use_list) s.list_passes += 1;
+            *p.st = s;
+        }
+        return;
+    }
+
+    // ---- 2. thresholds from the histogram (of the values the next selection sees) ----
+    // A BID pass leaves no histogram: the next pass is a HIST pass over the new state with windows
+    // placed by the sample kernel.
+    const long long need = jpw + 1;
+    if (was_bid) {
+        for (int w = tid; w < K; w += NT) {
+            p.tprev[w] = p.tkey[w];
+            p.win_base[w] = 0;
+            p.win_hbase[w] = AUC_HALF;
+            p.win_nlo[w] = AUC_HALF;
+            p.win_shift[w] = AUC_COLD_SHIFT;
+            p.tkey[w] = -1;
+            p.miss_run[w] = 0;
+        }
+        if (tid == 0) s_unresolved = 1;
+    } else if (!jump) {
+        for (int w = warp; w < K; w += NWARPS) {
+            const int base = p.win_base[w], shift = p.win_shift[w];
+            const int hbase = p.win_hbase[w], nlo = (shift == 0) ? p.win_nlo[w] : 0;
+            const unsigned long long gap = (shift == 0) ? p.gap_g[w] : 0ull;
+            unsigned int h[AUC_BPL];
+            unsigned int lsum = 0;
+#pragma unroll
+            for (int i = 0; i < AUC_BPL; ++i) { h[i] = p.hist_g[w * AUC_W + lane * AUC_BPL + i]; lsum += h[i]; }
+            // suffix sums over lanes (bins above mine)
+            unsigned int suf = lsum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                unsigned int o = __shfl_down_sync(0xffffffffu, suf, d);
+                if (lane + d < 32) suf += o;
+            }
+            const unsigned long long ab = p.above_g[w];
+            // strictly above my bins (the gap of a split window sits between bins nlo-1 and nlo)
+            unsigned long long cum_excl = ab + (suf - lsum) + ((AUC_BPL * lane + AUC_BPL - 1) < nlo ? gap : 0ull);
+            const unsigned long long total = ab + __shfl_sync(0xffffffffu, suf, 0) + gap;
+            unsigned int hsum = 0;                                    // my bins of the upper run
+#pragma unroll
+            for (int i = 0; i < AUC_BPL; ++i) hsum += (AUC_BPL * lane + i >= nlo) ? h[i] : 0u;
+#pragma unroll
+            for (int d = 16; d; d >>= 1) hsum += __shfl_xor_sync(0xffffffffu, hsum, d);
+            const unsigned long long c_hi = ab + hsum;               // everything >= hbase
+            const bool in_gap = gap > 0 && c_hi < (unsigned long long)need && c_hi + gap >= (unsigned long long)need;
+            int found_bin = -1;
+            unsigned long long g_above = 0;
+            if (!in_gap && ab < (unsigned long long)need && total >= (unsigned long long)need) {
+                unsigned long long c = cum_excl;
+#pragma unroll
+                for (int i = AUC_BPL - 1; i >= 0; --i) {
+                    if (i != AUC_BPL - 1 && AUC_BPL * lane + i == nlo - 1) c += gap;   // stepping over the gap inside my bins
+                    if (found_bin < 0 && c < (unsigned long long)need && c + h[i] >= (unsigned long long)need) {
+                        found_bin = lane * AUC_BPL + i;
+                        g_above = c;
+                    }
+                    c += h[i];
+                }
+            }
+            unsigned int who = __ballot_sync(0xffffffffu, found_bin >= 0);
+            if (who) {
+                int src = __ffs(who) - 1;
+                found_bin = __shfl_sync(0xffffffffu, found_bin, src);
+                g_above = __shfl_sync(0xffffffffu, g_above, src);
+                if (lane == 0) {
+                    p.miss_run[w] = 0;
+                    if (shift == 0) {
+                        p.tkey[w] = found_bin >= nlo ? hbase + found_bin - nlo : base + found_bin;
+                        p.take[w] = (int)(jpw - (long long)g_above);
+                    } else {   // refine inside the bin that holds the threshold
+                        int nshift = shift >= 8 ? shift - 8 : 0;
+                        const int nb2 = base + (found_bin << shift);
+                        p.win_base[w] = nb2;
+                        p.win_hbase[w] = nb2 + AUC_HALF;
+                p.win_nlo[w] = AUC_HALF;
+                        p.win_nlo[w] = AUC_HALF;
+                        p.win_shift[w] = nshift;
+                        p.tkey[w] = -1;
+                        atomicAdd(&s_unresolved, 1);
+                    }
+                }
+            } else if (lane == 0 && in_gap) {
+                // the threshold lies between the two halves of a split window: histogram just that range
+                int nb2 = base + nlo, span = hbase - nb2, nshift = 0;
+                while ((span >> nshift) > AUC_W) ++nshift;
+                p.win_base[w] = nb2;
+                p.win_hbase[w] = nb2 + AUC_HALF;
+                p.win_nlo[w] = AUC_HALF;
+                p.win_shift[w] = nshift;
+                p.tkey[w] = -1;
+                atomicAdd(&s_unresolved, 1);
+                atomicAdd(&s_miss, 1);
+            } else if (lane == 0) {
+                // the window missed the threshold: slide one window up / down, restart coarse if that
+                // keeps failing (or if the window was a refinement, which cannot miss by construction)
+                const int run = p.miss_run[w];
+                const bool is_above = ab >= (unsigned long long)need;
+                int nb = is_above ? (shift == 0 ? hbase + (AUC_W - nlo) : base + (AUC_W << shift)) : base - (AUC_W << shift);
+                if (shift != 0 || run >= 2 || nb < AUC_MIN_KEY || nb > 65536 - AUC_W) {
+                    p.win_base[w] = 0;
+                    p.win_hbase[w] = AUC_HALF;
+                    p.win_nlo[w] = AUC_HALF;
+            p.win_nlo[w] = AUC_HALF;
+                    p.win_shift[w] = AUC_COLD_SHIFT;
+                    p.miss_run[w] = 0;
+                } else {
+                    p.win_base[w] = nb;
+                    p.win_hbase[w] = nb + AUC_HALF;
+                    p.win_nlo[w] = AUC_HALF;
+                    p.miss_run[w] = run + 1;
+                }
+                p.tkey[w] = -1;
+                atomicAdd(&s_unresolved, 1);
+                if (shift == 0) atomicAdd(&s_miss, 1);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- 3. zero the merged histograms for the next pass ----
+    for (int i = tid; i < K * AUC_W + 2 * K + 2; i += NT) p.hist_g[i] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        s.passes += 1;
+        if (!was_bid) s.cold_passes += 1;
+        s.window_misses += s_miss;
+        if (was_bid) s.counter += 1;                                     // :125
+        s.ff_pending = 0;
+        s.need_sample = was_bid ? 1 : 0;
+        if (was_bid && s.use_list) s.list_passes += 1;
+        if (!was_bid) {      // lists of the pass that just ran: complete unless a segment overflowed
+            s.use_list = (*p.list_ok != 0 && !s.force_scan) ? 1 : 0;
+            *p.list_ok = 1;
+        }
+        if (jump) {
+            // frozen at counter c (already incremented to c+1): rounds c+1..99 add eps each
+            s.ff_pending = 100 - s.counter;
+            s.counter = 100;
+            s.mode = MODE_HIST;
+        } else {
+            s.mode = (s_unresolved == 0) ? MODE_BID : MODE_HIST;
+        }
+        *p.st = s;
+    }
+}
+
+
+__global__ void __launch_bounds__(1024, 1)
+auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw, int expect) {
+    auction_resolve_body(p, N, K, jpw, expect);
+}
+
+// Single-GPU runs fold the resolve step into the pass kernel itself: the CTA that finishes last (a ticket
+// counter) sees every other CTA's histogram merges / bid counts and runs the resolve body, which saves a
+// kernel boundary per pass.  Sharded runs cannot (the merged histograms must be summed over ranks first).
+__device__ __forceinline__ bool auction_last_cta(unsigned int* ticket) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        s_last = (t == gridDim.x - 1) ? 1 : 0;
+        if (s_last) *ticket = 0;
+    }
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last != 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -318,7 +527,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 // survivors, kept as register bitmasks, become bids; column maximum; cost / owner update.
 template <int J>
 __global__ void __launch_bounds__(AUC_THREADS, (J == 128 ? 2 : 1))
-auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int K, long long jpw, AuctionPtrs p) {
+auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int K, long long jpw, AuctionPtrs p,
+                    long long n_global, int fused) {
     constexpr int CPL = J / 32;           // columns per lane
     constexpr int NH2 = CPL / 2;          // half2 words per lane
     constexpr int MAXR = 256 / AUC_NW * (J == 128 ? 1 : 2) / 2;   // rows per warp: 8 (K<=128) / 16 (K<=256)
@@ -587,6 +797,7 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
         if (s_nwith) atomicAdd(p.n_with, s_nwith);
         if (s_nviol) atomicAdd(p.n_viol, s_nviol);
     }
+    if (fused && auction_last_cta(p.ticket)) auction_resolve_body(p, n_global, K, n_global / K, MODE_BID);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -610,7 +821,8 @@ __device__ __forceinline__ uint4 ldg_stream128(const void* ptr) {
 }
 
 __global__ void __launch_bounds__(AUC_THREADS, 2)
-auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int K, int J, int spc, AuctionPtrs p) {
+auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int K, int J, int spc, AuctionPtrs p,
+                    long long n_global, int fused) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const AuctionState st = *p.st;
     if (st.mode != MODE_HIST) return;
@@ -946,6 +1158,7 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
         if (sm.above[i]) atomicAdd(&p.above_g[i], sm.above[i]);
         if (sm.gap[i]) atomicAdd(&p.gap_g[i], sm.gap[i]);
     }
+    if (fused && auction_last_cta(p.ticket)) auction_resolve_body(p, n_global, K, n_global / K, MODE_HIST);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -957,7 +1170,7 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
 // one segment per worker that straddles the worker's quota.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(AUC_THREADS, 2)
-auction_bidlist_kernel(long long N, int K, int J, int spc, AuctionPtrs p) {
+auction_bidlist_kernel(long long N, int K, int J, int spc, AuctionPtrs p, long long n_global, int fused) {
     const AuctionState st = *p.st;
     if (st.mode != MODE_BID || !st.use_list) return;
     constexpr int NCH = AUC_SEG_CAP / 32;
@@ -1091,6 +1304,7 @@ auction_bidlist_kernel(long long N, int K, int J, int spc, AuctionPtrs p) {
         if (s_nwith) atomicAdd(p.n_with, s_nwith);
         if (s_nviol) atomicAdd(p.n_viol, s_nviol);
     }
+    if (fused && auction_last_cta(p.ticket)) auction_resolve_body(p, n_global, K, n_global / K, MODE_BID);
 }
 
 static inline size_t auction_hist_smem(int K) {
@@ -1290,187 +1504,6 @@ auction_sample_kernel(const __half* __restrict__ S, long long ld, long long N, i
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// resolve: merged histograms -> thresholds / next windows / state machine.  One CTA.
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024, 1)
-auction_resolve_kernel(AuctionPtrs p, long long N, int K, long long jpw) {
-    __shared__ int s_unresolved, s_miss;
-    __shared__ AuctionState s;
-    __shared__ unsigned long long s_nwith_g, s_nviol_g;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { s = *p.st; s_unresolved = 0; s_miss = 0; s_nwith_g = *p.n_with; s_nviol_g = *p.n_viol; }
-    __syncthreads();
-    if (s.mode == MODE_DONE) return;
-    const bool was_bid = (s.mode == MODE_BID);
-
-    // ---- 1. outcome of the bidding round that just ran ----
-    bool finished = false, jump = false;
-    if (was_bid) {
-        if (s_nwith_g == (unsigned long long)N) {
-            finished = true;                                  // :113-114
-        } else if (s_nviol_g == 0 && s.counter >= 1) {
-            if (s.counter >= 100 && s.counter <= 1000) finished = true;   // frozen: ends at counter 1001
-            else if (s.counter < 99) jump = true;                        // frozen in the retain phase
-        }
-    }
-    if (finished) {
-        __syncthreads();
-        if (tid == 0) {
-            bool normal = (s_nwith_g == (unsigned long long)N);
-            s.rounds = normal ? s.counter + 1 : 1002;
-            s.frozen_exit = normal ? 0 : 1;
-            s.mode = MODE_DONE;
-            s.done = 1;
-            s.passes += 1;
-            if (s.use_list) s.list_passes += 1;
-            *p.st = s;
-        }
-        return;
-    }
-
-    // ---- 2. thresholds from the histogram (of the values the next selection sees) ----
-    // A BID pass leaves no histogram: the next pass is a HIST pass over the new state with windows
-    // placed by the sample kernel.
-    const long long need = jpw + 1;
-    if (was_bid) {
-        for (int w = tid; w < K; w += 1024) {
-            p.tprev[w] = p.tkey[w];
-            p.win_base[w] = 0;
-            p.win_hbase[w] = AUC_HALF;
-            p.win_nlo[w] = AUC_HALF;
-            p.win_shift[w] = AUC_COLD_SHIFT;
-            p.tkey[w] = -1;
-            p.miss_run[w] = 0;
-        }
-        if (tid == 0) s_unresolved = 1;
-    } else if (!jump) {
-        for (int w = warp; w < K; w += 32) {
-            const int base = p.win_base[w], shift = p.win_shift[w];
-            const int hbase = p.win_hbase[w], nlo = (shift == 0) ? p.win_nlo[w] : 0;
-            const unsigned long long gap = (shift == 0) ? p.gap_g[w] : 0ull;
-            unsigned int h[AUC_BPL];
-            unsigned int lsum = 0;
-#pragma unroll
-            for (int i = 0; i < AUC_BPL; ++i) { h[i] = p.hist_g[w * AUC_W + lane * AUC_BPL + i]; lsum += h[i]; }
-            // suffix sums over lanes (bins above mine)
-            unsigned int suf = lsum;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                unsigned int o = __shfl_down_sync(0xffffffffu, suf, d);
-                if (lane + d < 32) suf += o;
-            }
-            const unsigned long long ab = p.above_g[w];
-            // strictly above my bins (the gap of a split window sits between bins nlo-1 and nlo)
-            unsigned long long cum_excl = ab + (suf - lsum) + ((AUC_BPL * lane + AUC_BPL - 1) < nlo ? gap : 0ull);
-            const unsigned long long total = ab + __shfl_sync(0xffffffffu, suf, 0) + gap;
-            unsigned int hsum = 0;                                    // my bins of the upper run
-#pragma unroll
-            for (int i = 0; i < AUC_BPL; ++i) hsum += (AUC_BPL * lane + i >= nlo) ? h[i] : 0u;
-#pragma unroll
-            for (int d = 16; d; d >>= 1) hsum += __shfl_xor_sync(0xffffffffu, hsum, d);
-            const unsigned long long c_hi = ab + hsum;               // everything >= hbase
-            const bool in_gap = gap > 0 && c_hi < (unsigned long long)need && c_hi + gap >= (unsigned long long)need;
-            int found_bin = -1;
-            unsigned long long g_above = 0;
-            if (!in_gap && ab < (unsigned long long)need && total >= (unsigned long long)need) {
-                unsigned long long c = cum_excl;
-#pragma unroll
-                for (int i = AUC_BPL - 1; i >= 0; --i) {
-                    if (i != AUC_BPL - 1 && AUC_BPL * lane + i == nlo - 1) c += gap;   // stepping over the gap inside my bins
-                    if (found_bin < 0 && c < (unsigned long long)need && c + h[i] >= (unsigned long long)need) {
-                        found_bin = lane * AUC_BPL + i;
-                        g_above = c;
-                    }
-                    c += h[i];
-                }
-            }
-            unsigned int who = __ballot_sync(0xffffffffu, found_bin >= 0);
-            if (who) {
-                int src = __ffs(who) - 1;
-                found_bin = __shfl_sync(0xffffffffu, found_bin, src);
-                g_above = __shfl_sync(0xffffffffu, g_above, src);
-                if (lane == 0) {
-                    p.miss_run[w] = 0;
-                    if (shift == 0) {
-                        p.tkey[w] = found_bin >= nlo ? hbase + found_bin - nlo : base + found_bin;
-                        p.take[w] = (int)(jpw - (long long)g_above);
-                    } else {   // refine inside the bin that holds the threshold
-                        int nshift = shift >= 8 ? shift - 8 : 0;
-                        const int nb2 = base + (found_bin << shift);
-                        p.win_base[w] = nb2;
-                        p.win_hbase[w] = nb2 + AUC_HALF;
-                p.win_nlo[w] = AUC_HALF;
-                        p.win_nlo[w] = AUC_HALF;
-                        p.win_shift[w] = nshift;
-                        p.tkey[w] = -1;
-                        atomicAdd(&s_unresolved, 1);
-                    }
-                }
-            } else if (lane == 0 && in_gap) {
-                // the threshold lies between the two halves of a split window: histogram just that range
-                int nb2 = base + nlo, span = hbase - nb2, nshift = 0;
-                while ((span >> nshift) > AUC_W) ++nshift;
-                p.win_base[w] = nb2;
-                p.win_hbase[w] = nb2 + AUC_HALF;
-                p.win_nlo[w] = AUC_HALF;
-                p.win_shift[w] = nshift;
-                p.tkey[w] = -1;
-                atomicAdd(&s_unresolved, 1);
-                atomicAdd(&s_miss, 1);
-            } else if (lane == 0) {
-                // the window missed the threshold: slide one window up / down, restart coarse if that
-                // keeps failing (or if the window was a refinement, which cannot miss by construction)
-                const int run = p.miss_run[w];
-                const bool is_above = ab >= (unsigned long long)need;
-                int nb = is_above ? (shift == 0 ? hbase + (AUC_W - nlo) : base + (AUC_W << shift)) : base - (AUC_W << shift);
-                if (shift != 0 || run >= 2 || nb < AUC_MIN_KEY || nb > 65536 - AUC_W) {
-                    p.win_base[w] = 0;
-                    p.win_hbase[w] = AUC_HALF;
-                    p.win_nlo[w] = AUC_HALF;
-            p.win_nlo[w] = AUC_HALF;
-                    p.win_shift[w] = AUC_COLD_SHIFT;
-                    p.miss_run[w] = 0;
-                } else {
-                    p.win_base[w] = nb;
-                    p.win_hbase[w] = nb + AUC_HALF;
-                    p.win_nlo[w] = AUC_HALF;
-                    p.miss_run[w] = run + 1;
-                }
-                p.tkey[w] = -1;
-                atomicAdd(&s_unresolved, 1);
-                if (shift == 0) atomicAdd(&s_miss, 1);
-            }
-        }
-    }
-    __syncthreads();
-    // ---- 3. zero the merged histograms for the next pass ----
-    for (int i = tid; i < K * AUC_W + 2 * K + 2; i += 1024) p.hist_g[i] = 0;
-    __syncthreads();
-    if (tid == 0) {
-        s.passes += 1;
-        if (!was_bid) s.cold_passes += 1;
-        s.window_misses += s_miss;
-        if (was_bid) s.counter += 1;                                     // :125
-        s.ff_pending = 0;
-        s.need_sample = was_bid ? 1 : 0;
-        if (was_bid && s.use_list) s.list_passes += 1;
-        if (!was_bid) {      // lists of the pass that just ran: complete unless a segment overflowed
-            s.use_list = (*p.list_ok != 0 && !s.force_scan) ? 1 : 0;
-            *p.list_ok = 1;
-        }
-        if (jump) {
-            // frozen at counter c (already incremented to c+1): rounds c+1..99 add eps each
-            s.ff_pending = 100 - s.counter;
-            s.counter = 100;
-            s.mode = MODE_HIST;
-        } else {
-            s.mode = (s_unresolved == 0) ? MODE_BID : MODE_HIST;
-        }
-        *p.st = s;
-    }
-}
-
 // After a resolve that leaves every worker resolved: per-CTA exclusive prefix of the number of
 // values equal to the threshold (bin tkey-base of the per-CTA dumps), and the window predicted for
 // the values after this round's cost update.  Grid = K CTAs.
@@ -1535,6 +1568,39 @@ static int auction_prepare(int64_t n, int64_t ld, int32_t k, void* workspace, si
     if (a->G > AUC_MAX_CTAS) return fail(RQK_ERR_UNSUPPORTED, "%s: n=%lld jobs per GPU exceed the 66 M limit of this build", who, n);
     a->J = auction_tile_cols(k);
     a->smem = auction_pass_smem(k, a->J);
+    return 0;
+}
+
+// Enqueues the kernels of one pass; the device-side state machine makes those whose turn it is not return at
+// once.  which: bit 0 window sampling, bit 1 HIST, bit 2 BID (list replay + S scan), bit 3 tie prefix (between
+// HIST and BID; only meaningful with fused resolve).  fused: the last CTA of a pass kernel runs the resolve step.
+static int auction_launch(const AuctionArgs& a, const void* scores_t, int64_t ld, int64_t n, int32_t k, int64_t n_global,
+                          int which, int fused, cudaStream_t stream) {
+    auto kern = (a.J == 128) ? auction_pass_kernel<128> : auction_pass_kernel<64>;
+    static size_t smem_set[2] = {0, 0};
+    size_t& cur = smem_set[a.J == 128 ? 0 : 1];
+    if (a.smem > cur) {
+        RQK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem));
+        cur = a.smem;
+    }
+    const int spc = auction_spc(n, k);
+    if (which & 1)
+        auction_sample_kernel<<<k, 1024, 0, stream>>>((const __half*)scores_t, ld, n, k, n_global / k, a.p, nullptr, 0, nullptr, 0);
+    if (which & 2) {
+        static size_t hs_set = 0;
+        const size_t hs = auction_hist_smem(k);
+        if (hs > hs_set) {
+            RQK_CUDA_OK(cudaFuncSetAttribute(auction_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
+            hs_set = hs;
+        }
+        auction_hist_kernel<<<a.G, AUC_THREADS, hs, stream>>>((const __half*)scores_t, ld, n, k, a.J, spc, a.p, n_global, fused);
+    }
+    if (which & 8) auction_tieprefix_kernel<<<k, AUC_MAX_CTAS, 0, stream>>>(a.p, k, a.G);
+    if (which & 4) {
+        auction_bidlist_kernel<<<a.G, AUC_THREADS, 0, stream>>>(n, k, a.J, spc, a.p, n_global, fused);
+        kern<<<a.G, AUC_THREADS, a.smem, stream>>>((const __half*)scores_t, ld, n, k, n_global / k, a.p, n_global, fused);
+    }
+    RQK_LAUNCH_OK();
     return 0;
 }
 }  // namespace rqk
@@ -1606,33 +1672,9 @@ int rqk_auction_pass(const void* scores_t, int64_t ld, int64_t n, int32_t k, int
     if (rc) return rc;
     if (!scores_t) return fail(RQK_ERR_ARG, "rqk_auction_pass: null scores%s");
     if (n_global < k) return fail(RQK_ERR_ARG, "rqk_auction_pass: n_global=%s%lld < k=%lld (argmin path, reference :24-26)", "", n_global, k);
-    auto kern = (a.J == 128) ? auction_pass_kernel<128> : auction_pass_kernel<64>;
-    static size_t smem_set[2] = {0, 0};
-    size_t& cur = smem_set[a.J == 128 ? 0 : 1];
-    if (a.smem > cur) {
-        RQK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem));
-        cur = a.smem;
-    }
     if (which == 0) which = 7;
-    if (n_global == n && (which & 1))   // sharded jobs: rqk_auction_sample_collect / _window (ranks must agree on the windows)
-        auction_sample_kernel<<<k, 1024, 0, (cudaStream_t)stream_>>>((const __half*)scores_t, ld, n, k, n_global / k, a.p,
-                                                                      nullptr, 0, nullptr, 0);
-    if (which & 2) {
-        static size_t hs_set = 0;
-        const size_t hs = auction_hist_smem(k);
-        if (hs > hs_set) {
-            RQK_CUDA_OK(cudaFuncSetAttribute(auction_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
-            hs_set = hs;
-        }
-        auction_hist_kernel<<<a.G, AUC_THREADS, hs, (cudaStream_t)stream_>>>((const __half*)scores_t, ld, n, k, a.J,
-                                                                              auction_spc(n, k), a.p);
-    }
-    if (which & 4) {
-        auction_bidlist_kernel<<<a.G, AUC_THREADS, 0, (cudaStream_t)stream_>>>(n, k, a.J, auction_spc(n, k), a.p);
-        kern<<<a.G, AUC_THREADS, a.smem, (cudaStream_t)stream_>>>((const __half*)scores_t, ld, n, k, n_global / k, a.p);
-    }
-    RQK_LAUNCH_OK();
-    return 0;
+    if (n_global != n) which &= ~1;   // sharded jobs: rqk_auction_sample_collect / _window (ranks must agree on the windows)
+    return auction_launch(a, scores_t, ld, n, k, n_global, which, 0, (cudaStream_t)stream_);
 }
 
 // Sharded window sampling, step 1: keys of `count` (<= 4096) evenly strided local jobs per worker -> out [k][count]
@@ -1673,7 +1715,7 @@ int rqk_auction_resolve(int64_t n, int64_t ld, int32_t k, int64_t n_global, void
     int rc = auction_prepare(n, ld, k, workspace, workspace_bytes, &a, "rqk_auction_resolve");
     if (rc) return rc;
     cudaStream_t stream = (cudaStream_t)stream_;
-    auction_resolve_kernel<<<1, 1024, 0, stream>>>(a.p, n_global, k, n_global / k);
+    auction_resolve_kernel<<<1, 1024, 0, stream>>>(a.p, n_global, k, n_global / k, -1);
     auction_tieprefix_kernel<<<k, AUC_MAX_CTAS, 0, stream>>>(a.p, k, a.G);
     RQK_LAUNCH_OK();
     return 0;
@@ -1741,14 +1783,41 @@ int rqk_auction(const void* scores_t, int64_t ld, int64_t n, int32_t k, const vo
     if (rc) return rc;
     rqk_auction_info st;
     memset(&st, 0, sizeof(st));
-    const int batch = 6;
+    AuctionArgs a;
+    if ((rc = auction_prepare(n, ld, k, workspace, workspace_bytes, &a, "rqk_auction"))) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    // A round = sample, HIST (+ resolve in its last CTA), tie prefix, BID (+ resolve).  The host never waits for
+    // the round it just enqueued: the state is copied to a pinned two-slot mailbox after every batch and the
+    // host looks at the copy of the batch BEFORE the one it enqueued last, so the GPU always has work queued
+    // (passes enqueued after the auction finished return at once).  The mailbox (pinned host memory, 2 x 128 B
+    // per host thread) is the one allocation this library makes.
+    static thread_local AuctionState* mailbox = nullptr;
+    static thread_local cudaEvent_t ev[2];
+    if (!mailbox) {
+        RQK_CUDA_OK(cudaHostAlloc((void**)&mailbox, 2 * sizeof(AuctionState), cudaHostAllocDefault));
+        RQK_CUDA_OK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+        RQK_CUDA_OK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    }
+    const int rounds_per_batch = 2;
+    const AuctionState* fin = nullptr;
     // hard stop: the reference itself cannot exceed 1002 rounds; each round is a handful of passes at most
-    for (int it = 0; it < 8000 && !st.done; it += batch) {
-        for (int q = 0; q < batch; ++q) {
-            if ((rc = rqk_auction_pass(scores_t, ld, n, k, n, 0, workspace, workspace_bytes, stream_))) return rc;
-            if ((rc = rqk_auction_resolve(n, ld, k, n, workspace, workspace_bytes, stream_))) return rc;
+    for (int b = 0; b < 4000 && !fin; ++b) {
+        for (int q = 0; q < rounds_per_batch; ++q)
+            if ((rc = auction_launch(a, scores_t, ld, n, k, n, 1 | 2 | 4 | 8, 1, stream))) return rc;
+        RQK_CUDA_OK(cudaMemcpyAsync(&mailbox[b & 1], a.p.st, sizeof(AuctionState), cudaMemcpyDeviceToHost, stream));
+        RQK_CUDA_OK(cudaEventRecord(ev[b & 1], stream));
+        if (b >= 1) {
+            RQK_CUDA_OK(cudaEventSynchronize(ev[(b - 1) & 1]));
+            if (mailbox[(b - 1) & 1].done) fin = &mailbox[(b - 1) & 1];
         }
-        if ((rc = rqk_auction_poll(n, ld, k, workspace, workspace_bytes, &st, stream_))) return rc;
+    }
+    // drain the trailing (no-op) batch so that no mailbox copy is in flight when this thread's next auction starts
+    RQK_CUDA_OK(cudaStreamSynchronize(stream));
+    if (fin) {
+        st.done = fin->done; st.rounds = fin->rounds; st.passes = fin->passes; st.cold_passes = fin->cold_passes;
+        st.window_misses = fin->window_misses; st.frozen_exit = fin->frozen_exit; st.counter = fin->counter;
+        st.eps_bits = (uint16_t)fin->eps_bits;
+        st.list_passes = (uint16_t)(fin->list_passes > 65535 ? 65535 : fin->list_passes);
     }
     if (!st.done) return fail(RQK_ERR_INTERNAL, "rqk_auction: did not terminate%s");
     if ((rc = rqk_auction_finalize(n, ld, k, workspace, workspace_bytes, assign, stream_))) return rc;
