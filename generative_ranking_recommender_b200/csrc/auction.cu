@@ -89,6 +89,7 @@ struct AuctionPtrs {
     AuctionState* st;
     __half* cost;
     short* owner;
+    __half* sown;             // [ld] S[owner[j]][j]: the owner's own value of job j (valid where owner >= 0)
     // "reduce block": contiguous int32 [K*W + 2K + 2]; the only per-pass data ranks must sum when the
     // jobs are sharded over GPUs (hist_g | above_g | gap_g | n_with | n_viol)
     unsigned int* hist_g;     // [K][W]
@@ -143,6 +144,7 @@ static inline size_t auction_ws_layout(long long N, long long ld, int K, Auction
     size_t o_st = take_(sizeof(AuctionState));
     size_t o_cost = take_((size_t)ld * 2);
     size_t o_own = take_((size_t)ld * 2);
+    size_t o_sown = take_((size_t)ld * 2);
     size_t o_hist = take_(((size_t)K * AUC_W + 2 * K + 2) * 4);
     size_t o_tt = take_((size_t)K * 4);
     size_t o_wb = take_((size_t)K * 4);
@@ -166,6 +168,7 @@ static inline size_t auction_ws_layout(long long N, long long ld, int K, Auction
         p->st = (AuctionState*)(base + o_st);
         p->cost = (__half*)(base + o_cost);
         p->owner = (short*)(base + o_own);
+        p->sown = (__half*)(base + o_sown);
         p->hist_g = (unsigned int*)(base + o_hist);
         p->above_g = p->hist_g + (size_t)K * AUC_W;
         p->gap_g = p->above_g + K;
@@ -774,6 +777,7 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
                         const short wnr = (short)(0xffffu - (pk & 0xffffu));
                         p.cost[col] = __hadd(__ushort_as_half(sm.colcost[tid]), bits2h(pk >> 16));
                         p.owner[col] = wnr;
+                        p.sown[col] = tile[(size_t)wnr * J + tid];
                     } else {
                         p.owner[col] = -1;
                         if (old_owner >= 0) vv = true;                       // an owned job lost its bidder
@@ -876,12 +880,17 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
         unsigned int* seg_lists = p.seg_list + (size_t)seg * K * AUC_SEG_CAP;
         if (tid < K) seg_cnt_s[tid] = 0;
         // ---- stage costs / owners of the sub-range (retain fast-forward applied here, once) ----
-        for (int i = tid; i < HS_SUB; i += AUC_THREADS) {
+        unsigned short so_r[HS_SUB / AUC_THREADS];   // the owner's own value of my jobs (kept by the BID kernels)
+#pragma unroll
+        for (int it = 0; it < HS_SUB / AUC_THREADS; ++it) {
+            const int i = tid + it * AUC_THREADS;
             unsigned short c = 0;
             short o = -1;
+            so_r[it] = 0;
             if (i < sublen) {
                 __half ch = p.cost[sub + i];
                 o = p.owner[sub + i];
+                so_r[it] = __half_as_ushort(p.sown[sub + i]);
                 if (ff > 0 && o >= 0) {
                     for (int r = 0; r < ff; ++r) ch = __hadd(ch, eps);
                     p.cost[sub + i] = ch;
@@ -893,10 +902,12 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
         }
         __syncthreads();
         // ---- owner entries (value = S): one per job ----
-        for (int i = tid; i < sublen; i += AUC_THREADS) {
-            const int o = own_s[i];
+#pragma unroll
+        for (int it = 0; it < HS_SUB / AUC_THREADS; ++it) {
+            const int i = tid + it * AUC_THREADS;
+            const int o = (i < sublen) ? own_s[i] : -1;
             if (o >= 0 && sm.r_base[o] > 0) {
-                const int key = (int)h2key(h2bits(S[(size_t)o * ld + sub + i]));
+                const int key = (int)h2key((unsigned)so_r[it]);
                 window_count(sm, o, key);
                 if (key >= sm.r_base[o]) {
                     const unsigned int slot = atomicAdd(&seg_cnt_s[o], 1u);
@@ -1170,7 +1181,8 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
 // one segment per worker that straddles the worker's quota.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(AUC_THREADS, 2)
-auction_bidlist_kernel(long long N, int K, int J, int spc, AuctionPtrs p, long long n_global, int fused) {
+auction_bidlist_kernel(const __half* __restrict__ S, long long ld, long long N, int K, int J, int spc, AuctionPtrs p,
+                       long long n_global, int fused) {
     const AuctionState st = *p.st;
     if (st.mode != MODE_BID || !st.use_list) return;
     constexpr int NCH = AUC_SEG_CAP / 32;
@@ -1217,18 +1229,43 @@ auction_bidlist_kernel(long long N, int K, int J, int spc, AuctionPtrs p, long l
         }
         __syncthreads();
         // ---- segments: a warp per worker ----
-        for (int w = warp; w < K; w += AUC_NW) {
-            unsigned int E = p.seg_cnt[(size_t)seg * K + w];
-            if (E > AUC_SEG_CAP) E = AUC_SEG_CAP;            // cannot happen when use_list is set
+        // lengths of this warp's segments with one load; the first 64 entries of the next segment are fetched
+        // while the current one is replayed (a segment holds ~60)
+        const int nrows = (K - warp + AUC_NW - 1) / AUC_NW;
+        unsigned int E_l = (lane < nrows) ? __ldcg(p.seg_cnt + (size_t)seg * K + warp + AUC_NW * lane) : 0u;
+        if (E_l > AUC_SEG_CAP) E_l = AUC_SEG_CAP;            // cannot happen when use_list is set
+        unsigned int pre0 = 0, pre1 = 0;
+        {
+            const unsigned int E0 = __shfl_sync(0xffffffffu, E_l, 0);
+            const unsigned int* L0 = p.seg_list + ((size_t)seg * K + warp) * AUC_SEG_CAP;
+            if ((unsigned)lane < E0) pre0 = __ldcg(L0 + lane);
+            if ((unsigned)lane + 32 < E0) pre1 = __ldcg(L0 + 32 + lane);
+        }
+        for (int r = 0; r < nrows; ++r) {
+            const int w = warp + AUC_NW * r;
+            const unsigned int E = __shfl_sync(0xffffffffu, E_l, r);
             const unsigned int* L = p.seg_list + ((size_t)seg * K + w) * AUC_SEG_CAP;
             const int tk = r_tk[w];
             const __half T = bits2h(key2h((unsigned)tk));
             unsigned int ent[NCH], tmask[NCH];
             unsigned int n_ties = 0;
+            ent[0] = pre0;
+            ent[1] = pre1;
+#pragma unroll
+            for (int c = 2; c < NCH; ++c) {
+                const unsigned int idx = c * 32 + lane;
+                ent[c] = (idx < E) ? __ldcg(L + idx) : 0u;   // key 0 is below every threshold: never a bidder
+            }
+            pre0 = 0; pre1 = 0;
+            if (r + 1 < nrows) {
+                const unsigned int En = __shfl_sync(0xffffffffu, E_l, r + 1);
+                const unsigned int* Ln = L + (size_t)AUC_NW * AUC_SEG_CAP;
+                if ((unsigned)lane < En) pre0 = __ldcg(Ln + lane);
+                if ((unsigned)lane + 32 < En) pre1 = __ldcg(Ln + 32 + lane);
+            }
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 const unsigned int idx = c * 32 + lane;
-                ent[c] = (idx < E) ? __ldcg(L + idx) : 0u;   // key 0 is below every threshold: never a bidder
                 tmask[c] = __ballot_sync(0xffffffffu, idx < E && (int)(ent[c] & 0xffffu) == tk);
                 n_ties += __popc(tmask[c]);
             }
@@ -1286,7 +1323,10 @@ auction_bidlist_kernel(long long N, int K, int J, int spc, AuctionPtrs p, long l
                     has = true;
                     const short wnr = (short)(0xffffu - (pk & 0xffffu));
                     p.cost[sub + i] = __hadd(__ushort_as_half(cost_s[i]), bits2h(pk >> 16));
-                    if (wnr != old_owner) p.owner[sub + i] = wnr;
+                    if (wnr != old_owner) {
+                        p.owner[sub + i] = wnr;
+                        p.sown[sub + i] = S[(size_t)wnr * ld + sub + i];
+                    }
                 } else {
                     if (old_owner >= 0) { p.owner[sub + i] = -1; vv = true; }    // an owned job lost its bidder
                 }
@@ -1597,7 +1637,7 @@ static int auction_launch(const AuctionArgs& a, const void* scores_t, int64_t ld
     }
     if (which & 8) auction_tieprefix_kernel<<<k, AUC_MAX_CTAS, 0, stream>>>(a.p, k, a.G);
     if (which & 4) {
-        auction_bidlist_kernel<<<a.G, AUC_THREADS, 0, stream>>>(n, k, a.J, spc, a.p, n_global, fused);
+        auction_bidlist_kernel<<<a.G, AUC_THREADS, 0, stream>>>((const __half*)scores_t, ld, n, k, a.J, spc, a.p, n_global, fused);
         kern<<<a.G, AUC_THREADS, a.smem, stream>>>((const __half*)scores_t, ld, n, k, n_global / k, a.p, n_global, fused);
     }
     RQK_LAUNCH_OK();
