@@ -82,7 +82,8 @@ struct AuctionState {
     int use_list;       // the coming BID pass reads the survivor lists of the HIST pass instead of S
     int force_scan;     // debugging / tests: never use the lists
     int list_passes;    // BID passes served from the lists
-    int pad_[12];
+    int sink[4];        // statistics: worker-rounds whose threshold sank by < 64, < 128, < 250, >= 250 keys
+    int pad_[8];
 };
 
 struct AuctionPtrs {
@@ -339,6 +340,12 @@ __device__ __noinline__ void auction_resolve_body(AuctionPtrs p, long long N, in
                 if (lane == 0) {
                     p.miss_run[w] = 0;
                     if (shift == 0) {
+                        const int tk_new = found_bin >= nlo ? hbase + found_bin - nlo : base + found_bin;
+                        const int tp = p.tprev[w];
+                        if (tp >= 0) {
+                            const int d = tp - tk_new;
+                            atomicAdd(&s.sink[d < 64 ? 0 : d < 128 ? 1 : d < 250 ? 2 : 3], 1);
+                        }
                         p.tkey[w] = found_bin >= nlo ? hbase + found_bin - nlo : base + found_bin;
                         p.take[w] = (int)(jpw - (long long)g_above);
                     } else {   // refine inside the bin that holds the threshold
@@ -1216,9 +1223,22 @@ auction_bidlist_kernel(const __half* __restrict__ S, long long ld, long long N, 
     for (long long sub = c_begin; sub < c_end; sub += AUC_SUB, ++seg) {
         const int sublen = (int)((c_end - sub) < AUC_SUB ? (c_end - sub) : AUC_SUB);
         // ---- stage cost / owner; bids that do not depend on S (retain hack :87, fallback :89) ----
-        for (int i = tid; i < sublen; i += AUC_THREADS) {
-            const unsigned short c = __half_as_ushort(p.cost[sub + i]);
-            const short o = p.owner[sub + i];
+        constexpr int PER = AUC_SUB / AUC_THREADS;
+        unsigned short c_r[PER];
+        short o_r[PER];
+#pragma unroll
+        for (int it = 0; it < PER; ++it) {                                       // all loads first: one latency, not PER
+            const int i = tid + it * AUC_THREADS;
+            c_r[it] = 0;
+            o_r[it] = -1;
+            if (i < sublen) { c_r[it] = __half_as_ushort(p.cost[sub + i]); o_r[it] = p.owner[sub + i]; }
+        }
+#pragma unroll
+        for (int it = 0; it < PER; ++it) {
+            const int i = tid + it * AUC_THREADS;
+            if (i >= sublen) break;
+            const unsigned short c = c_r[it];
+            const short o = o_r[it];
             cost_s[i] = c;
             own_s[i] = o;
             unsigned int init = 0;
@@ -1312,11 +1332,24 @@ auction_bidlist_kernel(const __half* __restrict__ S, long long ld, long long N, 
         }
         __syncthreads();
         // ---- highest bid per job, cost / owner update (:104, :118-123) ----
-        for (int i0 = 0; i0 < sublen; i0 += AUC_THREADS) {
-            const int i = i0 + tid;
+        unsigned short sv_r[PER];
+        unsigned int pk_r[PER];
+#pragma unroll
+        for (int it = 0; it < PER; ++it) {                                       // new owners' own values: loads first
+            const int i = tid + it * AUC_THREADS;
+            pk_r[it] = (i < sublen) ? colmax[i] : 0u;
+            sv_r[it] = 0;
+            if (pk_r[it]) {
+                const short wnr = (short)(0xffffu - (pk_r[it] & 0xffffu));
+                if (wnr != own_s[i]) sv_r[it] = __half_as_ushort(S[(size_t)wnr * ld + sub + i]);
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < PER; ++it) {
+            const int i = tid + it * AUC_THREADS;
             bool has = false, vv = false;
             if (i < sublen) {
-                const unsigned int pk = colmax[i];
+                const unsigned int pk = pk_r[it];
                 const short old_owner = own_s[i];
                 vv = colviol[i] != 0;
                 if (pk) {
@@ -1325,7 +1358,7 @@ auction_bidlist_kernel(const __half* __restrict__ S, long long ld, long long N, 
                     p.cost[sub + i] = __hadd(__ushort_as_half(cost_s[i]), bits2h(pk >> 16));
                     if (wnr != old_owner) {
                         p.owner[sub + i] = wnr;
-                        p.sown[sub + i] = S[(size_t)wnr * ld + sub + i];
+                        p.sown[sub + i] = __ushort_as_half(sv_r[it]);
                     }
                 } else {
                     if (old_owner >= 0) { p.owner[sub + i] = -1; vv = true; }    // an owned job lost its bidder
@@ -1363,6 +1396,38 @@ static inline size_t auction_pass_smem(int K, int J) {
 // Grid = K CTAs x 1024 threads, 4096 samples.
 // ------------------------------------------------------------------------------------------
 constexpr int AUC_SAMPLE = 4096;
+// Warp-parallel descending scan of a 256-bin histogram: the highest bin b with base + sum(hist[b..255]) >= need,
+// and base + sum(hist[b+1..255]).  Called by one full warp; results written by lane 0 (and returned to all lanes).
+__device__ __forceinline__ void sample_select_bin(const unsigned int* hist, int base, int need, int* out_bin, int* out_above) {
+    const int lane = threadIdx.x & 31;
+    int h[8], lsum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { h[i] = (int)hist[lane * 8 + i]; lsum += h[i]; }
+    int suf = lsum;                                   // inclusive suffix sum over lanes
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_down_sync(0xffffffffu, suf, d);
+        if (lane + d < 32) suf += o;
+    }
+    int c = base + suf - lsum, bin = -1, above = 0;
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+        if (bin < 0 && c + h[i] >= need) { bin = lane * 8 + i; above = c; }
+        c += h[i];
+    }
+    const unsigned int who = __ballot_sync(0xffffffffu, bin >= 0);
+    int rb = 0, ra = base + __shfl_sync(0xffffffffu, suf, 0);   // not found: bin 0, everything above (as the serial scan)
+    if (who) {
+        const int src = 31 - __clz(who);
+        rb = __shfl_sync(0xffffffffu, bin, src);
+        ra = __shfl_sync(0xffffffffu, above, src);
+    }
+    if (lane == 0) { *out_bin = rb; *out_above = ra; }
+    *out_bin = rb;
+    *out_above = ra;
+}
+
+
 
 // Sharded jobs: every rank samples AUC_SAMPLE / world jobs of its shard (collect_out != null: write the keys
 // and return), the host all-gathers them, and every rank places identical windows from the union
@@ -1379,25 +1444,43 @@ auction_sample_kernel(const __half* __restrict__ S, long long ld, long long N, i
     if (collect_out) ns = collect_n < ns ? collect_n : ns;
     if (ext_keys) ns = ext_n;
     const __half eps = bits2h(st.eps_bits);
-    for (int i = tid; i < AUC_SAMPLE; i += 1024) {
-        unsigned short key = 0;                                            // padding sorts last
-        if (ext_keys) {
-            if (i < ns) key = ext_keys[(size_t)w * ext_n + i];
-        } else if (i < ns) {
-            // 16 consecutive jobs = one 32-byte sector of the row; chunks evenly strided over the jobs
-            const long long nchunks = (ns + 15) / 16, chunk = i >> 4;
-            long long col = (N / nchunks) * chunk + (i & 15);
-            if (col >= N) col = N - 1;
-            __half c = p.cost[col];
-            const short o = p.owner[col];
-            if (st.ff_pending > 0 && o >= 0)
-                for (int r = 0; r < st.ff_pending; ++r) c = __hadd(c, eps);
-            const __half s = S[(size_t)w * ld + col];
-            const __half v = (o == w) ? s : __hsub(s, c);
-            key = (unsigned short)h2key(h2bits(v));
+    {
+        constexpr int PER = AUC_SAMPLE / 1024;
+        __half c_r[PER], s_r[PER];
+        short o_r[PER];
+        unsigned short k_r[PER];
+        const long long nchunks = (ns + 15) / 16, cstride = N / (nchunks > 0 ? nchunks : 1);
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {                                        // all loads first: one latency, not PER
+            const int i = tid + q * 1024;
+            k_r[q] = 0;                                                        // padding sorts last
+            c_r[q] = s_r[q] = __ushort_as_half(0);
+            o_r[q] = -1;
+            if (ext_keys) {
+                if (i < ns) k_r[q] = ext_keys[(size_t)w * ext_n + i];
+            } else if (i < ns) {
+                // 16 consecutive jobs = one 32-byte sector of the row; chunks evenly strided over the jobs
+                long long col = cstride * (i >> 4) + (i & 15);
+                if (col >= N) col = N - 1;
+                c_r[q] = p.cost[col];
+                o_r[q] = p.owner[col];
+                s_r[q] = S[(size_t)w * ld + col];
+            }
         }
-        keys[i] = key;
-        if (collect_out && i < collect_n) collect_out[(size_t)w * collect_n + i] = key;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int i = tid + q * 1024;
+            unsigned short key = k_r[q];
+            if (!ext_keys && i < ns) {
+                __half c = c_r[q];
+                if (st.ff_pending > 0 && o_r[q] >= 0)
+                    for (int r = 0; r < st.ff_pending; ++r) c = __hadd(c, eps);
+                const __half v = (o_r[q] == w) ? s_r[q] : __hsub(s_r[q], c);
+                key = (unsigned short)h2key(h2bits(v));
+            }
+            keys[i] = key;
+            if (collect_out && i < collect_n) collect_out[(size_t)w * collect_n + i] = key;
+        }
     }
     if (collect_out) return;
     __syncthreads();
@@ -1420,15 +1503,7 @@ auction_sample_kernel(const __half* __restrict__ S, long long ld, long long N, i
             __syncthreads();
             for (int i = tid; i < AUC_SAMPLE; i += 1024) atomicAdd(&shist[keys[i] >> 8], 1u);
             __syncthreads();
-            if (tid == 0) {
-                int cum = 0, bsel = 0;
-                for (int bb = 255; bb >= 0; --bb) {
-                    if (cum + (int)shist[bb] >= need_n) { bsel = bb; break; }
-                    cum += shist[bb];
-                }
-                s_b1 = bsel;
-                s_above1 = cum;
-            }
+            if (tid < 32) sample_select_bin(shist, 0, need_n, &s_b1, &s_above1);
             __syncthreads();
             const int b1 = s_b1;
             if (tid < 256) shist[tid] = 0;
@@ -1436,13 +1511,10 @@ auction_sample_kernel(const __half* __restrict__ S, long long ld, long long N, i
             for (int i = tid; i < AUC_SAMPLE; i += 1024)
                 if ((keys[i] >> 8) == b1) atomicAdd(&shist[keys[i] & 255], 1u);
             __syncthreads();
-            if (tid == 0) {
-                int cum = s_above1, bsel = 0;
-                for (int bb = 255; bb >= 0; --bb) {
-                    if (cum + (int)shist[bb] >= need_n) { bsel = bb; break; }
-                    cum += shist[bb];
-                }
-                s_vlo = (b1 << 8) | bsel;
+            if (tid < 32) {
+                int bsel, dummy;
+                sample_select_bin(shist, s_above1, need_n, &bsel, &dummy);
+                if (tid == 0) s_vlo = (b1 << 8) | bsel;
             }
             __syncthreads();
             const int vlo = s_vlo;

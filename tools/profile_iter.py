@@ -25,3 +25,6 @@ for it in range(int(os.environ.get("PROF_ITERS", 2))):
     torch.cuda.synchronize()
     print(f"iteration {it}: rounds {stats.rounds} passes {stats.passes} cold {stats.cold_passes} "
           f"misses {stats.window_misses} shift {shift:.4f}")
+    from generative_ranking_recommender_b200 import engine as _e
+    _ws = _e.SCRATCH.get("auction", 256, dev)
+    print("   threshold sink per worker-round (<64, <128, <250, >=250 keys):", _ws[:128].view(torch.int32)[17:21].tolist())
