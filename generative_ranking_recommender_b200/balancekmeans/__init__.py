@@ -15,6 +15,7 @@ instead of silently running somewhere else.  There is no CPU path: a CPU device 
 """
 from __future__ import annotations
 
+import ctypes
 import pickle
 import threading
 from typing import List, Optional
@@ -129,37 +130,91 @@ def _minmax_keys(s_half: torch.Tensor) -> torch.Tensor:
 # KMeans
 # ------------------------------------------------------------------------------------------------
 
-class _InitPrefetcher:
-    """Draws the NEXT `np.random.choice` of the fit on a host thread while the GPU iterates
-    (the draw permutes all N rows, 0.4 s at 10 M).  The NumPy global state is
-    snapshotted first and restored if the draw turns out not to be needed, so the stream the rest
-    of the program sees is exactly the reference's."""
+def legacy_choice(n: int, k: int, state=None):
+    """np.random.choice(n, k, replace=False) on NumPy's global legacy generator, computed by the library
+    (csrc/seed_draw.cu) from the generator's MT19937 state: same indices, same state afterwards, a fraction of
+    the time, and without the interpreter lock.  With `state` (an np.random.get_state() tuple) the global
+    generator is left alone and (indices, new_state) is returned."""
+    use_global = state is None
+    st = np.random.get_state() if use_global else state
+    if st[0] != "MT19937" or k > n:                       # not the legacy generator's stock configuration
+        if not use_global:
+            raise ValueError("legacy_choice: unsupported generator state")
+        return np.random.choice(n, k, replace=(k > n))
+    key = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
+    pos = ctypes.c_int32(int(st[2]))
+    scratch = np.empty(n, dtype=np.int64)
+    out = np.empty(k, dtype=np.int64)
+    engine.check(engine.lib().rqk_legacy_choice(key.ctypes.data_as(ctypes.c_void_p), ctypes.byref(pos), n, k,
+                                                scratch.ctypes.data_as(ctypes.c_void_p),
+                                                out.ctypes.data_as(ctypes.c_void_p)))
+    new_state = ("MT19937", key, int(pos.value), st[3], st[4])
+    if use_global:
+        np.random.set_state(new_state)
+        return out
+    return out, new_state
 
-    def __init__(self, n: int, k: int):
-        self.n, self.k = n, k
+
+class _SpeculativeDraw:
+    """Hides the host-side seed draws behind the GPU work (every draw permutes all N rows).
+    Every draw of a fit is np.random.choice(N, K, replace=False) on the global generator, i.e. a prefix of ONE
+    permutation whose RNG consumption does not depend on K, so as soon as a draw has been handed out the NEXT
+    one can be computed on a host thread from a snapshot of the generator state (the library call runs without
+    the interpreter lock).  The result is only used if the global state still equals the snapshot when the next
+    draw is asked for - then the state is advanced exactly as NumPy would have - and silently dropped otherwise,
+    so the random stream the rest of the program sees is the reference's."""
+
+    KMAX = 4096
+
+    def __init__(self):
         self.thread: Optional[threading.Thread] = None
+        self.n = -1
         self.state = None
         self.result = None
+        self.new_state = None
 
-    def start(self):
-        self.state = np.random.get_state()
+    @staticmethod
+    def _same(a, b) -> bool:
+        return a[0] == b[0] and int(a[2]) == int(b[2]) and int(a[3]) == int(b[3]) and \
+            float(a[4]) == float(b[4]) and np.array_equal(a[1], b[1])
+
+    def start(self, n: int):
+        if n < 200000:                                     # cheap draws are not worth a thread
+            return
+        st = np.random.get_state()
+        if st[0] != "MT19937":
+            return
+        self.join()
+        self.n, self.state, self.result, self.new_state = n, st, None, None
 
         def work():
-            self.result = np.random.choice(self.n, self.k, replace=(self.k > self.n))
+            self.result, self.new_state = legacy_choice(n, min(n, self.KMAX), st)
 
         self.thread = threading.Thread(target=work, daemon=True)
         self.thread.start()
 
-    def take(self) -> np.ndarray:
-        self.thread.join()
-        self.thread = None
-        return self.result
-
-    def cancel(self):
+    def join(self):
         if self.thread is not None:
             self.thread.join()
             self.thread = None
-            np.random.set_state(self.state)
+
+    def take(self, n: int, k: int) -> Optional[np.ndarray]:
+        if self.state is None or n != self.n or k > min(n, self.KMAX):
+            return None
+        if not self._same(np.random.get_state(), self.state):
+            self.join()
+            self.state = None
+            return None
+        self.join()
+        res, new_state = self.result, self.new_state
+        self.state = None
+        if res is None:
+            return None
+        np.random.set_state(new_state)
+        return res[:k].copy()
+
+
+_SPECULATIVE = _SpeculativeDraw()
 
 
 class KMeans(object):
@@ -188,7 +243,14 @@ class KMeans(object):
     # -- initialisation ---------------------------------------------------------------------
     def _draw(self, num_samples: int) -> np.ndarray:
         """:247-253, host NumPy global RNG (full permutation of N, like the reference)."""
-        return np.random.choice(num_samples, self.n_clusters, replace=(self.n_clusters > num_samples))
+        k = self.n_clusters
+        if k > num_samples:
+            return np.random.choice(num_samples, k, replace=True)
+        idx = _SPECULATIVE.take(num_samples, k)
+        if idx is None:
+            idx = legacy_choice(num_samples, k)
+        _SPECULATIVE.start(num_samples)                     # the draw after this one, off the critical path
+        return idx
 
     def _rows(self, X: torch.Tensor, indices: np.ndarray, n_global: int, row0: int) -> torch.Tensor:
         shard = self._shard
@@ -312,43 +374,34 @@ class KMeans(object):
         min_loss, best = float("inf"), None
         pending = None      # centroids of the previous iteration whose loss is not known yet
         self.last_fit_stats = []
-        prefetch = _InitPrefetcher(n_global, k) if n_global >= 200000 else None
         scores_buf = None
-        try:
-            while True:
-                reinit = iteration > 0 and iteration % 10 == 0             # :305
-                if reinit:
-                    if pending is not None:                                # loss of the centres we are about to drop
-                        loss = loss_of(counts_of(pending))
-                        if loss <= min_loss:
-                            min_loss, best = loss, pending
-                        pending = None
-                    idx = prefetch.take() if (prefetch and prefetch.thread) else self._draw(n_global)
-                    self.cluster_centers = self._rows(X, idx, n_global, row0)
-                if prefetch and prefetch.thread is None and (iteration + 1) % 10 == 0 and \
-                        (iter_limit == 0 or iteration + 1 < iter_limit):
-                    prefetch.start()                                       # the draw of the coming re-init
-                score, assign, stats, shift = self._iterate(X, n_global, scores_buf)
-                scores_buf = score.scores_t
-                if pending is not None:                                    # :327-341 for the previous iteration
-                    c = score.counts.to(torch.int64)
-                    shard.all_reduce(c, "sum")
-                    loss = loss_of(c.cpu().numpy())
-                    if loss <= min_loss:                                   # `<=`: later ties win
+        while True:
+            reinit = iteration > 0 and iteration % 10 == 0             # :305
+            if reinit:
+                if pending is not None:                                # loss of the centres we are about to drop
+                    loss = loss_of(counts_of(pending))
+                    if loss <= min_loss:
                         min_loss, best = loss, pending
                     pending = None
-                pending = self.cluster_centers.clone()
-                iteration += 1
-                self.last_fit_stats.append({"iteration": iteration, "shift": shift,
-                                            "rounds": stats.rounds if stats else 0,
-                                            "passes": stats.passes if stats else 0})
-                if shift ** 2 < tol:                                       # :359
-                    break
-                if iter_limit != 0 and iteration >= iter_limit:            # :361
-                    break
-        finally:
-            if prefetch:
-                prefetch.cancel()
+                self.cluster_centers = self._rows(X, self._draw(n_global), n_global, row0)
+            score, assign, stats, shift = self._iterate(X, n_global, scores_buf)
+            scores_buf = score.scores_t
+            if pending is not None:                                    # :327-341 for the previous iteration
+                c = score.counts.to(torch.int64)
+                shard.all_reduce(c, "sum")
+                loss = loss_of(c.cpu().numpy())
+                if loss <= min_loss:                                   # `<=`: later ties win
+                    min_loss, best = loss, pending
+                pending = None
+            pending = self.cluster_centers.clone()
+            iteration += 1
+            self.last_fit_stats.append({"iteration": iteration, "shift": shift,
+                                        "rounds": stats.rounds if stats else 0,
+                                        "passes": stats.passes if stats else 0})
+            if shift ** 2 < tol:                                       # :359
+                break
+            if iter_limit != 0 and iteration >= iter_limit:            # :361
+                break
         loss = loss_of(counts_of(pending))                                 # loss of the final iteration
         if loss <= min_loss:
             min_loss, best = loss, pending

@@ -79,6 +79,11 @@ typedef struct rqk_auction_layout {
     int64_t tie_total_offset;  /* byte offset of int32[k]: local number of values equal to the threshold */
 } rqk_auction_layout;
 
+/* Host only.  np.random.choice(n, k, replace=False) of NumPy's legacy MT19937 RandomState, state in/out
+ * (KMeans.initialize, balancekmeans/__init__.py:247-253): key uint32[624], *pos from np.random.get_state();
+ * scratch int64[n], out int64[k], all host memory. */
+int rqk_legacy_choice(uint32_t* key, int32_t* pos, int64_t n, int64_t k, int64_t* scratch, int64_t* out);
+
 size_t rqk_auction_workspace_bytes(int64_t n, int32_t k);
 int rqk_auction_layout_query(int64_t n, int32_t k, rqk_auction_layout* out /*HOST*/);
 int rqk_auction(const void* scores_t, int64_t ld, int64_t n, int32_t k, const void* minmax_keys, int32_t* assign,

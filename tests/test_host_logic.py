@@ -11,7 +11,7 @@ import torch
 from generative_ranking_recommender_b200 import (CheckpointManager, HierarchicalRQKMeans, HierarchicalRQKMeansConfig,
                                                    hierarchicalRqClusterParams)
 from generative_ranking_recommender_b200._lib import RqkError
-from generative_ranking_recommender_b200.balancekmeans import KMeans, _InitPrefetcher, pairwise_cosine
+from generative_ranking_recommender_b200.balancekmeans import KMeans, pairwise_cosine
 
 
 def _cfg(**kw):
@@ -133,22 +133,39 @@ def test_product_never_imports_the_oracle():
                 assert "import oracle" not in src and "from oracle" not in src and "rqk_oracle" not in src, f
 
 
-def test_init_prefetcher_keeps_the_numpy_stream_exact():
+def test_speculative_draws_keep_the_numpy_stream_exact():
+    """KMeans._draw hands out np.random.choice(N, K, replace=False) of the global generator and computes the next
+    draw ahead on a thread; used or dropped, the stream every other consumer sees must be NumPy's own."""
+    n = 250000                                   # above the threshold that turns speculation on
     np.random.seed(7)
-    a = np.random.choice(1000, 8, replace=False)
-    b = np.random.choice(1000, 8, replace=False)
+    want = [np.random.choice(n, k, replace=False) for k in (8, 8, 16)]
+    mid = np.random.randint(1 << 30)
+    want.append(np.random.choice(n, 4, replace=False))
     after = np.random.randint(1 << 30)
-    # same stream, second draw prefetched on a thread
     np.random.seed(7)
-    a2 = np.random.choice(1000, 8, replace=False)
-    p = _InitPrefetcher(1000, 8)
-    p.start()
-    b2 = p.take()
-    assert np.array_equal(a, a2) and np.array_equal(b, b2) and np.random.randint(1 << 30) == after
-    # a cancelled prefetch leaves no trace
-    np.random.seed(7)
-    np.random.choice(1000, 8, replace=False)
-    p = _InitPrefetcher(1000, 8)
-    p.start()
-    p.cancel()
-    assert np.array_equal(np.random.choice(1000, 8, replace=False), b)
+    km8, km16, km4 = (KMeans(n_clusters=k, device=torch.device("cpu")) for k in (8, 16, 4))
+    got = [km8._draw(n), km8._draw(n), km16._draw(n)]          # 2nd and 3rd come from the speculative thread
+    assert np.random.randint(1 << 30) == mid                    # ... which the generator state reflects exactly
+    got.append(km4._draw(n))                                    # speculation invalidated by the randint: recomputed
+    assert np.random.randint(1 << 30) == after
+    for a, b in zip(want, got):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("n,k,seed", [(1, 1, 0), (10, 10, 1), (1000, 7, 2), (65537, 128, 3), (300000, 256, 4)])
+def test_legacy_choice_is_numpy_global_choice(n, k, seed):
+    """The library's host-side seed draw must be np.random.choice(n, k, replace=False) on the global legacy
+    generator: same indices, same generator state afterwards (reference: balancekmeans/__init__.py:247-253)."""
+    from generative_ranking_recommender_b200.balancekmeans import legacy_choice
+    np.random.seed(seed)
+    np.random.rand(seed + 3)                        # a state in the middle of a block of 624
+    want1 = np.random.choice(n, k, replace=False)
+    want2 = np.random.choice(n, k, replace=False)
+    tail = np.random.rand(4)
+    np.random.seed(seed)
+    np.random.rand(seed + 3)
+    got1 = legacy_choice(n, k)
+    got2, st = legacy_choice(n, k, np.random.get_state())     # explicit-state form leaves the global alone
+    assert np.array_equal(got1, want1) and np.array_equal(got2, want2)
+    np.random.set_state(st)
+    assert np.array_equal(np.random.rand(4), tail)
