@@ -1820,14 +1820,17 @@ int rqk_auction_sample_window(int64_t n, int64_t ld, int32_t k, int64_t n_global
 }
 
 // Thresholds from the (already rank-summed) reduce block + local tie prefix.
-int rqk_auction_resolve(int64_t n, int64_t ld, int32_t k, int64_t n_global, void* workspace, size_t workspace_bytes,
-                        void* stream_) {
+// expect: -1, or 0 (HIST) / 1 (BID): act only if that is the pass that just ran, so that a caller can enqueue
+// "HIST, resolve(0), BID, resolve(1)" per round without knowing whether the HIST pass resolved every threshold.
+int rqk_auction_resolve(int64_t n, int64_t ld, int32_t k, int64_t n_global, int32_t expect, void* workspace,
+                        size_t workspace_bytes, void* stream_) {
     using namespace rqk;
     AuctionArgs a;
     int rc = auction_prepare(n, ld, k, workspace, workspace_bytes, &a, "rqk_auction_resolve");
     if (rc) return rc;
     cudaStream_t stream = (cudaStream_t)stream_;
-    auction_resolve_kernel<<<1, 1024, 0, stream>>>(a.p, n_global, k, n_global / k, -1);
+    if (expect < -1 || expect > 1) return fail(RQK_ERR_ARG, "rqk_auction_resolve: expect must be -1, 0 or 1%s");
+    auction_resolve_kernel<<<1, 1024, 0, stream>>>(a.p, n_global, k, n_global / k, expect);
     auction_tieprefix_kernel<<<k, AUC_MAX_CTAS, 0, stream>>>(a.p, k, a.G);
     RQK_LAUNCH_OK();
     return 0;

@@ -46,6 +46,7 @@ class ShardGroup:
         self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         self.world = dist.get_world_size(group) if self.active else 1
         self.rank = dist.get_rank(group) if self.active else 0
+        self.nccl = self.active and dist.get_backend(group) == "nccl"
 
     def all_reduce(self, t: torch.Tensor, op: str = "sum"):
         if self.active:
@@ -58,9 +59,14 @@ class ShardGroup:
             return t.unsqueeze(0)
         # moved as raw bytes: NCCL has no 16-bit integer type and a gather needs none
         raw = t.contiguous().reshape(-1).view(torch.uint8)
-        parts = [torch.empty_like(raw) for _ in range(self.world)]
-        self.dist.all_gather(parts, raw, group=self.group)
-        return torch.stack(parts).view(t.dtype).reshape((self.world,) + tuple(t.shape))
+        if self.nccl:
+            out = torch.empty((self.world, raw.numel()), dtype=torch.uint8, device=raw.device)
+            self.dist.all_gather_into_tensor(out, raw, group=self.group)
+        else:                                                # gloo (the CPU tests) has no single-buffer gather
+            parts = [torch.empty_like(raw) for _ in range(self.world)]
+            self.dist.all_gather(parts, raw, group=self.group)
+            out = torch.stack(parts)
+        return out.view(t.dtype).reshape((self.world,) + tuple(t.shape))
 
 
 _NO_SHARD = None
@@ -70,7 +76,7 @@ def no_shard() -> ShardGroup:
     global _NO_SHARD
     if _NO_SHARD is None:
         g = ShardGroup.__new__(ShardGroup)
-        g.dist, g.group, g.active, g.world, g.rank = None, None, False, 1, 0
+        g.dist, g.group, g.active, g.world, g.rank, g.nccl = None, None, False, 1, 0, False
         _NO_SHARD = g
     return _NO_SHARD
 
@@ -193,18 +199,25 @@ def auction(scores_t: torch.Tensor, n: int, minmax: torch.Tensor,
     shard.all_reduce(mm[0:1], "max")
     shard.all_reduce(mm[1:2], "min")
     sess.init(mm)
-    batch = 6
+    batch = 3
     info = None
+    tail = sess.reduce_block[-2:]                                     # jobs with a bidder, frozen-state violations
     for _ in range(0, 5000, batch):
         for _q in range(batch):
-            # identical sampled windows on every rank: 4096 / world local jobs per worker, all-gathered
+            # One ROUND, enqueued without knowing its outcome (kernels whose turn it is not return at once):
+            # identical sampled windows on every rank (4096 / world local jobs per worker, all-gathered) ...
             local = sess.sample_collect(max(4096 // shard.world, 1))
             sess.sample_window(shard.all_gather(local).permute(1, 0, 2).reshape(k, -1))
-            sess.do_pass(6)
+            # ... thresholds from the rank-summed histograms, ties ranked across ranks in rank order ...
+            sess.do_pass(2)
             shard.all_reduce(sess.reduce_block, "sum")
-            sess.resolve()
+            sess.resolve(0)
             totals = shard.all_gather(sess.tie_total)                 # [world, k]
             sess.tie_offset(sharding.rank_tie_offsets(totals, shard.rank) if shard.rank > 0 else None)
+            # ... the bidding round on the local jobs, and its two global counters
+            sess.do_pass(4)
+            shard.all_reduce(tail, "sum")
+            sess.resolve(1)
         info = sess.poll()
         if info.done:
             break
@@ -257,8 +270,10 @@ class AuctionSession:
         check(self.L.rqk_auction_sample_window(self.n, self.ld, self.k, self.n_global, _ptr(self._keys),
                                                int(self._keys.shape[1]), *self._args(), _stream(self.dev)))
 
-    def resolve(self):
-        check(self.L.rqk_auction_resolve(self.n, self.ld, self.k, self.n_global, *self._args(), _stream(self.dev)))
+    def resolve(self, expect: int = -1):
+        """expect: -1, or 0 / 1 = act only if a HIST / BID pass has just run."""
+        check(self.L.rqk_auction_resolve(self.n, self.ld, self.k, self.n_global, expect, *self._args(),
+                                         _stream(self.dev)))
 
     def tie_offset(self, offsets: Optional[torch.Tensor]):
         if offsets is None:

@@ -199,9 +199,10 @@ def test_auction_constant_matrix(dev, engine, bid_path):
     assert np.array_equal(a.cpu().numpy().astype(np.int64), ref.assignment) and stats.rounds == ref.rounds
 
 
+@pytest.mark.parametrize("protocol", ["pass", "round"])
 @pytest.mark.parametrize("sampled", [True, False])
 @pytest.mark.parametrize("n,k,split", [(4100, 16, 2), (20010, 128, 3), (12900, 256, 2), (4096, 16, 4)])
-def test_sharded_auction_protocol_single_gpu_emulation(dev, engine, n, k, split, sampled, bid_path):
+def test_sharded_auction_protocol_single_gpu_emulation(dev, engine, n, k, split, sampled, bid_path, protocol):
     """The multi-GPU protocol (jobs sharded over ranks; reduce block summed between pass and resolve; tie
     totals gathered) driven for `split` virtual ranks in ONE process with the same C-ABI step functions.
     Must equal the unsharded result bit for bit."""
@@ -226,15 +227,35 @@ def test_sharded_auction_protocol_single_gpu_emulation(dev, engine, n, k, split,
             allk = torch.cat([q.sample_collect(4096 // split) for q in sess], dim=1)
             for q in sess:
                 q.sample_window(allk)
-        for q in sess:
-            q.do_pass(6)
-        total = sum(q.reduce_block.clone() for q in sess)
-        for q in sess:
-            q.reduce_block.copy_(total)
-            q.resolve()
-        tt = torch.stack([q.tie_total.clone() for q in sess])
-        for r, q in enumerate(sess):
-            q.tie_offset(tt[:r].sum(0, dtype=torch.int32) if r else None)
+        def all_reduce(view):
+            total = sum(view(q).clone() for q in sess)
+            for q in sess:
+                view(q).copy_(total)
+
+        def tie_offsets():
+            tt = torch.stack([q.tie_total.clone() for q in sess])
+            for r, q in enumerate(sess):
+                q.tie_offset(tt[:r].sum(0, dtype=torch.int32) if r else None)
+
+        if protocol == "pass":          # one pass per step, whichever the state machine wants
+            for q in sess:
+                q.do_pass(6)
+            all_reduce(lambda q: q.reduce_block)
+            for q in sess:
+                q.resolve()
+            tie_offsets()
+        else:                           # one ROUND per step, as engine.auction enqueues it (HIST, resolve, BID, resolve)
+            for q in sess:
+                q.do_pass(2)
+            all_reduce(lambda q: q.reduce_block)
+            for q in sess:
+                q.resolve(0)
+            tie_offsets()
+            for q in sess:
+                q.do_pass(4)
+            all_reduce(lambda q: q.reduce_block[-2:])
+            for q in sess:
+                q.resolve(1)
         infos = [q.poll() for q in sess]
         assert len({(i.done, i.counter, i.passes) for i in infos}) == 1, "ranks must stay in lock step"
         if infos[0].done:
