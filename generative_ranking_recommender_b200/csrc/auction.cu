@@ -1431,11 +1431,11 @@ __device__ __forceinline__ void sample_select_bin(const unsigned int* hist, int 
 
 // Sharded jobs: every rank samples AUC_SAMPLE / world jobs of its shard (collect_out != null: write the keys
 // and return), the host all-gathers them, and every rank places identical windows from the union
-// (ext_keys != null: [K][ext_n] keys, N = global job count).
+// (ext_keys != null: [ext_n / ext_cnt][K][ext_cnt] keys = every rank's gathered sample, N = global job count).
 __global__ void __launch_bounds__(1024, 1)
 auction_sample_kernel(const __half* __restrict__ S, long long ld, long long N, int K, long long jpw, AuctionPtrs p,
                       unsigned short* __restrict__ collect_out, int collect_n,
-                      const unsigned short* __restrict__ ext_keys, int ext_n) {
+                      const unsigned short* __restrict__ ext_keys, int ext_n, int ext_cnt) {
     const AuctionState st = *p.st;
     if (st.mode != MODE_HIST || !st.need_sample) return;
     __shared__ unsigned short keys[AUC_SAMPLE];
@@ -1457,7 +1457,7 @@ auction_sample_kernel(const __half* __restrict__ S, long long ld, long long N, i
             c_r[q] = s_r[q] = __ushort_as_half(0);
             o_r[q] = -1;
             if (ext_keys) {
-                if (i < ns) k_r[q] = ext_keys[(size_t)w * ext_n + i];
+                if (i < ns) k_r[q] = ext_keys[((size_t)(i / ext_cnt) * K + w) * ext_cnt + (i % ext_cnt)];   // [part][K][ext_cnt]
             } else if (i < ns) {
                 // 16 consecutive jobs = one 32-byte sector of the row; chunks evenly strided over the jobs
                 long long col = cstride * (i >> 4) + (i & 15);
@@ -1643,10 +1643,14 @@ auction_tieprefix_kernel(AuctionPtrs p, int K, int G) {
 }
 
 // sharded jobs: ranks are ordered, so a rank's CTAs come after all ties of lower ranks
-__global__ void auction_tie_offset_kernel(AuctionPtrs p, int K, int G, const int* __restrict__ offsets) {
+__global__ void auction_tie_offset_kernel(AuctionPtrs p, int K, int G, const int* __restrict__ totals, int rank) {
     if (p.st->mode != MODE_BID) return;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < G * K) p.tieprefix[i] += (unsigned int)offsets[i % K];
+    if (i < G * K) {
+        unsigned int off = 0;
+        for (int r = 0; r < rank; ++r) off += (unsigned int)totals[r * K + i % K];
+        p.tieprefix[i] += off;
+    }
 }
 
 __global__ void auction_finalize_kernel(AuctionPtrs p, long long N, int* __restrict__ assign) {
@@ -1697,7 +1701,7 @@ static int auction_launch(const AuctionArgs& a, const void* scores_t, int64_t ld
     }
     const int spc = auction_spc(n, k);
     if (which & 1)
-        auction_sample_kernel<<<k, 1024, 0, stream>>>((const __half*)scores_t, ld, n, k, n_global / k, a.p, nullptr, 0, nullptr, 0);
+        auction_sample_kernel<<<k, 1024, 0, stream>>>((const __half*)scores_t, ld, n, k, n_global / k, a.p, nullptr, 0, nullptr, 0, 1);
     if (which & 2) {
         static size_t hs_set = 0;
         const size_t hs = auction_hist_smem(k);
@@ -1800,21 +1804,23 @@ int rqk_auction_sample_collect(const void* scores_t, int64_t ld, int64_t n, int3
     if (rc) return rc;
     if (!scores_t || !out || count < 1 || count > AUC_SAMPLE) return fail(RQK_ERR_ARG, "rqk_auction_sample_collect: bad argument%s");
     auction_sample_kernel<<<k, 1024, 0, (cudaStream_t)stream_>>>((const __half*)scores_t, ld, n, k, n_global / k, a.p,
-                                                                  (unsigned short*)out, count, nullptr, 0);
+                                                                  (unsigned short*)out, count, nullptr, 0, 1);
     RQK_LAUNCH_OK();
     return 0;
 }
 
-// Sharded window sampling, step 2: keys [k][count] = the all-gathered samples of every rank (count <= 4096).
+// Sharded window sampling, step 2: keys [parts][k][count] = the all-gathered samples of every rank, exactly as an
+// all-gather of step 1's outputs lays them out (parts * count <= 4096).
 int rqk_auction_sample_window(int64_t n, int64_t ld, int32_t k, int64_t n_global, const void* keys, int32_t count,
-                              void* workspace, size_t workspace_bytes, void* stream_) {
+                              int32_t parts, void* workspace, size_t workspace_bytes, void* stream_) {
     using namespace rqk;
     AuctionArgs a;
     int rc = auction_prepare(n, ld, k, workspace, workspace_bytes, &a, "rqk_auction_sample_window");
     if (rc) return rc;
-    if (!keys || count < 1 || count > AUC_SAMPLE) return fail(RQK_ERR_ARG, "rqk_auction_sample_window: bad argument%s");
+    if (!keys || count < 1 || parts < 1 || (int64_t)count * parts > AUC_SAMPLE)
+        return fail(RQK_ERR_ARG, "rqk_auction_sample_window: bad argument%s");
     auction_sample_kernel<<<k, 1024, 0, (cudaStream_t)stream_>>>(nullptr, ld, n_global, k, n_global / k, a.p, nullptr, 0,
-                                                                  (const unsigned short*)keys, count);
+                                                                  (const unsigned short*)keys, count * parts, count);
     RQK_LAUNCH_OK();
     return 0;
 }
@@ -1836,15 +1842,17 @@ int rqk_auction_resolve(int64_t n, int64_t ld, int32_t k, int64_t n_global, int3
     return 0;
 }
 
-// offsets: device int32[k] = sum of tie_total over lower ranks.
-int rqk_auction_tie_offset(int64_t n, int64_t ld, int32_t k, const int32_t* offsets, void* workspace,
+// totals: device int32[world][k] = every rank's tie_total (an all-gather of it); this rank's CTAs come after all
+// ties of the ranks below it.
+int rqk_auction_tie_offset(int64_t n, int64_t ld, int32_t k, const int32_t* totals, int32_t rank, void* workspace,
                            size_t workspace_bytes, void* stream_) {
     using namespace rqk;
     AuctionArgs a;
     int rc = auction_prepare(n, ld, k, workspace, workspace_bytes, &a, "rqk_auction_tie_offset");
     if (rc) return rc;
-    if (!offsets) return fail(RQK_ERR_ARG, "rqk_auction_tie_offset: null offsets%s");
-    auction_tie_offset_kernel<<<ceil_div(a.G * k, 256), 256, 0, (cudaStream_t)stream_>>>(a.p, k, a.G, offsets);
+    if (!totals || rank < 0) return fail(RQK_ERR_ARG, "rqk_auction_tie_offset: bad argument%s");
+    if (rank == 0) return 0;
+    auction_tie_offset_kernel<<<ceil_div(a.G * k, 256), 256, 0, (cudaStream_t)stream_>>>(a.p, k, a.G, totals, rank);
     RQK_LAUNCH_OK();
     return 0;
 }

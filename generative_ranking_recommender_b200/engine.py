@@ -207,13 +207,13 @@ def auction(scores_t: torch.Tensor, n: int, minmax: torch.Tensor,
             # One ROUND, enqueued without knowing its outcome (kernels whose turn it is not return at once):
             # identical sampled windows on every rank (4096 / world local jobs per worker, all-gathered) ...
             local = sess.sample_collect(max(4096 // shard.world, 1))
-            sess.sample_window(shard.all_gather(local).permute(1, 0, 2).reshape(k, -1))
+            sess.sample_window(shard.all_gather(local))
             # ... thresholds from the rank-summed histograms, ties ranked across ranks in rank order ...
             sess.do_pass(2)
             shard.all_reduce(sess.reduce_block, "sum")
             sess.resolve(0)
             totals = shard.all_gather(sess.tie_total)                 # [world, k]
-            sess.tie_offset(sharding.rank_tie_offsets(totals, shard.rank) if shard.rank > 0 else None)
+            sess.tie_offset(totals, shard.rank)
             # ... the bidding round on the local jobs, and its two global counters
             sess.do_pass(4)
             shard.all_reduce(tail, "sum")
@@ -265,21 +265,26 @@ class AuctionSession:
         return out
 
     def sample_window(self, keys: torch.Tensor):
-        """Step 2: keys int16 [k, total] = every rank's samples side by side (total <= 4096)."""
+        """Step 2: keys int16 [world, k, count] = the all-gather of every rank's step-1 output (world * count <=
+        4096); [k, count] is accepted for a single part."""
+        if keys.dim() == 2:
+            keys = keys.unsqueeze(0)
         self._keys = keys.contiguous()
-        check(self.L.rqk_auction_sample_window(self.n, self.ld, self.k, self.n_global, _ptr(self._keys),
-                                               int(self._keys.shape[1]), *self._args(), _stream(self.dev)))
+        parts, _, count = self._keys.shape
+        check(self.L.rqk_auction_sample_window(self.n, self.ld, self.k, self.n_global, _ptr(self._keys), int(count),
+                                               int(parts), *self._args(), _stream(self.dev)))
 
     def resolve(self, expect: int = -1):
         """expect: -1, or 0 / 1 = act only if a HIST / BID pass has just run."""
         check(self.L.rqk_auction_resolve(self.n, self.ld, self.k, self.n_global, expect, *self._args(),
                                          _stream(self.dev)))
 
-    def tie_offset(self, offsets: Optional[torch.Tensor]):
-        if offsets is None:
+    def tie_offset(self, totals: torch.Tensor, rank: int):
+        """totals int32 [world, k] = the all-gather of every rank's `tie_total`."""
+        if rank == 0:
             return
-        self._offs = offsets.to(torch.int32).contiguous()
-        check(self.L.rqk_auction_tie_offset(self.n, self.ld, self.k, _ptr(self._offs), *self._args(),
+        self._tot = totals.to(torch.int32).contiguous()
+        check(self.L.rqk_auction_tie_offset(self.n, self.ld, self.k, _ptr(self._tot), int(rank), *self._args(),
                                             _stream(self.dev)))
 
     def poll(self) -> AuctionInfo:

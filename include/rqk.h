@@ -97,11 +97,11 @@ int rqk_auction_pass(const void* scores_t, int64_t ld, int64_t n, int32_t k, int
 int rqk_auction_sample_collect(const void* scores_t, int64_t ld, int64_t n, int32_t k, int64_t n_global, void* out,
                                int32_t count, void* workspace, size_t workspace_bytes, void* stream);
 int rqk_auction_sample_window(int64_t n, int64_t ld, int32_t k, int64_t n_global, const void* keys, int32_t count,
-                              void* workspace, size_t workspace_bytes, void* stream);
+                              int32_t parts, void* workspace, size_t workspace_bytes, void* stream);   /* keys [parts][k][count] */
 int rqk_auction_resolve(int64_t n, int64_t ld, int32_t k, int64_t n_global, int32_t expect, void* workspace,
                         size_t workspace_bytes, void* stream);   /* expect: -1 any, 0 after a HIST pass, 1 after a BID pass */
-int rqk_auction_tie_offset(int64_t n, int64_t ld, int32_t k, const int32_t* offsets, void* workspace,
-                           size_t workspace_bytes, void* stream);
+int rqk_auction_tie_offset(int64_t n, int64_t ld, int32_t k, const int32_t* totals /*[world][k]*/, int32_t rank,
+                           void* workspace, size_t workspace_bytes, void* stream);
 int rqk_auction_poll(int64_t n, int64_t ld, int32_t k, void* workspace, size_t workspace_bytes,
                      rqk_auction_info* info /*HOST*/, void* stream);   /* synchronises */
 int rqk_auction_finalize(int64_t n, int64_t ld, int32_t k, void* workspace, size_t workspace_bytes, int32_t* assign,

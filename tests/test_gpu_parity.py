@@ -224,7 +224,7 @@ def test_sharded_auction_protocol_single_gpu_emulation(dev, engine, n, k, split,
     done = False
     for _ in range(3000):
         if sampled:      # identical windows on every rank from the all-gathered per-rank samples
-            allk = torch.cat([q.sample_collect(4096 // split) for q in sess], dim=1)
+            allk = torch.stack([q.sample_collect(4096 // split) for q in sess])      # [ranks, k, count], as all-gathered
             for q in sess:
                 q.sample_window(allk)
         def all_reduce(view):
@@ -235,7 +235,7 @@ def test_sharded_auction_protocol_single_gpu_emulation(dev, engine, n, k, split,
         def tie_offsets():
             tt = torch.stack([q.tie_total.clone() for q in sess])
             for r, q in enumerate(sess):
-                q.tie_offset(tt[:r].sum(0, dtype=torch.int32) if r else None)
+                q.tie_offset(tt, r)
 
         if protocol == "pass":          # one pass per step, whichever the state machine wants
             for q in sess:
