@@ -42,54 +42,101 @@ def _env_int(name, default):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md's clocks line).  The timed region of
+    a default run is ~0.1 s, shorter than nvidia-smi's start-up, so the sampler reads NVML directly (the same
+    counters nvidia-smi prints) every 2 ms on a host thread; nvidia-smi -lms is the fallback without pynvml.
+    Only samples taken between mark_begin() and mark_end() count."""
+
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index):
         self.index = index
-        self.samples = []
+        self.samples = []          # (time, sm_mhz, reasons bitmask or set)
+        self.max_mhz = None
+        self.stop_flag = False
+        self.thread = None
         self.proc = None
+        self.t0 = self.t1 = None
+        self.source = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        try:
+                            bits = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                        except Exception:
+                            bits = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        self.samples.append((time.perf_counter(), mhz, bits))
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.source = "nvidia-smi"
+
+            def read():
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for line in self.proc.stdout:
+                    f = [x.strip() for x in line.split(",")]
+                    try:
+                        mhz, self.max_mhz = float(f[0]), float(f[1])
+                    except (ValueError, IndexError):
+                        continue
+                    bits = sum(self.REASONS[n] for n, v in zip(names, f[2:6]) if v.lower().startswith("active"))
+                    self.samples.append((time.perf_counter(), mhz, bits))
+
+            self.thread = threading.Thread(target=read, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append(line.strip())
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        mhz, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            f = [x.strip() for x in s.split(",")]
-            if len(f) < 6:
-                continue
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
             try:
-                mhz.append(float(f[0]))
-                mx = float(f[1])
-            except ValueError:
-                continue
-            for n, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        mhz.sort()
-        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(mhz)}
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        if self.thread:
+            self.thread.join(timeout=2)
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"], "samples": 0}
+        inside = [x for x in self.samples if self.t0 is not None and self.t0 <= x[0] <= (self.t1 or x[0])]
+        mhz = sorted(x[1] for x in inside)
+        bits = 0
+        for x in inside:
+            bits |= x[2]
+        reasons = sorted(n for n, b in self.REASONS.items() if bits & b)
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(mhz), "source": self.source}
 
 
 def measured_peaks():
@@ -246,20 +293,24 @@ def main():
             passes.append(stats.passes)
             rounds.append(stats.rounds)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                                      # before the warm-up: it is streaming when the timed region starts
     for i in range(args.warmup):
         step(i)
     passes.clear()
     rounds.clear()
-    sampler = ClockSampler(local)
     barrier()
     if rank == 0:
-        sampler.start()
+        sampler.mark_begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(args.steps):
         step(args.warmup + i)
     ev1.record()
     barrier()
+    if rank == 0:
+        sampler.mark_end()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
