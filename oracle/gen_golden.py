@@ -215,10 +215,58 @@ def gen_iter_limit():
     print("iter_limit:", len(rows))
 
 
+def gen_io():
+    """The reference driver's own CSV reader, id assembly, jsonl writer and statistics on a small case with the
+    awkward inputs (short rows, non-numeric fields, wrong dimension, quotes / non-ASCII / duplicate song ids)."""
+    import json
+    import tempfile
+    from src.semantic_id_generator import train_semantic_ids as ref_t
+    cls = ref_t.SemanticIDTrainer
+    rng = np.random.default_rng(3)
+    D, L = 6, 3
+    names = ["s1", "song,with,commas", 'quo"te', "дом", "s1", "tab\tid", "7", "s8", "", "s10"]
+    lines = []
+    for i, nm in enumerate(names):
+        vec = ["%.6g" % v for v in rng.standard_normal(D)]
+        if i == 2:
+            vec = vec[:-1]                      # wrong dimension
+        if i == 5:
+            vec[1] = "abc"                      # non-numeric
+        row = [nm] + vec
+        import csv as _csv, io as _io
+        bio = _io.StringIO()
+        _csv.writer(bio).writerow(row)
+        lines.append(bio.getvalue())
+    lines.insert(4, "lonely\r\n")              # fewer than two fields
+    csv_text = "".join(lines)
+    tmp = tempfile.mkdtemp()
+    csv_path = os.path.join(tmp, "v.csv")
+    open(csv_path, "w", encoding="utf-8", newline="").write(csv_text)
+    fake = types.SimpleNamespace(rqkmeans_config=types.SimpleNamespace(embedding_dim=D, layer_clusters=[4, 4, 8],
+                                                                       need_clusters=[4, 4, 8]))
+    fake.config = types.SimpleNamespace(data=types.SimpleNamespace(song_vectors_file=csv_path))
+    ids, emb = cls.load_song_vectors(fake, None)
+    ids7, emb7 = cls.load_song_vectors(fake, 7)
+    n = len(ids)
+    cluster_ids = [torch.from_numpy(rng.integers(0, k, n).astype(np.int64)) for k in (4, 4, 8)]
+    cluster_ids[2][1] = cluster_ids[2][0]; cluster_ids[1][1] = cluster_ids[1][0]; cluster_ids[0][1] = cluster_ids[0][0]
+    sem = cls._generate_semantic_ids(fake, ids, {"cluster_ids": cluster_ids})
+    out_path = os.path.join(tmp, "o", "song_semantic_ids.jsonl")
+    fake.config = types.SimpleNamespace(data=types.SimpleNamespace(semantic_ids_file=out_path))
+    cls._save_semantic_ids(fake, sem)
+    stats = cls._generate_statistics(fake, sem)
+    np.savez_compressed(os.path.join(OUT, "io.npz"), csv=np.frombuffer(csv_text.encode("utf-8"), dtype=np.uint8),
+                        song_ids=np.array(json.dumps(ids)), emb=emb.numpy(), song_ids7=np.array(json.dumps(ids7)),
+                        cluster_ids=torch.stack(cluster_ids).numpy(),
+                        jsonl=np.frombuffer(open(out_path, "rb").read(), dtype=np.uint8),
+                        stats=np.array(json.dumps(stats)))
+    print("io:", n, "songs,", len(sem), "distinct ids written")
+
+
 if __name__ == "__main__":
     import contextlib
     import io
-    which = sys.argv[1:] or ["auction", "eps", "distance", "stage", "encode", "fit_stats", "iter_limit"]
+    which = sys.argv[1:] or ["auction", "eps", "distance", "stage", "encode", "fit_stats", "iter_limit", "io"]
     for w in which:
         buf = io.StringIO()
         with contextlib.redirect_stdout(buf):   # the reference prints every iteration
