@@ -61,6 +61,7 @@ constexpr int AUC_COLD_SHIFT = 8;  // 256 bins x 256 keys cover all 65536 fp16 k
 constexpr int AUC_MIN_KEY = 0x0400; // key of the most negative finite half: fine windows never reach -inf
 constexpr int AUC_SUB = 4096;      // jobs whose cost / owner are staged in shared memory at a time
 constexpr int AUC_QCAP = 128;      // per-warp survivor queue of the HIST kernel
+constexpr int AUC_SAMPLE_MAX = 4096; // window-sampling jobs per worker (all ranks together)
 constexpr int AUC_SEG_CAP = 256;   // survivor-list entries per (sub-range, worker); ~60 expected
 
 enum { MODE_HIST = 0, MODE_BID = 1, MODE_DONE = 2 };
@@ -114,6 +115,7 @@ struct AuctionPtrs {
     unsigned int* seg_list;   // [G*spc][K][AUC_SEG_CAP]  (job - sub-range start) << 16 | value key
     unsigned int* seg_cnt;    // [G*spc][K]  entries the HIST pass wanted to write (> AUC_SEG_CAP: overflow)
     int* list_ok;             // [1] cleared by a HIST CTA whose segment overflowed
+    unsigned int* rank_off;   // [K] ties at the threshold held by lower ranks (peer-memory sharding; else 0)
     unsigned int* ticket;     // [1] CTAs finished in the running pass kernel (fused resolve)
 };
 
@@ -162,6 +164,7 @@ static inline size_t auction_ws_layout(long long N, long long ld, int K, Auction
     size_t o_sl = take_(nseg * K * AUC_SEG_CAP * 4);
     size_t o_sc = take_(nseg * K * 4);
     size_t o_lo = take_(4);
+    size_t o_ro = take_((size_t)K * 4);
     size_t o_tk2 = take_(4);
     if (reduce_off) *reduce_off = o_hist;
     if (tie_total_off) *tie_total_off = o_tt;
@@ -189,6 +192,7 @@ static inline size_t auction_ws_layout(long long N, long long ld, int K, Auction
         p->seg_list = (unsigned int*)(base + o_sl);
         p->seg_cnt = (unsigned int*)(base + o_sc);
         p->list_ok = (int*)(base + o_lo);
+        p->rank_off = (unsigned int*)(base + o_ro);
         p->ticket = (unsigned int*)(base + o_tk2);
     }
     return off;
@@ -214,6 +218,7 @@ __global__ void auction_init_kernel(AuctionPtrs p, long long ld, int K, const un
         p.take[j] = 0;
         p.tprev[j] = -1;
         p.miss_run[j] = 0;
+        p.rank_off[j] = 0;
     }
     if (i == 0) {
         AuctionState s;
@@ -234,6 +239,69 @@ __global__ void auction_init_kernel(AuctionPtrs p, long long ld, int K, const un
         s.smin_bits = smin;
         *p.st = s;
     }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Jobs sharded over GPUs, exchange through peer memory (NVLink / NVSwitch P2P) instead of NCCL.
+// Every rank owns one "exchange block" in symmetric memory (allocated and mapped into every peer by
+// the host: torch symmetric memory); kernels read the other ranks' blocks directly and synchronise
+// with monotonically increasing sequence flags, so that the collective a round needs (sum of the
+// threshold histograms, rank-major tie counts, the two bid counters, the window samples) is part of
+// the resolve / sampling kernel instead of a library call between two kernels.
+//   flags  int32 [3 kinds][8 ranks]   flags[kind][r] = last sequence number rank r has published
+//   tail   int32 [2 parities][2]      jobs with a bidder, frozen-state violations of the local BID round
+//   hist   int32 [2 parities][RB]     local reduce block (RB = K*256 + 2K + 2)
+//   sample uint16[2 parities][K][cnt] local window samples
+// Blocks are double-buffered by the parity of the sequence number: a rank can only be two exchanges
+// ahead of a peer that still reads its block, never in the same parity.
+// ------------------------------------------------------------------------------------------
+constexpr int PEER_MAX = 8;
+constexpr int PEER_FLAGS_BYTES = 256;
+constexpr int PEER_TAIL_BYTES = 256;
+struct PeerCtx {
+    unsigned char* buf[PEER_MAX];
+    int world, rank;
+};
+__host__ __device__ inline size_t peer_rb_words(int K) { return ((size_t)K * AUC_W + 2 * K + 2 + 63) / 64 * 64; }
+__host__ __device__ inline size_t peer_sample_off(int K) { return PEER_FLAGS_BYTES + PEER_TAIL_BYTES + 2 * peer_rb_words(K) * 4; }
+__host__ __device__ inline size_t peer_bytes(int K) { return peer_sample_off(K) + 2 * (size_t)K * AUC_SAMPLE_MAX * 2; }
+__device__ __forceinline__ int* peer_flags(const PeerCtx& c, int r) { return reinterpret_cast<int*>(c.buf[r]); }
+__device__ __forceinline__ int* peer_tail(const PeerCtx& c, int r, int par) {
+    return reinterpret_cast<int*>(c.buf[r] + PEER_FLAGS_BYTES) + 2 * par;
+}
+__device__ __forceinline__ unsigned int* peer_hist(const PeerCtx& c, int r, int K, int par) {
+    return reinterpret_cast<unsigned int*>(c.buf[r] + PEER_FLAGS_BYTES + PEER_TAIL_BYTES) + (size_t)par * peer_rb_words(K);
+}
+__device__ __forceinline__ const unsigned short* peer_sample(const PeerCtx& c, int r, int K, int par) {
+    return reinterpret_cast<const unsigned short*>(c.buf[r] + peer_sample_off(K)) + (size_t)par * K * AUC_SAMPLE_MAX;
+}
+// All threads of the CTA call this after their stores to the local exchange block.  Returns false on a timeout
+// (a peer that never arrives: 4 s), which the caller turns into an error state instead of a hang.
+__device__ bool peer_barrier(const PeerCtx& c, int kind, int seq) {
+    __shared__ int s_ok;
+    __threadfence_system();
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t == 0) s_ok = 1;
+    __syncthreads();
+    if (t < c.world && t != c.rank) {
+        int* dst = peer_flags(c, t) + kind * PEER_MAX + c.rank;
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(dst), "r"(seq) : "memory");
+        const int* src = peer_flags(c, c.rank) + kind * PEER_MAX + t;
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        int v;
+        do {
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+            if (v >= seq) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 4000000000ull) { s_ok = 0; break; }
+            __nanosleep(200);
+        } while (true);
+    }
+    __syncthreads();
+    return s_ok != 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -445,6 +513,66 @@ __device__ __forceinline__ bool auction_last_cta(unsigned int* ticket) {
     __syncthreads();
     if (s_last) __threadfence();
     return s_last != 0;
+}
+
+
+// Resolve step of a sharded job with the rank exchange inside (1 CTA per rank).  expect = MODE_HIST: publish
+// the local reduce block, wait for the peers, sum theirs into it, resolve, and derive this rank's tie offsets
+// from the peers' LOCAL histograms at the resolved threshold bins; expect = MODE_BID: the same for the two bid
+// counters.  Every rank runs the identical state machine, so all take the same early exits.
+__global__ void __launch_bounds__(1024, 1)
+auction_resolve_peer_kernel(AuctionPtrs p, long long N, int K, long long jpw, int expect, PeerCtx peers, int seq) {
+    const int mode = p.st->mode;
+    if (mode == MODE_DONE || mode != expect) return;
+    const int tid = threadIdx.x, NT = blockDim.x, par = seq & 1;
+    const int RB = K * AUC_W + 2 * K + 2;
+    if (expect == MODE_HIST) {
+        unsigned int* mine = peer_hist(peers, peers.rank, K, par);
+        for (int i = tid; i < RB; i += NT) mine[i] = p.hist_g[i];
+        if (!peer_barrier(peers, 1, seq)) { if (tid == 0) { p.st->error = 1; p.st->mode = MODE_DONE; p.st->done = 1; } return; }
+        for (int r = 0; r < peers.world; ++r) {
+            if (r == peers.rank) continue;
+            const unsigned int* theirs = peer_hist(peers, r, K, par);
+            for (int i = tid; i < RB; i += NT) p.hist_g[i] += __ldcv(theirs + i);
+        }
+        __syncthreads();
+        auction_resolve_body(p, N, K, jpw, expect);
+        __syncthreads();
+        if (p.st->mode == MODE_BID) {
+            for (int w = tid; w < K; w += NT) {
+                const int base = p.win_base[w], hbase = p.win_hbase[w], nlo = p.win_nlo[w], tk = p.tkey[w];
+                const int bin = tk >= hbase ? nlo + tk - hbase : tk - base;
+                unsigned int off = 0;
+                for (int r = 0; r < peers.rank; ++r) off += __ldcv(peer_hist(peers, r, K, par) + (size_t)w * AUC_W + bin);
+                p.rank_off[w] = off;
+            }
+        }
+    } else {
+        if (tid == 0) {
+            int* mine = peer_tail(peers, peers.rank, par);
+            mine[0] = (int)*p.n_with;
+            mine[1] = (int)*p.n_viol;
+        }
+        if (!peer_barrier(peers, 2, seq)) { if (tid == 0) { p.st->error = 1; p.st->mode = MODE_DONE; p.st->done = 1; } return; }
+        if (tid == 0) {
+            unsigned int a = 0, b = 0;
+            for (int r = 0; r < peers.world; ++r) {
+                const int* t = peer_tail(peers, r, par);
+                a += (unsigned int)__ldcv(t);
+                b += (unsigned int)__ldcv(t + 1);
+            }
+            *p.n_with = a;
+            *p.n_viol = b;
+        }
+        __syncthreads();
+        auction_resolve_body(p, N, K, jpw, expect);
+    }
+}
+
+// Between the local sample collection and the window placement: every rank's samples are in place.
+__global__ void auction_peer_barrier_kernel(AuctionPtrs p, PeerCtx peers, int kind, int seq) {
+    if (p.st->mode != MODE_HIST || !p.st->need_sample) return;
+    if (!peer_barrier(peers, kind, seq) && threadIdx.x == 0) { p.st->error = 1; p.st->mode = MODE_DONE; p.st->done = 1; }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1435,14 +1563,14 @@ __device__ __forceinline__ void sample_select_bin(const unsigned int* hist, int 
 __global__ void __launch_bounds__(1024, 1)
 auction_sample_kernel(const __half* __restrict__ S, long long ld, long long N, int K, long long jpw, AuctionPtrs p,
                       unsigned short* __restrict__ collect_out, int collect_n,
-                      const unsigned short* __restrict__ ext_keys, int ext_n, int ext_cnt) {
+                      const unsigned short* __restrict__ ext_keys, int ext_n, int ext_cnt, PeerCtx peers, int peer_par) {
     const AuctionState st = *p.st;
     if (st.mode != MODE_HIST || !st.need_sample) return;
     __shared__ unsigned short keys[AUC_SAMPLE];
     const int w = blockIdx.x, tid = threadIdx.x;
     long long ns = N < AUC_SAMPLE ? N : AUC_SAMPLE;
     if (collect_out) ns = collect_n < ns ? collect_n : ns;
-    if (ext_keys) ns = ext_n;
+    if (ext_keys || peers.world > 0) ns = ext_n;
     const __half eps = bits2h(st.eps_bits);
     {
         constexpr int PER = AUC_SAMPLE / 1024;
@@ -1456,8 +1584,13 @@ auction_sample_kernel(const __half* __restrict__ S, long long ld, long long N, i
             k_r[q] = 0;                                                        // padding sorts last
             c_r[q] = s_r[q] = __ushort_as_half(0);
             o_r[q] = -1;
-            if (ext_keys) {
-                if (i < ns) k_r[q] = ext_keys[((size_t)(i / ext_cnt) * K + w) * ext_cnt + (i % ext_cnt)];   // [part][K][ext_cnt]
+            if (ext_keys || peers.world > 0) {
+                if (i < ns) {
+                    if (peers.world > 0)      // part r = rank r's sample block, read through its peer mapping
+                        k_r[q] = __ldcv(peer_sample(peers, i / ext_cnt, K, peer_par) + (size_t)w * ext_cnt + (i % ext_cnt));
+                    else
+                        k_r[q] = ext_keys[((size_t)(i / ext_cnt) * K + w) * ext_cnt + (i % ext_cnt)];   // [part][K][ext_cnt]
+                }
             } else if (i < ns) {
                 // 16 consecutive jobs = one 32-byte sector of the row; chunks evenly strided over the jobs
                 long long col = cstride * (i >> 4) + (i & 15);
@@ -1471,7 +1604,7 @@ auction_sample_kernel(const __half* __restrict__ S, long long ld, long long N, i
         for (int q = 0; q < PER; ++q) {
             const int i = tid + q * 1024;
             unsigned short key = k_r[q];
-            if (!ext_keys && i < ns) {
+            if (!ext_keys && peers.world == 0 && i < ns) {
                 __half c = c_r[q];
                 if (st.ff_pending > 0 && o_r[q] >= 0)
                     for (int r = 0; r < st.ff_pending; ++r) c = __hadd(c, eps);
@@ -1638,7 +1771,7 @@ auction_tieprefix_kernel(AuctionPtrs p, int K, int G) {
         cnt[tid] += v;
         __syncthreads();
     }
-    if (tid < G) p.tieprefix[(size_t)tid * K + w] = cnt[tid] - c;
+    if (tid < G) p.tieprefix[(size_t)tid * K + w] = cnt[tid] - c + p.rank_off[w];
     if (tid == AUC_MAX_CTAS - 1) p.tie_total[w] = cnt[AUC_MAX_CTAS - 1];
 }
 
@@ -1701,7 +1834,7 @@ static int auction_launch(const AuctionArgs& a, const void* scores_t, int64_t ld
     }
     const int spc = auction_spc(n, k);
     if (which & 1)
-        auction_sample_kernel<<<k, 1024, 0, stream>>>((const __half*)scores_t, ld, n, k, n_global / k, a.p, nullptr, 0, nullptr, 0, 1);
+        auction_sample_kernel<<<k, 1024, 0, stream>>>((const __half*)scores_t, ld, n, k, n_global / k, a.p, nullptr, 0, nullptr, 0, 1, PeerCtx{}, 0);
     if (which & 2) {
         static size_t hs_set = 0;
         const size_t hs = auction_hist_smem(k);
@@ -1804,7 +1937,7 @@ int rqk_auction_sample_collect(const void* scores_t, int64_t ld, int64_t n, int3
     if (rc) return rc;
     if (!scores_t || !out || count < 1 || count > AUC_SAMPLE) return fail(RQK_ERR_ARG, "rqk_auction_sample_collect: bad argument%s");
     auction_sample_kernel<<<k, 1024, 0, (cudaStream_t)stream_>>>((const __half*)scores_t, ld, n, k, n_global / k, a.p,
-                                                                  (unsigned short*)out, count, nullptr, 0, 1);
+                                                                  (unsigned short*)out, count, nullptr, 0, 1, PeerCtx{}, 0);
     RQK_LAUNCH_OK();
     return 0;
 }
@@ -1820,7 +1953,7 @@ int rqk_auction_sample_window(int64_t n, int64_t ld, int32_t k, int64_t n_global
     if (!keys || count < 1 || parts < 1 || (int64_t)count * parts > AUC_SAMPLE)
         return fail(RQK_ERR_ARG, "rqk_auction_sample_window: bad argument%s");
     auction_sample_kernel<<<k, 1024, 0, (cudaStream_t)stream_>>>(nullptr, ld, n_global, k, n_global / k, a.p, nullptr, 0,
-                                                                  (const unsigned short*)keys, count * parts, count);
+                                                                  (const unsigned short*)keys, count * parts, count, PeerCtx{}, 0);
     RQK_LAUNCH_OK();
     return 0;
 }
@@ -1838,6 +1971,63 @@ int rqk_auction_resolve(int64_t n, int64_t ld, int32_t k, int64_t n_global, int3
     if (expect < -1 || expect > 1) return fail(RQK_ERR_ARG, "rqk_auction_resolve: expect must be -1, 0 or 1%s");
     auction_resolve_kernel<<<1, 1024, 0, stream>>>(a.p, n_global, k, n_global / k, expect);
     auction_tieprefix_kernel<<<k, AUC_MAX_CTAS, 0, stream>>>(a.p, k, a.G);
+    RQK_LAUNCH_OK();
+    return 0;
+}
+
+// ---- peer-memory sharding: the exchange is inside the kernels ----
+// peers: HOST array of `world` device pointers, peers[r] = rank r's exchange block (rqk_auction_peer_bytes(k_max)
+// bytes of symmetric memory, zeroed once before first use) as mapped into THIS process; seq: a number that every
+// rank increases by one per call of either function (flags are never reset).
+size_t rqk_auction_peer_bytes(int32_t k) { return rqk::peer_bytes(k); }
+
+static int peer_ctx(const void* const* peers, int32_t world, int32_t rank, rqk::PeerCtx* c, const char* who) {
+    using namespace rqk;
+    if (!peers || world < 1 || world > PEER_MAX || rank < 0 || rank >= world)
+        return fail(RQK_ERR_ARG, "%s: bad peer arguments (world 1..8)", who);
+    for (int r = 0; r < PEER_MAX; ++r) c->buf[r] = r < world ? (unsigned char*)peers[r] : nullptr;
+    for (int r = 0; r < world; ++r)
+        if (!c->buf[r]) return fail(RQK_ERR_ARG, "%s: null peer pointer", who);
+    c->world = world;
+    c->rank = rank;
+    return 0;
+}
+
+// Window sampling of a sharded job: local samples into the own exchange block, flag barrier, windows from the union.
+int rqk_auction_peer_sample(const void* scores_t, int64_t ld, int64_t n, int32_t k, int64_t n_global, int32_t count,
+                            const void* const* peers, int32_t world, int32_t rank, int32_t seq, void* workspace,
+                            size_t workspace_bytes, void* stream_) {
+    using namespace rqk;
+    AuctionArgs a;
+    int rc = auction_prepare(n, ld, k, workspace, workspace_bytes, &a, "rqk_auction_peer_sample");
+    if (rc) return rc;
+    PeerCtx c;
+    if ((rc = peer_ctx(peers, world, rank, &c, "rqk_auction_peer_sample"))) return rc;
+    if (!scores_t || count < 1 || (int64_t)count * world > AUC_SAMPLE) return fail(RQK_ERR_ARG, "rqk_auction_peer_sample: bad argument%s");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    unsigned short* mine = reinterpret_cast<unsigned short*>(c.buf[rank] + peer_sample_off(k)) + (size_t)(seq & 1) * k * AUC_SAMPLE_MAX;
+    auction_sample_kernel<<<k, 1024, 0, stream>>>((const __half*)scores_t, ld, n, k, n_global / k, a.p, mine, count, nullptr, 0, 1,
+                                                  PeerCtx{}, 0);
+    auction_peer_barrier_kernel<<<1, 32, 0, stream>>>(a.p, c, 0, seq);
+    auction_sample_kernel<<<k, 1024, 0, stream>>>(nullptr, ld, n_global, k, n_global / k, a.p, nullptr, 0, nullptr, count * world, count,
+                                                  c, seq & 1);
+    RQK_LAUNCH_OK();
+    return 0;
+}
+
+// Resolve step of a sharded job with the rank exchange inside (expect: 0 after a HIST pass, 1 after a BID pass).
+int rqk_auction_peer_resolve(int64_t n, int64_t ld, int32_t k, int64_t n_global, int32_t expect, const void* const* peers,
+                             int32_t world, int32_t rank, int32_t seq, void* workspace, size_t workspace_bytes, void* stream_) {
+    using namespace rqk;
+    AuctionArgs a;
+    int rc = auction_prepare(n, ld, k, workspace, workspace_bytes, &a, "rqk_auction_peer_resolve");
+    if (rc) return rc;
+    PeerCtx c;
+    if ((rc = peer_ctx(peers, world, rank, &c, "rqk_auction_peer_resolve"))) return rc;
+    if (expect != 0 && expect != 1) return fail(RQK_ERR_ARG, "rqk_auction_peer_resolve: expect must be 0 or 1%s");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    auction_resolve_peer_kernel<<<1, 1024, 0, stream>>>(a.p, n_global, k, n_global / k, expect, c, seq);
+    if (expect == 0) auction_tieprefix_kernel<<<k, AUC_MAX_CTAS, 0, stream>>>(a.p, k, a.G);
     RQK_LAUNCH_OK();
     return 0;
 }
@@ -1869,6 +2059,8 @@ int rqk_auction_poll(int64_t n, int64_t ld, int32_t k, void* workspace, size_t w
     cudaStream_t stream = (cudaStream_t)stream_;
     RQK_CUDA_OK(cudaMemcpyAsync(&host, a.p.st, sizeof(host), cudaMemcpyDeviceToHost, stream));
     RQK_CUDA_OK(cudaStreamSynchronize(stream));
+    if (host.error)
+        return fail(RQK_ERR_INTERNAL, "auction: device-side error %s%lld (1 = a peer rank did not arrive within 4 s)", "", (long long)host.error);
     info->done = host.done;
     info->rounds = host.rounds;
     info->passes = host.passes;

@@ -47,6 +47,40 @@ class ShardGroup:
         self.world = dist.get_world_size(group) if self.active else 1
         self.rank = dist.get_rank(group) if self.active else 0
         self.nccl = self.active and dist.get_backend(group) == "nccl"
+        self._peer = None
+        self._seq = 0
+
+    def next_seq(self) -> int:
+        self._seq += 1
+        return self._seq
+
+    def peer_block(self, dev: torch.device):
+        """This rank's exchange block in symmetric memory, mapped into every peer (NVLink P2P), for the auction's
+        in-kernel exchange (csrc/auction.cu).  None if unavailable on ANY rank (then NCCL carries the exchange) or
+        switched off with RQK_NO_PEER=1."""
+        if self._peer is None:
+            import os
+            ok, err = 0, ""
+            if self.nccl and self.world <= 8 and os.environ.get("RQK_NO_PEER", "0") != "1":
+                try:
+                    import torch.distributed._symmetric_memory as symm
+                    nbytes = int(lib().rqk_auction_peer_bytes(256))
+                    t = symm.empty(nbytes, dtype=torch.uint8, device=dev)
+                    t.zero_()
+                    h = symm.rendezvous(t, group=self.group if self.group is not None else self.dist.group.WORLD)
+                    ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in h.buffer_ptrs])
+                    self._peer = (t, h, ptrs)
+                    ok = 1
+                except Exception as e:          # no P2P mapping between these devices, or an older torch
+                    err = repr(e)
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            if self.active:
+                self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN, group=self.group)   # also orders the zero-fill
+            torch.cuda.synchronize(dev)
+            if int(flag.item()) != 1:
+                self._peer = False
+                self.peer_error = err
+        return self._peer or None
 
     def all_reduce(self, t: torch.Tensor, op: str = "sum"):
         if self.active:
@@ -77,6 +111,7 @@ def no_shard() -> ShardGroup:
     if _NO_SHARD is None:
         g = ShardGroup.__new__(ShardGroup)
         g.dist, g.group, g.active, g.world, g.rank, g.nccl = None, None, False, 1, 0, False
+        g._peer, g._seq = False, 0
         _NO_SHARD = g
     return _NO_SHARD
 
@@ -201,6 +236,25 @@ def auction(scores_t: torch.Tensor, n: int, minmax: torch.Tensor,
     sess.init(mm)
     batch = 3
     info = None
+    peer = shard.peer_block(dev)
+    if peer is not None:
+        # Exchange through peer memory: the sums over ranks happen inside the sampling / resolve kernels
+        # (flag barrier + direct reads of the peers' exchange blocks over NVLink); no collective call per round.
+        ptrs = peer[2]
+        count = max(4096 // shard.world, 1)
+        for _ in range(0, 5000, batch):
+            for _q in range(batch):
+                sess.peer_sample(count, ptrs, shard.world, shard.rank, shard.next_seq())
+                sess.do_pass(2)
+                sess.peer_resolve(0, ptrs, shard.world, shard.rank, shard.next_seq())
+                sess.do_pass(4)
+                sess.peer_resolve(1, ptrs, shard.world, shard.rank, shard.next_seq())
+            info = sess.poll()
+            if info.done:
+                break
+        if info is None or not info.done:
+            raise _lib.RqkError("sharded auction did not terminate")
+        return sess.finalize(), _info_to_stats(info)
     tail = sess.reduce_block[-2:]                                     # jobs with a bidder, frozen-state violations
     for _ in range(0, 5000, batch):
         for _q in range(batch):
@@ -273,6 +327,14 @@ class AuctionSession:
         parts, _, count = self._keys.shape
         check(self.L.rqk_auction_sample_window(self.n, self.ld, self.k, self.n_global, _ptr(self._keys), int(count),
                                                int(parts), *self._args(), _stream(self.dev)))
+
+    def peer_sample(self, count: int, ptrs, world: int, rank: int, seq: int):
+        check(self.L.rqk_auction_peer_sample(_ptr(self.s), self.ld, self.n, self.k, self.n_global, int(count),
+                                             ptrs, world, rank, seq, *self._args(), _stream(self.dev)))
+
+    def peer_resolve(self, expect: int, ptrs, world: int, rank: int, seq: int):
+        check(self.L.rqk_auction_peer_resolve(self.n, self.ld, self.k, self.n_global, expect, ptrs, world, rank, seq,
+                                              *self._args(), _stream(self.dev)))
 
     def resolve(self, expect: int = -1):
         """expect: -1, or 0 / 1 = act only if a HIST / BID pass has just run."""

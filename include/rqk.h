@@ -102,6 +102,16 @@ int rqk_auction_resolve(int64_t n, int64_t ld, int32_t k, int64_t n_global, int3
                         size_t workspace_bytes, void* stream);   /* expect: -1 any, 0 after a HIST pass, 1 after a BID pass */
 int rqk_auction_tie_offset(int64_t n, int64_t ld, int32_t k, const int32_t* totals /*[world][k]*/, int32_t rank,
                            void* workspace, size_t workspace_bytes, void* stream);
+/* Jobs sharded over GPUs, exchange through peer memory instead of NCCL.  peers: HOST array
+ * of `world` (<= 8) device pointers, peers[r] = rank r's exchange block of rqk_auction_peer_bytes(k_max) bytes of
+ * symmetric memory (zeroed once) as mapped into this process; seq: increased by one per call by every rank. */
+size_t rqk_auction_peer_bytes(int32_t k);
+int rqk_auction_peer_sample(const void* scores_t, int64_t ld, int64_t n, int32_t k, int64_t n_global, int32_t count,
+                            const void* const* peers, int32_t world, int32_t rank, int32_t seq, void* workspace,
+                            size_t workspace_bytes, void* stream);
+int rqk_auction_peer_resolve(int64_t n, int64_t ld, int32_t k, int64_t n_global, int32_t expect,
+                             const void* const* peers, int32_t world, int32_t rank, int32_t seq, void* workspace,
+                             size_t workspace_bytes, void* stream);
 int rqk_auction_poll(int64_t n, int64_t ld, int32_t k, void* workspace, size_t workspace_bytes,
                      rqk_auction_info* info /*HOST*/, void* stream);   /* synchronises */
 int rqk_auction_finalize(int64_t n, int64_t ld, int32_t k, void* workspace, size_t workspace_bytes, int32_t* assign,

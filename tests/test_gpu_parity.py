@@ -267,6 +267,37 @@ def test_sharded_auction_protocol_single_gpu_emulation(dev, engine, n, k, split,
     assert infos[0].rounds == ref.rounds
 
 
+@pytest.mark.parametrize("n,k", [(4100, 16), (20010, 128), (12900, 256)])
+def test_peer_exchange_protocol_single_rank(dev, engine, n, k, bid_path):
+    """The peer-memory form of the sharded protocol (exchange inside the sampling / resolve kernels) with a world of
+    one rank: its own exchange block is the only peer.  (Two ranks cannot be emulated on one GPU: their kernels
+    would wait for each other on one stream; tools/dist_check.py runs the real thing on 2 GPUs.)"""
+    import ctypes
+    rng = np.random.default_rng(n)
+    x = O.synth_mix(n, 64, seed=n, modes=max(8, k))
+    c = x[rng.choice(n, k, replace=False)]
+    s = O.score_matrix_half_t(O.pairwise_distance_full(x, c, 100000))
+    ref = O.auction_lap_half_t(s)
+    st = _scores_to_device(s, dev, engine)
+    block = torch.zeros(int(engine.lib().rqk_auction_peer_bytes(256)), dtype=torch.uint8, device=dev)
+    ptrs = (ctypes.c_void_p * 1)(block.data_ptr())
+    sess = engine.AuctionSession(st, n, n)
+    sess.init(_mm(st, n))
+    seq, info = 0, None
+    for _ in range(1500):
+        sess.peer_sample(4096, ptrs, 1, 0, seq + 1)
+        sess.do_pass(2)
+        sess.peer_resolve(0, ptrs, 1, 0, seq + 2)
+        sess.do_pass(4)
+        sess.peer_resolve(1, ptrs, 1, 0, seq + 3)
+        seq += 3
+        info = sess.poll()
+        if info.done:
+            break
+    assert info.done and info.rounds == ref.rounds
+    assert np.array_equal(sess.finalize().cpu().numpy().astype(np.int64), ref.assignment)
+
+
 # ------------------------------------------------------------------------------------------------
 # centroid update, residual
 # ------------------------------------------------------------------------------------------------
