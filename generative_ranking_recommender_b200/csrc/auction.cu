@@ -530,10 +530,24 @@ auction_resolve_peer_kernel(AuctionPtrs p, long long N, int K, long long jpw, in
         unsigned int* mine = peer_hist(peers, peers.rank, K, par);
         for (int i = tid; i < RB; i += NT) mine[i] = p.hist_g[i];
         if (!peer_barrier(peers, 1, seq)) { if (tid == 0) { p.st->error = 1; p.st->mode = MODE_DONE; p.st->done = 1; } return; }
-        for (int r = 0; r < peers.world; ++r) {
-            if (r == peers.rank) continue;
-            const unsigned int* theirs = peer_hist(peers, r, K, par);
-            for (int i = tid; i < RB; i += NT) p.hist_g[i] += __ldcv(theirs + i);
+        // a peer load costs 2-3 us of NVLink latency: keep 4 words x (world - 1) peers in flight per thread
+        for (int i0 = tid; i0 < RB; i0 += 4 * NT) {
+            unsigned int acc[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int r = 0; r < PEER_MAX; ++r) {
+                if (r >= peers.world || r == peers.rank) continue;
+                const unsigned int* theirs = peer_hist(peers, r, K, par);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * NT;
+                    if (i < RB) acc[u] += __ldcv(theirs + i);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * NT;
+                if (i < RB) p.hist_g[i] += acc[u];
+            }
         }
         __syncthreads();
         auction_resolve_body(p, N, K, jpw, expect);
@@ -2013,6 +2027,31 @@ int rqk_auction_peer_sample(const void* scores_t, int64_t ld, int64_t n, int32_t
                                                   c, seq & 1);
     RQK_LAUNCH_OK();
     return 0;
+}
+
+int rqk_auction_peer_resolve(int64_t n, int64_t ld, int32_t k, int64_t n_global, int32_t expect, const void* const* peers,
+                             int32_t world, int32_t rank, int32_t seq, void* workspace, size_t workspace_bytes, void* stream_);
+
+// One whole ROUND of a sharded job in one call (nine launches): local samples -> flag barrier -> windows from the
+// union; HIST pass; 1-CTA kernel that sums the peers' histograms, resolves and derives the rank-major tie offsets;
+// tie prefix; bidding round; 1-CTA kernel that sums the peers' counters and advances the state.  Uses sequence
+// numbers seq0+1 .. seq0+3 (the caller advances its counter by 3).  (Running the exchange in the last CTA of the
+// pass kernels instead, as the single-GPU driver does with its resolve step, measured SLOWER on 2 x B200: the
+// exchange is a chain of NVLink round trips, and a 1024-thread kernel of its own keeps more of them in flight.)
+int rqk_auction_peer_round(const void* scores_t, int64_t ld, int64_t n, int32_t k, int64_t n_global, int32_t count,
+                           const void* const* peers, int32_t world, int32_t rank, int32_t seq0, void* workspace,
+                           size_t workspace_bytes, void* stream_) {
+    using namespace rqk;
+    int rc = rqk_auction_peer_sample(scores_t, ld, n, k, n_global, count, peers, world, rank, seq0 + 1, workspace,
+                                     workspace_bytes, stream_);
+    if (rc) return rc;
+    AuctionArgs a;
+    if ((rc = auction_prepare(n, ld, k, workspace, workspace_bytes, &a, "rqk_auction_peer_round"))) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if ((rc = auction_launch(a, scores_t, ld, n, k, n_global, 2, 0, stream))) return rc;
+    if ((rc = rqk_auction_peer_resolve(n, ld, k, n_global, 0, peers, world, rank, seq0 + 2, workspace, workspace_bytes, stream_))) return rc;
+    if ((rc = auction_launch(a, scores_t, ld, n, k, n_global, 4, 0, stream))) return rc;
+    return rqk_auction_peer_resolve(n, ld, k, n_global, 1, peers, world, rank, seq0 + 3, workspace, workspace_bytes, stream_);
 }
 
 // Resolve step of a sharded job with the rank exchange inside (expect: 0 after a HIST pass, 1 after a BID pass).

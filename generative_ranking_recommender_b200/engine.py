@@ -50,9 +50,11 @@ class ShardGroup:
         self._peer = None
         self._seq = 0
 
-    def next_seq(self) -> int:
-        self._seq += 1
-        return self._seq
+    def take_seq(self, count: int) -> int:
+        """Reserves `count` exchange sequence numbers; returns the number before the first of them."""
+        s = self._seq
+        self._seq += count
+        return s
 
     def peer_block(self, dev: torch.device):
         """This rank's exchange block in symmetric memory, mapped into every peer (NVLink P2P), for the auction's
@@ -104,6 +106,7 @@ class ShardGroup:
 
 
 _NO_SHARD = None
+_PEER_STEPS = __import__("os").environ.get("RQK_PEER_MODE", "round") == "steps"
 
 
 def no_shard() -> ShardGroup:
@@ -244,11 +247,15 @@ def auction(scores_t: torch.Tensor, n: int, minmax: torch.Tensor,
         count = max(4096 // shard.world, 1)
         for _ in range(0, 5000, batch):
             for _q in range(batch):
-                sess.peer_sample(count, ptrs, shard.world, shard.rank, shard.next_seq())
-                sess.do_pass(2)
-                sess.peer_resolve(0, ptrs, shard.world, shard.rank, shard.next_seq())
-                sess.do_pass(4)
-                sess.peer_resolve(1, ptrs, shard.world, shard.rank, shard.next_seq())
+                if _PEER_STEPS:          # the exchange + resolve as their own 1-CTA kernels (debugging / timing)
+                    s0 = shard.take_seq(3)
+                    sess.peer_sample(count, ptrs, shard.world, shard.rank, s0 + 1)
+                    sess.do_pass(2)
+                    sess.peer_resolve(0, ptrs, shard.world, shard.rank, s0 + 2)
+                    sess.do_pass(4)
+                    sess.peer_resolve(1, ptrs, shard.world, shard.rank, s0 + 3)
+                else:
+                    sess.peer_round(count, ptrs, shard.world, shard.rank, shard.take_seq(3))
             info = sess.poll()
             if info.done:
                 break
@@ -331,6 +338,10 @@ class AuctionSession:
     def peer_sample(self, count: int, ptrs, world: int, rank: int, seq: int):
         check(self.L.rqk_auction_peer_sample(_ptr(self.s), self.ld, self.n, self.k, self.n_global, int(count),
                                              ptrs, world, rank, seq, *self._args(), _stream(self.dev)))
+
+    def peer_round(self, count: int, ptrs, world: int, rank: int, seq0: int):
+        check(self.L.rqk_auction_peer_round(_ptr(self.s), self.ld, self.n, self.k, self.n_global, int(count), ptrs,
+                                            world, rank, seq0, *self._args(), _stream(self.dev)))
 
     def peer_resolve(self, expect: int, ptrs, world: int, rank: int, seq: int):
         check(self.L.rqk_auction_peer_resolve(self.n, self.ld, self.k, self.n_global, expect, ptrs, world, rank, seq,

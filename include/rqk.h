@@ -109,6 +109,9 @@ size_t rqk_auction_peer_bytes(int32_t k);
 int rqk_auction_peer_sample(const void* scores_t, int64_t ld, int64_t n, int32_t k, int64_t n_global, int32_t count,
                             const void* const* peers, int32_t world, int32_t rank, int32_t seq, void* workspace,
                             size_t workspace_bytes, void* stream);
+int rqk_auction_peer_round(const void* scores_t, int64_t ld, int64_t n, int32_t k, int64_t n_global, int32_t count,
+                           const void* const* peers, int32_t world, int32_t rank, int32_t seq0, void* workspace,
+                           size_t workspace_bytes, void* stream);   /* a whole round (9 launches); uses seq0+1 .. seq0+3 */
 int rqk_auction_peer_resolve(int64_t n, int64_t ld, int32_t k, int64_t n_global, int32_t expect,
                              const void* const* peers, int32_t world, int32_t rank, int32_t seq, void* workspace,
                              size_t workspace_bytes, void* stream);
