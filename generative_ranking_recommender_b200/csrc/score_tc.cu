@@ -30,8 +30,9 @@ namespace rqk {
 
 constexpr int TC_BM = 128;           // rows per tile (UMMA M)
 constexpr int TC_BK = 32;            // fp32 per k-block = one 128-byte swizzle row
-constexpr int TC_THREADS = 320;      // 10 warps
-constexpr int TC_EPI_WARP0 = 0, TC_XF_WARP0 = 4, TC_TMA_WARP = 8, TC_MMA_WARP = 9;
+constexpr int TC_THREADS = 352;      // 11 warps
+constexpr int TC_EPI_WARP0 = 0, TC_XF_WARP0 = 4, TC_TMA_WARP = 8, TC_MMA_WARP = 9, TC_XLOAD_WARP = 10;
+constexpr int TC_MAX_RAW = 8;        // raw X blocks in flight ahead of the operand stages
 
 // ---------------- PTX wrappers ----------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -91,10 +92,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// fp32 -> tf32, round to nearest with ties away from zero (what cvt.rna.tf32.f32 computes), done on the integer
+// pipe: add half a tf32 ulp to the magnitude bits and clear the 13 low mantissa bits.  The conversion instruction
+// runs at a fraction of the integer rate, and the transform warps execute two of them per element of X.
 __device__ __forceinline__ float to_tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
 // K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart
@@ -120,6 +122,7 @@ struct ScoreTcParams {
     int dim, K, KC;          // KC = K rounded up to 16 (UMMA N)
     int tmem_cols;           // columns per accumulator stage (power of two >= 32, >= KC)
     int stages;
+    int raw;                 // depth of the raw X ring
     const float* c2;         // [K] |c|^2
     ScoreOut o;
     int debug;               // timing attribution only (RQK_SCORE_DEBUG): 1 = skip epilogue math, 2 = hi.hi MMA only, 4 = no transform
@@ -132,7 +135,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     // SWIZZLE_128B tiles need 1024-byte alignment; do not rely on the attribute alone
     unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int KC = P.KC, stages = P.stages;
+    const int KC = P.KC, stages = P.stages, nraw = P.raw;
     const int kblocks = P.dim / TC_BK;
     const long long ntiles = (P.n + TC_BM - 1) / TC_BM;
 
@@ -140,14 +143,20 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const uint32_t a_bytes = TC_BM * TC_BK * 4;           // 16384
     const uint32_t b_bytes = (uint32_t)KC * TC_BK * 4;    // KC*128, multiple of 2048
     const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
-    unsigned char* tail = smem + (size_t)stages * stage_bytes;
+    // raw X ring: the X stream from HBM runs up to `nraw` k-blocks ahead of the operand stages, so that the HBM
+    // latency is covered by bytes in flight instead of by stage occupancy (a stage is held from its centroid
+    // load until its MMAs retire)
+    unsigned char* raw0 = smem + (size_t)stages * stage_bytes;
+    unsigned char* tail = raw0 + (size_t)nraw * a_bytes;
     uint64_t* full_bar = (uint64_t*)tail;          // [stages]
     uint64_t* xf_bar = full_bar + 8;               // [stages]
     uint64_t* empty_bar = xf_bar + 8;              // [stages]
     uint64_t* tmem_full = empty_bar + 8;           // [2]
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
     uint64_t* x2_full = tmem_empty + 2;            // [2]
-    uint32_t* tmem_base_slot = (uint32_t*)(x2_full + 2);
+    uint64_t* raw_full = x2_full + 2;              // [TC_MAX_RAW]
+    uint64_t* raw_empty = raw_full + TC_MAX_RAW;   // [TC_MAX_RAW]
+    uint32_t* tmem_base_slot = (uint32_t*)(raw_empty + TC_MAX_RAW);
     float* x2s = (float*)(tmem_base_slot + 4);     // [2][128]
     float* c2s = x2s + 2 * TC_BM;                  // [KC]
     int* cnt_s = (int*)(c2s + 256);                // [256]
@@ -164,6 +173,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             mbar_init(&full_bar[s], 1);
             mbar_init(&xf_bar[s], 128);
             mbar_init(&empty_bar[s], 1);
+        }
+        for (int i = 0; i < nraw; ++i) {
+            mbar_init(&raw_full[i], 1);
+            mbar_init(&raw_empty[i], 128);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
@@ -182,17 +195,29 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
 
-    if (warp == TC_TMA_WARP) {
-        // ===================== TMA producer =====================
+    if (warp == TC_XLOAD_WARP) {
+        // ===================== TMA producer: X blocks into the raw ring =====================
         if (lane == 0) {
-            int s = 0; uint32_t ph = 0;
+            int rs = 0; uint32_t rph = 0;
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int row0 = (int)(tile * TC_BM);
                 for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&raw_empty[rs], rph ^ 1);
+                    mbar_expect_tx(&raw_full[rs], a_bytes);
+                    tma_load_2d(raw0 + (size_t)rs * a_bytes, &map_x, &raw_full[rs], kb * TC_BK, row0);
+                    if (++rs == nraw) { rs = 0; rph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == TC_TMA_WARP) {
+        // ===================== TMA producer: centroid hi / lo blocks into the operand stages =====================
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     unsigned char* st = smem + (size_t)s * stage_bytes;
-                    mbar_expect_tx(&full_bar[s], a_bytes + 2 * b_bytes);
-                    tma_load_2d(st, &map_x, &full_bar[s], kb * TC_BK, row0);
+                    mbar_expect_tx(&full_bar[s], 2 * b_bytes);
                     tma_load_2d(st + 2 * a_bytes, &map_chi, &full_bar[s], kb * TC_BK, 0);
                     tma_load_2d(st + 2 * a_bytes + b_bytes, &map_clo, &full_bar[s], kb * TC_BK, 0);
                     if (++s == stages) { s = 0; ph ^= 1; }
@@ -240,18 +265,23 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         // ===================== transform: hi/lo split + row norms =====================
         const int r = (warp - TC_XF_WARP0) * 32 + lane;     // row of the tile owned by this thread
         int s = 0; uint32_t ph = 0;
+        int rs = 0; uint32_t rph = 0;
         int a = 0; uint32_t aph = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             float nrm = 0.f;
             for (int kb = 0; kb < kblocks; ++kb) {
-                mbar_wait(&full_bar[s], ph);
+                mbar_wait(&raw_full[rs], rph);               // the raw X block has landed
+                mbar_wait(&empty_bar[s], ph ^ 1);            // the operand stage is free (its last MMAs retired)
                 if (P.debug & 4) {
                     fence_proxy_async();
                     mbar_arrive(&xf_bar[s]);
+                    mbar_arrive(&raw_empty[rs]);
                     if (++s == stages) { s = 0; ph ^= 1; }
+                    if (++rs == nraw) { rs = 0; rph ^= 1; }
                     continue;
                 }
                 unsigned char* st = smem + (size_t)s * stage_bytes;
+                const float4* raw = reinterpret_cast<const float4*>(raw0 + (size_t)rs * a_bytes + (size_t)r * 128);
                 float4* hi = reinterpret_cast<float4*>(st + (size_t)r * 128);
                 float4* lo = reinterpret_cast<float4*>(st + a_bytes + (size_t)r * 128);
 #pragma unroll
@@ -260,7 +290,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     // is also conflict-free; summing in LOGICAL order keeps a row's norm independent of where
                     // the row lands in a tile, so row-sharded runs reproduce the unsharded scores bit for bit
                     const int ch = c ^ (lane & 7);
-                    float4 v = hi[ch];
+                    float4 v = raw[ch];                       // same swizzled position in the raw block and in the operand tile
                     nrm = fmaf(v.x, v.x, nrm); nrm = fmaf(v.y, v.y, nrm);
                     nrm = fmaf(v.z, v.z, nrm); nrm = fmaf(v.w, v.w, nrm);
                     float4 h, l;
@@ -272,7 +302,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 }
                 fence_proxy_async();                         // generic-proxy writes -> visible to the UMMA reads
                 mbar_arrive(&xf_bar[s]);
+                mbar_arrive(&raw_empty[rs]);                 // the raw slot can be refilled
                 if (++s == stages) { s = 0; ph ^= 1; }
+                if (++rs == nraw) { rs = 0; rph ^= 1; }
             }
             mbar_wait(&tmem_empty[a], aph ^ 1);              // x2s[a] is free once the epilogue two tiles back is done
             x2s[a * TC_BM + r] = nrm;
@@ -460,12 +492,24 @@ int score_pass_tc(const float* x, long long n, int dim, const float* c, int K, f
         P.debug = dbg ? atoi(dbg) : 0;
     }
     const size_t stage_bytes = 2 * (size_t)TC_BM * TC_BK * 4 + 2 * (size_t)KC * TC_BK * 4;
-    const size_t tail = 8 * 8 * 3 + 2 * 8 * 3 + 16 + 2 * TC_BM * 4 + 256 * 4 + 256 * 4 + 64;
-    int stages = (int)((225 * 1024 - tail - 1024) / stage_bytes);
-    if (stages > 6) stages = 6;
-    if (stages < 2) return fail(RQK_ERR_UNSUPPORTED, "score_pass_tc: K=%s%lld does not fit two pipeline stages", "", K);
+    const size_t tail = 8 * 8 * 3 + 2 * 8 * 3 + 2 * 8 * TC_MAX_RAW + 16 + 2 * TC_BM * 4 + 256 * 4 + 256 * 4 + 64;
+    const size_t raw_bytes = (size_t)TC_BM * TC_BK * 4;
+    const long long room = 225 * 1024 - (long long)tail - 1024;
+    // two operand stages (A hi/lo + centroid hi/lo blocks); the rest of shared memory is the raw X ring
+    int stages = 2;
+    if (room < (long long)(stages * stage_bytes + raw_bytes))
+        return fail(RQK_ERR_UNSUPPORTED, "score_pass_tc: K=%s%lld does not fit two pipeline stages", "", K);
+    int raw = (int)((room - (long long)(stages * stage_bytes)) / (long long)raw_bytes);
+    if (raw > TC_MAX_RAW) {                      // small K: spend the surplus on a third operand stage
+        if (room >= (long long)(3 * stage_bytes + 4 * raw_bytes)) {
+            stages = 3;
+            raw = (int)((room - (long long)(stages * stage_bytes)) / (long long)raw_bytes);
+        }
+        if (raw > TC_MAX_RAW) raw = TC_MAX_RAW;
+    }
     P.stages = stages;
-    const size_t smem = (size_t)stages * stage_bytes + tail + 1024;
+    P.raw = raw;
+    const size_t smem = (size_t)stages * stage_bytes + (size_t)raw * raw_bytes + tail + 1024;
 
     centroid_split_kernel<<<K, 128, 0, stream>>>(c, K, dim, chi, clo, c2);
     RQK_LAUNCH_OK();
