@@ -378,6 +378,25 @@ def main():
                 "note": "not a stream over S: reads ~2 % of it as L2-resident lists plus cost/owner of every job; "
                         "timed together with the early-exiting S-scanning fallback kernel"}
 
+    # ---- encode (the KMeans.predict + residual chain train() emits its ids with), rows resident in HBM ----
+    encode = None
+    if rank == 0:
+        try:
+            cs = [km.cluster_centers for km, _ in levels]
+            for _ in range(2):
+                engine.encode(x0, cs, CLUSTERS, [DIM], mode=0)
+            ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ee0.record()
+            for _ in range(3):
+                engine.encode(x0, cs, CLUSTERS, [DIM], mode=0)
+            ee1.record()
+            torch.cuda.synchronize()
+            t_enc = ee0.elapsed_time(ee1) / 3
+            encode = {"value": n / (t_enc / 1e3), "unit": "vectors/s", "rows": n, "ms": t_enc, "gpus": 1,
+                      "what": "3-level ids of resident fp32 rows (rqk_encode, mode 0)"}
+        except Exception as e:      # never lose the bench line over the side metric
+            encode = {"error": repr(e)}
+
     # ---- end to end through the public API: host array in, ids out ----
     e2e = None
     if not args.no_e2e:
@@ -417,7 +436,7 @@ def main():
                 "vs_baseline": None, "dtype": "3xTF32 distance (fp32 accumulate), fp16 auction, fp32 centroids",
                 "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
                 "gpu_launches": gpu_launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
-                "auction": {"passes_per_step": passes, "reference_rounds_per_step": rounds}}
+                "auction": {"passes_per_step": passes, "reference_rounds_per_step": rounds}, "encode": encode}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -16,14 +16,26 @@
 #include "common.cuh"
 
 namespace rqk {
-constexpr long long ENC_CHUNK = 1 << 20;
+// Rows per chunk of the level chain (bounds the workspace: two chunk x dim fp32 buffers).  Measured on B200 at
+// 1 M x 512, [128,128,256] (tools/encode_probe.py): 1 Mi rows 4.09 ms, 151 552 rows 4.44 ms, 37 888 rows (residual
+// L2-resident between levels) 5.46 ms - the chain is bound by its three score passes, not by the residual's HBM
+// traffic, so small L2-sized chunks only add pipeline fill.  RQK_ENC_CHUNK overrides (tuning).
+constexpr long long ENC_CHUNK_DEFAULT = 1 << 20;
+static long long enc_chunk() {
+    static long long v = 0;
+    if (!v) {
+        const char* e = getenv("RQK_ENC_CHUNK");
+        v = (e && atoll(e) >= 128) ? atoll(e) : ENC_CHUNK_DEFAULT;
+    }
+    return v;
+}
 }
 
 extern "C" {
 
 size_t rqk_encode_workspace_bytes(int64_t n, int32_t dim, int32_t kmax) {
     using namespace rqk;
-    long long chunk = n < ENC_CHUNK ? n : ENC_CHUNK;
+    long long chunk = n < enc_chunk() ? n : enc_chunk();
     return 2 * align256((size_t)chunk * dim * 4) + score_workspace_bytes(chunk, kmax, dim) + 256;
 }
 
@@ -43,7 +55,7 @@ int rqk_encode(const float* x, int64_t n, int32_t dim, int32_t levels, const voi
     if (workspace_bytes < rqk_encode_workspace_bytes(n, dim, kmax))
         return fail(RQK_ERR_WORKSPACE, "rqk_encode: workspace %s%lld too small", "", (long long)workspace_bytes);
     if (n == 0) return 0;
-    const long long chunk = n < ENC_CHUNK ? n : ENC_CHUNK;
+    const long long chunk = n < enc_chunk() ? n : enc_chunk();
     char* w = (char*)workspace;
     float* cur = (float*)w; w += align256((size_t)chunk * dim * 4);     // running (unweighted) data
     float* wtd = (float*)w; w += align256((size_t)chunk * dim * 4);     // weighted view when weights != 1

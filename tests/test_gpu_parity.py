@@ -176,6 +176,24 @@ def test_auction_bit_exact_vs_oracle(dev, engine, n, k, dim, bid_path):
         assert (np.bincount(a, minlength=k) == n // k).all()
 
 
+@pytest.mark.parametrize("n,k,grid", [(20010, 128, 2), (30000, 16, 3), (26000, 256, 1), (9000, 8, 1)])
+def test_auction_several_subranges_per_cta(dev, engine, n, k, grid, bid_path, monkeypatch):
+    """Large inputs give every CTA several 4096-job sub-ranges (one survivor-list segment and one bid-list CTA each, tie
+    prefix per segment).  RQK_AUCTION_GRID caps the number of CTAs so that the oracle can check that regime at small n."""
+    monkeypatch.setenv("RQK_AUCTION_GRID", str(grid))
+    rng = np.random.default_rng(n + grid)
+    x = O.synth_mix(n, 64, seed=n, modes=max(8, k))
+    c = x[rng.choice(n, k, replace=False)]
+    d = O.pairwise_distance_full(x, c, 100000)
+    d = np.round(d * 8) / 8 if k == 16 else d                 # k = 16: many exact ties at the thresholds
+    s = O.score_matrix_half_t(d)
+    ref = O.auction_lap_half_t(s)
+    st = _scores_to_device(s, dev, engine)
+    a, stats = engine.auction(st, n, _mm(st, n))
+    assert np.array_equal(a.cpu().numpy().astype(np.int64), ref.assignment)
+    assert stats.rounds == ref.rounds
+
+
 def test_auction_heavy_ties(dev, engine, bid_path):
     """Few distinct fp16 values: the canonical lowest-job-index rule decides almost every round."""
     rng = np.random.default_rng(5)
