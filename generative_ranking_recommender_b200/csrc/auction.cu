@@ -116,8 +116,6 @@ struct AuctionPtrs {
     unsigned int* seg_cnt;    // [G*spc][K]  entries the HIST pass wanted to write (> AUC_SEG_CAP: overflow)
     int* list_ok;             // [1] cleared by a HIST CTA whose segment overflowed
     unsigned int* rank_off;   // [K] ties at the threshold held by lower ranks (peer-memory sharding; else 0)
-    unsigned int* tiepre_seg; // [G*spc][K] ties at the threshold in lower segments (list rounds: one bid-list CTA per segment)
-    int* cta_dumped;          // [G] the CTA's histogram dump is valid (written only when one of its segments overflowed)
     unsigned int* ticket;     // [1] CTAs finished in the running pass kernel (fused resolve)
 };
 
@@ -170,8 +168,6 @@ static inline size_t auction_ws_layout(long long N, long long ld, int K, Auction
     size_t o_sc = take_(nseg * K * 4);
     size_t o_lo = take_(4);
     size_t o_ro = take_((size_t)K * 4);
-    size_t o_tps = take_(nseg * K * 4);
-    size_t o_cd = take_((size_t)G * 4);
     size_t o_tk2 = take_(4);
     if (reduce_off) *reduce_off = o_hist;
     if (tie_total_off) *tie_total_off = o_tt;
@@ -200,8 +196,6 @@ static inline size_t auction_ws_layout(long long N, long long ld, int K, Auction
         p->seg_cnt = (unsigned int*)(base + o_sc);
         p->list_ok = (int*)(base + o_lo);
         p->rank_off = (unsigned int*)(base + o_ro);
-        p->tiepre_seg = (unsigned int*)(base + o_tps);
-        p->cta_dumped = (int*)(base + o_cd);
         p->ticket = (unsigned int*)(base + o_tk2);
     }
     return off;
@@ -1030,8 +1024,6 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
         sm.r_lo2[i] = lob | (lob << 16);
     }
     __syncthreads();
-    __shared__ int s_overflow;
-    if (tid == 0) s_overflow = 0;
     const int any_cold = __syncthreads_or(tid < K && sm.r_base[tid] <= 0);   // cold rows take the unpipelined path
 
     int seg = b * spc;
@@ -1313,19 +1305,15 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
         if (tid < K) {
             const unsigned int c = seg_cnt_s[tid];
             p.seg_cnt[(size_t)seg * K + tid] = c;
-            if (c > AUC_SEG_CAP) { *p.list_ok = 0; s_overflow = 1; }
+            if (c > AUC_SEG_CAP) *p.list_ok = 0;
         }
     }
-    __syncthreads();
 
-    // ---- publish: merge of non-empty bins; the per-CTA dump only if the tie prefix cannot be counted from this
-    // CTA's survivor lists (a segment overflowed) or the list path is switched off ----
-    const bool need_dump = s_overflow != 0 || st.force_scan != 0;
-    if (tid == 0) p.cta_dumped[b] = need_dump ? 1 : 0;
+    // ---- publish: per-CTA dump (for the tie prefix) + merge of non-empty bins ----
     unsigned int* dump = reinterpret_cast<unsigned int*>(p.hist_cta + (size_t)b * K * AUC_W);
     for (int i = tid; i < K * AUC_W / 2; i += AUC_THREADS) {
         unsigned int h = sm.hist[i];
-        if (need_dump) dump[i] = h;
+        dump[i] = h;
         if (h & 0xffffu) atomicAdd(&p.hist_g[2 * i], h & 0xffffu);
         if (h >> 16) atomicAdd(&p.hist_g[2 * i + 1], h >> 16);
     }
@@ -1363,23 +1351,21 @@ auction_bidlist_kernel(const __half* __restrict__ S, long long ld, long long N, 
     const unsigned int eps_bits = st.eps_bits;
     const bool retain = counter >= 1 && counter < 100;      // :86
     const bool fallback = counter > 1000;                    // :88
-    // one CTA per SEGMENT (4096-job sub-range of a HIST CTA's range): blockIdx = b * spc + index of the sub-range
-    const int G = gridDim.x / spc, b = blockIdx.x / spc;
+    const int G = gridDim.x, b = blockIdx.x;
     const long long tiles_total = (N + J - 1) / J;
     const long long c_begin = (tiles_total * b / G) * J;
     long long c_end = (tiles_total * (b + 1) / G) * J;
     if (c_end > N) c_end = N;
-    const int seg = blockIdx.x;
-    const long long sub0 = c_begin + (long long)(blockIdx.x % spc) * AUC_SUB;
 
     for (int i = tid; i < K; i += AUC_THREADS) {
-        tie_seen[i] = p.tiepre_seg[(size_t)seg * K + i];
+        tie_seen[i] = p.tieprefix[(size_t)b * K + i];
         r_tk[i] = p.tkey[i];
         r_take[i] = p.take[i];
     }
     if (tid == 0) { s_nwith = 0; s_nviol = 0; }
 
-    for (long long sub = sub0; sub < c_end && sub == sub0; sub += AUC_SUB) {   // at most once (an unused slot: never)
+    int seg = b * spc;
+    for (long long sub = c_begin; sub < c_end; sub += AUC_SUB, ++seg) {
         const int sublen = (int)((c_end - sub) < AUC_SUB ? (c_end - sub) : AUC_SUB);
         // ---- stage cost / owner; bids that do not depend on S (retain hack :87, fallback :89) ----
         constexpr int PER = AUC_SUB / AUC_THREADS;
@@ -1432,8 +1418,11 @@ auction_bidlist_kernel(const __half* __restrict__ S, long long ld, long long N, 
             ent[1] = pre1;
 #pragma unroll
             for (int c = 2; c < NCH; ++c) {
-                const unsigned int idx = c * 32 + lane;
-                ent[c] = (idx < E) ? __ldcg(L + idx) : 0u;   // key 0 is below every threshold: never a bidder
+                ent[c] = 0u;                                   // key 0 is below every threshold: never a bidder
+                if ((unsigned)(c * 32) < E) {                  // warp-uniform: a segment holds ~60 entries, rarely > 64
+                    const unsigned int idx = c * 32 + lane;
+                    if (idx < E) ent[c] = __ldcg(L + idx);
+                }
             }
             pre0 = 0; pre1 = 0;
             if (r + 1 < nrows) {
@@ -1444,9 +1433,12 @@ auction_bidlist_kernel(const __half* __restrict__ S, long long ld, long long N, 
             }
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
-                const unsigned int idx = c * 32 + lane;
-                tmask[c] = __ballot_sync(0xffffffffu, idx < E && (int)(ent[c] & 0xffffu) == tk);
-                n_ties += __popc(tmask[c]);
+                tmask[c] = 0u;
+                if ((unsigned)(c * 32) < E) {
+                    const unsigned int idx = c * 32 + lane;
+                    tmask[c] = __ballot_sync(0xffffffffu, idx < E && (int)(ent[c] & 0xffffu) == tk);
+                    n_ties += __popc(tmask[c]);
+                }
             }
             const unsigned int seen0 = tie_seen[w];
             const long long quota = r_take[w];
@@ -1471,6 +1463,7 @@ auction_bidlist_kernel(const __half* __restrict__ S, long long ld, long long N, 
             }
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
+                if ((unsigned)(c * 32) >= E) break;
                 const unsigned int idx = c * 32 + lane;
                 if (idx >= E) continue;
                 const int key = (int)(ent[c] & 0xffffu);
@@ -1780,87 +1773,40 @@ auction_sample_kernel(const __half* __restrict__ S, long long ld, long long N, i
     }
 }
 
-// After a resolve that leaves every worker resolved: how many values equal to the threshold precede each unit of
-// the bidding round in job order (the canonical tie rule takes the lowest job indices first).  Grid = K CTAs (one
-// per worker) x 1024 threads.
-//   list rounds   units = segments (4096-job sub-ranges), counts taken from the survivor lists themselves (a warp
-//                 per segment, 32 entries per load), so that every segment gets its own bid-list CTA and the HIST
-//                 kernel does not have to dump its per-CTA histograms;
-//   scan rounds   units = HIST CTAs; a CTA whose segment overflowed (or every CTA when the list path is switched
-//                 off) has dumped its histogram, the others are still counted from their complete lists.
-// Two passes over the worker's units: counts + prefix inside each warp's contiguous range, then the warps' offsets.
+// After a resolve that leaves every worker resolved: per-CTA exclusive prefix of the number of
+// values equal to the threshold (bin tkey-base of the per-CTA dumps), and the window predicted for
+// the values after this round's cost update.  Grid = K CTAs.
 __global__ void __launch_bounds__(AUC_MAX_CTAS, 1)
-auction_tieprefix_kernel(AuctionPtrs p, int K, int G, int spc) {
-    const AuctionState st = *p.st;
-    if (st.mode != MODE_BID) return;
-    const int w = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NWARPS = AUC_MAX_CTAS / 32;
-    __shared__ unsigned int wtot[NWARPS], woff[NWARPS];
+auction_tieprefix_kernel(AuctionPtrs p, int K, int G) {
+    if (p.st->mode != MODE_BID) return;
+    const int w = blockIdx.x, tid = threadIdx.x;
+    __shared__ unsigned int cnt[AUC_MAX_CTAS];
     const int base = p.win_base[w], hbase = p.win_hbase[w];
     const int tk = p.tkey[w];
     const int nlo = p.win_nlo[w];
     const int bin = tk >= hbase ? nlo + tk - hbase : tk - base;   // shift is 0 when resolved
-    // ties of worker w in segment `seg`, counted by one warp from the list (complete iff seg_cnt <= AUC_SEG_CAP)
-    auto seg_ties = [&](int seg) -> unsigned int {
-        unsigned int E = __ldcg(p.seg_cnt + (size_t)seg * K + w);
-        if (E > AUC_SEG_CAP) E = AUC_SEG_CAP;
-        const unsigned int* L = p.seg_list + ((size_t)seg * K + w) * AUC_SEG_CAP;
-        unsigned int c = 0;
-        for (unsigned int i0 = 0; i0 < E; i0 += 32) {
-            const unsigned int i = i0 + lane;
-            const bool hit = i < E && (int)(__ldcg(L + i) & 0xffffu) == tk;
-            c += __popc(__ballot_sync(0xffffffffu, hit));
-        }
-        return c;
-    };
-    const bool by_seg = st.use_list != 0;
-    const int nunits = by_seg ? G * spc : G;
-    unsigned int* out = by_seg ? p.tiepre_seg : p.tieprefix;
-    const int per = (nunits + NWARPS - 1) / NWARPS;
-    const int u0 = warp * per, u1 = (u0 + per < nunits) ? u0 + per : nunits;
-    unsigned int run = 0;
-    for (int u = u0; u < u1; ++u) {
-        unsigned int c = 0;
-        if (by_seg) {
-            c = seg_ties(u);
-        } else if (__ldcg(p.cta_dumped + u)) {
-            c = p.hist_cta[((size_t)u * K + w) * AUC_W + bin];
-        } else {
-            for (int sg = 0; sg < spc; ++sg) c += seg_ties(u * spc + sg);
-        }
-        if (lane == 0) out[(size_t)u * K + w] = run;
-        run += c;
-    }
-    if (lane == 0) wtot[warp] = run;
+    unsigned int c = 0;
+    if (tid < G) c = p.hist_cta[((size_t)tid * K + w) * AUC_W + bin];
+    cnt[tid] = c;
     __syncthreads();
-    if (warp == 0) {
-        const unsigned int v = wtot[lane];
-        unsigned int incl = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned int o = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += o;
-        }
-        woff[lane] = incl - v;
-        if (lane == 31) p.tie_total[w] = incl;
+    for (int d = 1; d < AUC_MAX_CTAS; d <<= 1) {   // Hillis-Steele inclusive scan
+        unsigned int v = (tid >= d) ? cnt[tid - d] : 0;
+        __syncthreads();
+        cnt[tid] += v;
+        __syncthreads();
     }
-    __syncthreads();
-    const unsigned int add = woff[warp] + p.rank_off[w];
-    if (add)
-        for (int u = u0 + lane; u < u1; u += 32) out[(size_t)u * K + w] += add;
+    if (tid < G) p.tieprefix[(size_t)tid * K + w] = cnt[tid] - c + p.rank_off[w];
+    if (tid == AUC_MAX_CTAS - 1) p.tie_total[w] = cnt[AUC_MAX_CTAS - 1];
 }
 
 // sharded jobs: ranks are ordered, so a rank's CTAs come after all ties of lower ranks
-__global__ void auction_tie_offset_kernel(AuctionPtrs p, int K, int G, int spc, const int* __restrict__ totals, int rank) {
+__global__ void auction_tie_offset_kernel(AuctionPtrs p, int K, int G, const int* __restrict__ totals, int rank) {
     if (p.st->mode != MODE_BID) return;
-    const bool by_seg = p.st->use_list != 0;          // the prefix array the coming bidding round reads
-    unsigned int* out = by_seg ? p.tiepre_seg : p.tieprefix;
-    const int nunits = by_seg ? G * spc : G;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nunits * K) {
+    if (i < G * K) {
         unsigned int off = 0;
         for (int r = 0; r < rank; ++r) off += (unsigned int)totals[r * K + i % K];
-        out[i] += off;
+        p.tieprefix[i] += off;
     }
 }
 
@@ -1922,9 +1868,9 @@ static int auction_launch(const AuctionArgs& a, const void* scores_t, int64_t ld
         }
         auction_hist_kernel<<<a.G, AUC_THREADS, hs, stream>>>((const __half*)scores_t, ld, n, k, a.J, spc, a.p, n_global, fused);
     }
-    if (which & 8) auction_tieprefix_kernel<<<k, AUC_MAX_CTAS, 0, stream>>>(a.p, k, a.G, auction_spc(n, k));
+    if (which & 8) auction_tieprefix_kernel<<<k, AUC_MAX_CTAS, 0, stream>>>(a.p, k, a.G);
     if (which & 4) {
-        auction_bidlist_kernel<<<a.G * spc, AUC_THREADS, 0, stream>>>((const __half*)scores_t, ld, n, k, a.J, spc, a.p, n_global, fused);
+        auction_bidlist_kernel<<<a.G, AUC_THREADS, 0, stream>>>((const __half*)scores_t, ld, n, k, a.J, spc, a.p, n_global, fused);
         kern<<<a.G, AUC_THREADS, a.smem, stream>>>((const __half*)scores_t, ld, n, k, n_global / k, a.p, n_global, fused);
     }
     RQK_LAUNCH_OK();
@@ -1980,8 +1926,6 @@ int rqk_auction_init(int64_t n, int64_t ld, int32_t k, const void* minmax_keys, 
     if (!minmax_keys) return fail(RQK_ERR_ARG, "rqk_auction_init: null minmax_keys%s");
     cudaStream_t stream = (cudaStream_t)stream_;
     RQK_CUDA_OK(cudaMemsetAsync(a.p.tieprefix, 0, (size_t)a.G * k * 4, stream));
-    // segment slots a CTA never uses (its range is shorter than spc sub-ranges) must read as empty forever
-    RQK_CUDA_OK(cudaMemsetAsync(a.p.seg_cnt, 0, (size_t)a.G * auction_spc(n, k) * k * 4, stream));
     const char* ns = getenv("RQK_AUCTION_NO_LIST");      // tests: force the S-scanning BID kernel
     auction_init_kernel<<<148, 256, 0, stream>>>(a.p, ld, k, (const unsigned int*)minmax_keys, (ns && ns[0] == '1') ? 1 : 0);
     RQK_LAUNCH_OK();
@@ -2050,7 +1994,7 @@ int rqk_auction_resolve(int64_t n, int64_t ld, int32_t k, int64_t n_global, int3
     cudaStream_t stream = (cudaStream_t)stream_;
     if (expect < -1 || expect > 1) return fail(RQK_ERR_ARG, "rqk_auction_resolve: expect must be -1, 0 or 1%s");
     auction_resolve_kernel<<<1, 1024, 0, stream>>>(a.p, n_global, k, n_global / k, expect);
-    auction_tieprefix_kernel<<<k, AUC_MAX_CTAS, 0, stream>>>(a.p, k, a.G, auction_spc(n, k));
+    auction_tieprefix_kernel<<<k, AUC_MAX_CTAS, 0, stream>>>(a.p, k, a.G);
     RQK_LAUNCH_OK();
     return 0;
 }
@@ -2132,7 +2076,7 @@ int rqk_auction_peer_resolve(int64_t n, int64_t ld, int32_t k, int64_t n_global,
     if (expect != 0 && expect != 1) return fail(RQK_ERR_ARG, "rqk_auction_peer_resolve: expect must be 0 or 1%s");
     cudaStream_t stream = (cudaStream_t)stream_;
     auction_resolve_peer_kernel<<<1, 1024, 0, stream>>>(a.p, n_global, k, n_global / k, expect, c, seq);
-    if (expect == 0) auction_tieprefix_kernel<<<k, AUC_MAX_CTAS, 0, stream>>>(a.p, k, a.G, auction_spc(n, k));
+    if (expect == 0) auction_tieprefix_kernel<<<k, AUC_MAX_CTAS, 0, stream>>>(a.p, k, a.G);
     RQK_LAUNCH_OK();
     return 0;
 }
@@ -2147,8 +2091,7 @@ int rqk_auction_tie_offset(int64_t n, int64_t ld, int32_t k, const int32_t* tota
     if (rc) return rc;
     if (!totals || rank < 0) return fail(RQK_ERR_ARG, "rqk_auction_tie_offset: bad argument%s");
     if (rank == 0) return 0;
-    const int spc = auction_spc(n, k);
-    auction_tie_offset_kernel<<<ceil_div(a.G * spc * k, 256), 256, 0, (cudaStream_t)stream_>>>(a.p, k, a.G, spc, totals, rank);
+    auction_tie_offset_kernel<<<ceil_div(a.G * k, 256), 256, 0, (cudaStream_t)stream_>>>(a.p, k, a.G, totals, rank);
     RQK_LAUNCH_OK();
     return 0;
 }
