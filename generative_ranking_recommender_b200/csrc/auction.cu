@@ -531,7 +531,13 @@ auction_resolve_peer_kernel(AuctionPtrs p, long long N, int K, long long jpw, in
     const int RB = K * AUC_W + 2 * K + 2;
     if (expect == MODE_HIST) {
         unsigned int* mine = peer_hist(peers, peers.rank, K, par);
-        for (int i = tid; i < RB; i += NT) mine[i] = p.hist_g[i];
+        for (int i0 = tid; i0 < RB; i0 += 8 * NT) {            // 8 independent loads in flight per thread
+            unsigned int v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (i0 + u * NT < RB) ? __ldcg(p.hist_g + i0 + u * NT) : 0u;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) if (i0 + u * NT < RB) mine[i0 + u * NT] = v[u];
+        }
         if (!peer_barrier(peers, 1, seq)) { if (tid == 0) { p.st->error = 1; p.st->mode = MODE_DONE; p.st->done = 1; } return; }
         // a peer load costs 2-3 us of NVLink latency: keep 4 words x (world - 1) peers in flight per thread
         for (int i0 = tid; i0 < RB; i0 += 4 * NT) {
@@ -559,8 +565,13 @@ auction_resolve_peer_kernel(AuctionPtrs p, long long N, int K, long long jpw, in
             for (int w = tid; w < K; w += NT) {
                 const int base = p.win_base[w], hbase = p.win_hbase[w], nlo = p.win_nlo[w], tk = p.tkey[w];
                 const int bin = tk >= hbase ? nlo + tk - hbase : tk - base;
+                unsigned int part[PEER_MAX];
+#pragma unroll
+                for (int r = 0; r < PEER_MAX; ++r)                // all lower ranks' loads in flight together
+                    part[r] = (r < peers.rank) ? __ldcv(peer_hist(peers, r, K, par) + (size_t)w * AUC_W + bin) : 0u;
                 unsigned int off = 0;
-                for (int r = 0; r < peers.rank; ++r) off += __ldcv(peer_hist(peers, r, K, par) + (size_t)w * AUC_W + bin);
+#pragma unroll
+                for (int r = 0; r < PEER_MAX; ++r) off += part[r];
                 p.rank_off[w] = off;
             }
         }
@@ -571,15 +582,19 @@ auction_resolve_peer_kernel(AuctionPtrs p, long long N, int K, long long jpw, in
             mine[1] = (int)*p.n_viol;
         }
         if (!peer_barrier(peers, 2, seq)) { if (tid == 0) { p.st->error = 1; p.st->mode = MODE_DONE; p.st->done = 1; } return; }
-        if (tid == 0) {
+        if (tid < 32) {                                        // one lane per rank: the peer loads overlap
             unsigned int a = 0, b = 0;
-            for (int r = 0; r < peers.world; ++r) {
-                const int* t = peer_tail(peers, r, par);
-                a += (unsigned int)__ldcv(t);
-                b += (unsigned int)__ldcv(t + 1);
+            if (tid < peers.world) {
+                const int* t = peer_tail(peers, tid, par);
+                a = (unsigned int)__ldcv(t);
+                b = (unsigned int)__ldcv(t + 1);
             }
-            *p.n_with = a;
-            *p.n_viol = b;
+#pragma unroll
+            for (int d = 16; d; d >>= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, d);
+                b += __shfl_xor_sync(0xffffffffu, b, d);
+            }
+            if (tid == 0) { *p.n_with = a; *p.n_viol = b; }
         }
         __syncthreads();
         auction_resolve_body(p, N, K, jpw, expect);
