@@ -292,12 +292,12 @@ class HierarchicalRQKMeans:
                         "last-layer dual-KMeans + match-matrix strategy (layer_clusters != need_clusters) "
                         "is the next scope row (SURVEY.md 8f), not built yet")
                 else:                                                                   # :464-475
-                    raise NotImplementedError(
-                        "recursive middle-layer strategy (layer_clusters != need_clusters) "
-                        "is the next scope row (SURVEY.md 8f), not built yet")
+                    centers, ids, raw_ids = self._train_middle_layer(current_data, layer)
                 if layer < L - 1:
-                    # :660 / :1088-1128, in place: the residual IS the next level's input (:501-503)
-                    engine.residual_normalise(current_data, ids, centers, self.config.group_dims, out=current_data)
+                    # :660 / :1088-1128 (:898 for a recursive layer: the RAW id picks the centre), in place: the
+                    # residual IS the next level's input (:501-503)
+                    engine.residual_normalise(current_data, ids if n_clusters == need_clusters else raw_ids, centers,
+                                              self.config.group_dims, out=current_data)
                 ids_cpu = ids.long().cpu()                                              # :534 (int64, CPU)
                 self.cluster_centers_list.append(centers)                               # :478-479
                 self.result_cluster_ids.append(ids_cpu)
@@ -346,17 +346,115 @@ class HierarchicalRQKMeans:
         ids = engine.score_pass(X, cluster_centers, argmin=True).argmin                 # :654 KMeans.predict
         return cluster_centers, ids
 
+    def _train_middle_layer(self, X: torch.Tensor, layer: int):                         # :671-752
+        """Recursive strategy: one balanced fit of need[layer] centres inside every cluster of the previous layer,
+        then the block-restricted reassignment (:839-904).  Returns (centres [pre*cur, D], ids in [0, cur), raw ids)."""
+        if self._shard is not None and self._shard.active:
+            raise NotImplementedError("recursive middle layers with rows sharded over GPUs are not built yet")
+        cur_need = self.config.need_clusters[layer]
+        pre_need = self.config.need_clusters[layer - 1]
+        if layer - 1 >= len(self.result_cluster_ids):
+            raise RuntimeError(
+                f"Previous layer {layer - 1} cluster IDs not found. "
+                f"Expected at least {layer} layers but only have {len(self.result_cluster_ids)} layers.")
+        dev = X.device
+        prev = self.result_cluster_ids[layer - 1].to(dev)
+        target_nodes_num = 1
+        for idx, x in enumerate(self.config.need_clusters):                             # :699-703 (layers after this one)
+            if idx > layer:
+                target_nodes_num *= x
+        order = torch.argsort(prev, stable=True)              # rows of parent i = order[start[i]:start[i + 1]], ascending
+        counts = torch.bincount(prev, minlength=pre_need).cpu().tolist()
+        centers_list = []
+        stats, start = [], 0
+        for i in range(pre_need):                                                       # :709-733
+            rows = order[start:start + counts[i]]
+            start += counts[i]
+            sub = engine.gather_rows(X, rows)
+            iters = self._calculate_adaptive_iter_limit(len(rows), cur_need, layer, self.config.iter_limit,
+                                                        is_sub_cluster=True)
+            km = KMeans(n_clusters=cur_need, device=self.device, balanced=True)
+            km.fit_by_min_loss(X=sub, target_nodes_num=target_nodes_num, distance="euclidean", iter_limit=iters,
+                               tqdm_flag=False, half=cur_need >= 512, online=False)
+            stats.extend(km.last_fit_stats)
+            centers_list.append(km.cluster_centers.detach())
+        self.fit_stats.append(stats)
+        centers = torch.cat(centers_list, dim=0)                                        # :736
+        raw = self._reassign_middle_layer(X, centers, prev, pre_need, cur_need)
+        return centers, raw % cur_need, raw
+
+    @staticmethod
+    def _reassign_middle_layer(X: torch.Tensor, centers: torch.Tensor, prev: torch.Tensor, pre_need: int,
+                               cur_need: int) -> torch.Tensor:                          # :839-904 (ids; the caller subtracts)
+        """Raw ids in [0, pre*cur): the reference takes the argmin over ALL pre*cur centres with +10000 outside the
+        parent's block (:866-886), which is the argmin inside the block (distances are far below 10000)."""
+        prev = prev.long()
+        order = torch.argsort(prev, stable=True)
+        counts = torch.bincount(prev, minlength=pre_need).cpu().tolist()
+        raw = torch.empty(len(X), dtype=torch.int32, device=X.device)
+        start = 0
+        for i in range(pre_need):
+            rows = order[start:start + counts[i]]
+            start += counts[i]
+            if counts[i]:
+                block = centers[i * cur_need:(i + 1) * cur_need].contiguous()
+                raw[rows] = engine.score_pass(engine.gather_rows(X, rows), block, argmin=True).argmin + i * cur_need
+        return raw
+
     # ---- inference ----
+    def _predict_chain(self, x: torch.Tensor) -> torch.Tensor:
+        """predict() level by level, for models with a recursive middle layer (:539-581, :1146-1305).  Kept quirks:
+        the residual handed on comes from the UNWEIGHTED data (:577) and, after a recursive layer, is taken with the
+        id modulo need[layer], i.e. from the FIRST parent's block of centres (:577 after :1231)."""
+        L = len(self.cluster_centers_list)
+        dev = x.device
+        cur, all_ids = x, []
+        for layer in range(L):
+            c = self.cluster_centers_list[layer].to(dev, torch.float32)
+            w = self._weight_vector(layer, dev)
+            xw = engine.scale_dims(cur, w) if w is not None else cur
+            if layer == 0 or layer == L - 1:                                            # :1146-1173, :1235-1305 (no match matrix)
+                ids = engine.score_pass(xw, c, argmin=True).argmin
+            else:                                                                       # :1175-1233
+                pre_need, cur_need = self.config.need_clusters[layer - 1], self.config.need_clusters[layer]
+                prev = all_ids[layer - 1].long()
+                if len(c) == pre_need * cur_need:
+                    order = torch.argsort(prev, stable=True)
+                    counts = torch.bincount(prev, minlength=pre_need).cpu().tolist()
+                    ids = torch.empty(len(x), dtype=torch.int32, device=dev)
+                    start = 0
+                    for i in range(pre_need):
+                        rows = order[start:start + counts[i]]
+                        start += counts[i]
+                        if counts[i]:
+                            sub = engine.gather_rows(xw, rows)
+                            ids[rows] = engine.score_pass(sub, c[i * cur_need:(i + 1) * cur_need].contiguous(),
+                                                          argmin=True).argmin
+                else:
+                    raise NotImplementedError("middle layer whose centres are neither need[l-1]*need[l] nor direct")
+            all_ids.append(ids)
+            if layer < L - 1:
+                cur = engine.residual_normalise(cur, ids, c, self.config.group_dims)
+        return torch.stack(all_ids)
+
     def predict(self, X: np.ndarray) -> np.ndarray:                                     # :539-581
         if not self.is_trained or not self.cluster_centers_list:
             raise RuntimeError("Model not trained. Call train() first or load a trained model.")
         if X.shape[1] != self.config.embedding_dim:
             raise ValueError(
                 f"Input dimension {X.shape[1]} does not match config embedding_dim {self.config.embedding_dim}")
-        if list(self.config.layer_clusters) != list(self.config.need_clusters) or self.match_matrices:
-            raise NotImplementedError("predict() for recursive / match-matrix layers is the next scope row")
+        if self.match_matrices:
+            raise NotImplementedError("predict() with a match matrix (last-layer dual K-Means) is the next scope row")
         dev = torch.device(self.device)
         x = self._h2d(X, dev)
+        L = len(self.cluster_centers_list)
+        recursive = [l for l in range(1, L - 1)
+                     if len(self.cluster_centers_list[l]) != self.config.need_clusters[l]]
+        if recursive or len(self.cluster_centers_list[-1]) != self.config.need_clusters[-1] or \
+                len(self.cluster_centers_list[0]) != self.config.need_clusters[0]:
+            if len(self.cluster_centers_list[-1]) != self.config.need_clusters[-1]:
+                raise NotImplementedError("predict() for a last layer trained with the dual K-Means strategy")
+            return self._predict_chain(x).t().contiguous().long().cpu().numpy()
         centers = [c.to(dev, torch.float32) for c in self.cluster_centers_list]
         weights = [self._weight_vector(l, dev) for l in range(len(centers))]
         ids = engine.encode(x, centers, self.config.need_clusters, self.config.group_dims, weights, mode=1)

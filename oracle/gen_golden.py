@@ -215,6 +215,25 @@ def gen_iter_limit():
     print("iter_limit:", len(rows))
 
 
+def gen_middle():
+    """A hybrid config whose middle layer takes the recursive strategy (layer_clusters != need_clusters there, direct
+    layers either side): the unmodified reference's train() and predict() on a small mixture."""
+    n, d = 4096, 32
+    x = O.synth_mix(n, d, seed=11, modes=64).astype(np.float32)
+    cfg = ref_h.HierarchicalRQKMeansConfig(layer_clusters=[8, 64, 16], need_clusters=[8, 8, 16], embedding_dim=d,
+                                           group_dims=[d], hierarchical_weights=[[1.0]] * 3, iter_limit=20)
+    set_seed(42)
+    m = ref_h.HierarchicalRQKMeans(cfg, device=torch.device("cpu"))
+    out = m.train(x, resume=False)
+    pred = m.predict(x)
+    np.savez_compressed(os.path.join(OUT, "middle.npz"), x=x,
+                        c0=out["cluster_centers"][0].numpy(), c1=out["cluster_centers"][1].numpy(),
+                        c2=out["cluster_centers"][2].numpy(),
+                        train_ids=np.stack([t.numpy() for t in out["cluster_ids"]]), predict_ids=pred)
+    print("middle:", [tuple(c.shape) for c in out["cluster_centers"]], "unique ids",
+          len({tuple(r) for r in np.stack([t.numpy() for t in out["cluster_ids"]]).T.tolist()}))
+
+
 def gen_io():
     """The reference driver's own CSV reader, id assembly, jsonl writer and statistics on a small case with the
     awkward inputs (short rows, non-numeric fields, wrong dimension, quotes / non-ASCII / duplicate song ids)."""
@@ -266,7 +285,7 @@ def gen_io():
 if __name__ == "__main__":
     import contextlib
     import io
-    which = sys.argv[1:] or ["auction", "eps", "distance", "stage", "encode", "fit_stats", "iter_limit", "io"]
+    which = sys.argv[1:] or ["auction", "eps", "distance", "stage", "encode", "fit_stats", "iter_limit", "io", "middle"]
     for w in which:
         buf = io.StringIO()
         with contextlib.redirect_stdout(buf):   # the reference prints every iteration

@@ -406,6 +406,42 @@ def train_direct(x: np.ndarray, clusters: Sequence[int], group_dims: Sequence[in
     return ids_all, centers_all, traces
 
 
+def reassign_middle_layer(xw: np.ndarray, centers: np.ndarray, prev_ids: np.ndarray, pre_need: int, cur_need: int,
+                          group_dims: Sequence[int]):
+    """_reassign_clusters_middle_layer_with_residuals, hierarchical_rq_kmeans.py:839-904: argmin over ALL
+    pre_need * cur_need centres with +10000 (fp32) outside the parent's block; the residual uses the raw id."""
+    d = pairwise_distance_full(xw, centers, 100000)
+    mask = np.zeros_like(d)
+    for ci in range(pre_need):                                             # :876-881
+        rows = prev_ids == ci
+        if rows.any():
+            mask[rows, ci * cur_need:(ci + 1) * cur_need] = 1.0
+    d = d + np.float32(10000.0) * (np.float32(1.0) - mask)                 # :884
+    raw = np.argmin(d, axis=1).astype(np.int64)                            # :886
+    return raw, residual_normalised(xw, raw, centers, group_dims)          # :898
+
+
+def train_middle_layer(xw: np.ndarray, prev_ids: np.ndarray, need_clusters: Sequence[int], layer: int,
+                       group_dims: Sequence[int], iter_limit: int = 100):
+    """_train_middle_layer, hierarchical_rq_kmeans.py:671-752: one balanced fit of need[layer] centres inside
+    every cluster of the previous layer (sub-cluster iteration budget), then the block-masked reassignment.
+    Returns (centres [pre*cur, D], ids in [0, cur), residual)."""
+    cur_need, pre_need = need_clusters[layer], need_clusters[layer - 1]
+    target = 1
+    for idx, c in enumerate(need_clusters):                                # :699-703 (layers AFTER this one)
+        if idx > layer:
+            target *= c
+    centers = []
+    for i in range(pre_need):                                              # :709-733
+        rows = np.where(prev_ids == i)[0]
+        iters = adaptive_iter_limit(len(rows), cur_need, layer, iter_limit, True)
+        c, _ = fit_by_min_loss(xw[rows], cur_need, target, iters, balanced=True)
+        centers.append(c)
+    centers = np.concatenate(centers, axis=0)                              # :736
+    raw, res = reassign_middle_layer(xw, centers, prev_ids, pre_need, cur_need, group_dims)
+    return centers, raw % cur_need, res                                    # :750
+
+
 def encode_train_chain(x: np.ndarray, centers_list: Sequence[np.ndarray],
                        group_dims: Sequence[int], weights: Sequence[Sequence[float]]):
     """The ids `train()` emits for given centroids: per level KMeans.predict + normalised residual."""

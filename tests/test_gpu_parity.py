@@ -529,3 +529,60 @@ def test_full_size_iteration_properties(dev, engine, n, k):
     # linearity: the K cluster sums add up to the column sums of X (fp32 tolerance)
     tot = x.double().sum(0)
     assert ((sums.double().sum(0) - tot).abs() <= 1e-3 * x.double().abs().sum(0) / n ** 0.5 + 1e-2).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# recursive middle layer: layer_clusters != need_clusters in the middle
+# ------------------------------------------------------------------------------------------------
+def _middle_model(dev):
+    from generative_ranking_recommender_b200.hierarchical_rq_kmeans import HierarchicalRQKMeans, HierarchicalRQKMeansConfig
+    cfg = HierarchicalRQKMeansConfig(layer_clusters=[8, 64, 16], need_clusters=[8, 8, 16], embedding_dim=32,
+                                     group_dims=[32], hierarchical_weights=[[1.0]] * 3, iter_limit=20)
+    return HierarchicalRQKMeans(cfg, device=dev)
+
+
+def test_middle_layer_teacher_forced_on_reference_run(dev, engine, golden_dir):
+    """Given the centres (and previous-layer ids) of an unmodified reference run with a recursive middle layer, the
+    block-restricted reassignment (:839-904) and predict() (:1175-1233, quirks included) give the reference's ids."""
+    g = np.load(os.path.join(golden_dir, "middle.npz"))
+    x = torch.from_numpy(g["x"]).to(dev)
+    c0, c1, c2 = (torch.from_numpy(g[k]).to(dev) for k in ("c0", "c1", "c2"))
+    tid = g["train_ids"]
+    m = _middle_model(dev)
+    ids0 = engine.score_pass(x, c0, argmin=True).argmin
+    assert np.array_equal(ids0.cpu().numpy(), tid[0])
+    res0 = engine.residual_normalise(x, ids0, c0, [32])
+    raw = m._reassign_middle_layer(res0, c1, ids0, 8, 8)
+    assert np.array_equal((raw // 8).cpu().numpy(), tid[0]) and np.array_equal((raw % 8).cpu().numpy(), tid[1])
+    res1 = engine.residual_normalise(res0, raw, c1, [32])
+    assert np.array_equal(engine.score_pass(res1, c2, argmin=True).argmin.cpu().numpy(), tid[2])
+    m.cluster_centers_list, m.is_trained = [c0, c1, c2], True
+    assert np.array_equal(m.predict(g["x"]), g["predict_ids"])
+
+
+def test_middle_layer_training_structure(dev, engine, golden_dir):
+    """train() with a recursive middle layer: need[1] balanced children inside every layer-0 cluster, ids in range,
+    reproducible, as many distinct codes as the reference finds on the same data (its run: 903 of 1024)."""
+    g = np.load(os.path.join(golden_dir, "middle.npz"))
+    x = g["x"]
+    runs = []
+    for _ in range(2):
+        np.random.seed(42)
+        torch.manual_seed(42)
+        m = _middle_model(dev)
+        out = m.train(x, resume=False)
+        runs.append(np.stack([t.numpy() for t in out["cluster_ids"]]))
+    ids = runs[0]
+    assert np.array_equal(runs[0], runs[1])
+    assert tuple(out["cluster_centers"][1].shape) == (64, 32)
+    assert ids[1].min() == 0 and ids[1].max() == 7 and ids[2].max() == 15
+    for p in range(8):        # the ids come from the (unbalanced) reassignment to balanced-fit centres, as in the
+        rows = ids[0] == p    # reference, whose own run on this data spreads children over 0.6 .. 1.5 of the mean
+        sizes = np.bincount(ids[1][rows], minlength=8)
+        mean = rows.sum() / 8
+        assert sizes.min() >= 0.45 * mean and sizes.max() <= 1.7 * mean, (p, sizes)
+    ref_unique = len({tuple(r) for r in g["train_ids"].T.tolist()})
+    unique = len({tuple(r) for r in ids.T.tolist()})
+    assert abs(unique - ref_unique) <= 0.06 * ref_unique, (unique, ref_unique)
+    pred = m.predict(x)
+    assert pred.shape == (len(x), 3) and np.array_equal(pred[:, 0], ids[0])

@@ -158,3 +158,21 @@ def test_fit_statistics_overlap_reference(golden_dir):
     assert abs(mine[:, 0].mean() - ref[:, 0].mean()) < 0.015 * n, (mine, ref)
     assert 0.5 * ref[:, 1].min() <= mine[:, 1].mean() <= 2.0 * ref[:, 1].max(), (mine, ref)
     assert mine[:, 3].max() <= 2 * ref[:, 3].max() + 2
+
+
+def test_middle_layer_restatement_against_reference_run(golden_dir):
+    """Recursive middle layer (hierarchical_rq_kmeans.py:671-752, :839-904) and predict() over it (:1175-1233),
+    teacher-forced on the centres and ids of an unmodified reference run (oracle/gen_golden.py middle)."""
+    g = _load(golden_dir, "middle.npz")
+    x, c0, c1, c2, tid = g["x"], g["c0"], g["c1"], g["c2"], g["train_ids"]
+    assert c1.shape == (64, 32)
+    res0 = O.residual_normalised(x, tid[0], c0, [32])
+    assert np.array_equal(O.predict(x, c0), tid[0])
+    raw, res1 = O.reassign_middle_layer(res0, c1, tid[0], 8, 8, [32])
+    assert np.array_equal(raw // 8, tid[0]) and np.array_equal(raw % 8, tid[1])
+    assert np.array_equal(O.predict(res1, c2), tid[2])
+    pred = O.predict_hierarchy(x, [c0, c1, c2], [8, 8, 16], [32], [[1.0]] * 3)
+    assert np.array_equal(pred, g["predict_ids"])
+    # the reference's predict() differs from its own train() ids after a recursive layer (residual from the first
+    # parent's block, :577 after :1231) - the restatement must reproduce that, not "fix" it
+    assert (pred[:, 2] != tid[2]).mean() > 0.2
