@@ -66,6 +66,13 @@ constexpr int AUC_SEG_CAP = 256;   // survivor-list entries per (sub-range, work
 
 enum { MODE_HIST = 0, MODE_BID = 1, MODE_DONE = 2 };
 
+// Programmatic dependent launch (the single-GPU driver launches its round kernels with
+// cudaLaunchAttributeProgrammaticStreamSerialization): a kernel lets its successor be scheduled as soon as all of
+// its own CTAs have started, and the successor runs whatever does not depend on earlier kernels (shared-memory
+// set-up, parameter loads) before it waits for them to complete.  Both instructions are no-ops in a normal launch.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 struct AuctionState {
     int mode;
     int counter;        // the reference's `counter`
@@ -703,6 +710,8 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
     constexpr int NH2 = CPL / 2;          // half2 words per lane
     constexpr int MAXR = 256 / AUC_NW * (J == 128 ? 1 : 2) / 2;   // rows per warp: 8 (K<=128) / 16 (K<=256)
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    pdl_launch_dependents();
+    pdl_wait();
     const AuctionState st = *p.st;
     if (st.mode != MODE_BID || st.use_list) return;    // HIST passes run in auction_hist_kernel, list rounds in auction_bidlist_kernel
     const bool do_bid = true;
@@ -995,6 +1004,10 @@ __global__ void __launch_bounds__(AUC_THREADS, 2)
 auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int K, int J, int spc, AuctionPtrs p,
                     long long n_global, int fused) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    pdl_launch_dependents();
+    // nothing below depends on earlier kernels until pdl_wait(): the 64 KB histogram is cleared while they finish
+    for (int i = threadIdx.x; i < K * AUC_W / 2; i += AUC_THREADS) reinterpret_cast<unsigned int*>(smem_raw)[i] = 0;
+    pdl_wait();
     const AuctionState st = *p.st;
     if (st.mode != MODE_HIST) return;
     const int ff = st.ff_pending;
@@ -1026,7 +1039,6 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
     long long c_end = (tiles_total * (b + 1) / G) * J;
     if (c_end > N) c_end = N;
 
-    for (int i = tid; i < K * AUC_W / 2; i += AUC_THREADS) sm.hist[i] = 0;
     for (int i = tid; i < K; i += AUC_THREADS) {
         sm.above[i] = 0;
         sm.gap[i] = 0;
@@ -1350,6 +1362,8 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
 __global__ void __launch_bounds__(AUC_THREADS, 2)
 auction_bidlist_kernel(const __half* __restrict__ S, long long ld, long long N, int K, int J, int spc, AuctionPtrs p,
                        long long n_global, int fused) {
+    pdl_launch_dependents();
+    pdl_wait();
     const AuctionState st = *p.st;
     if (st.mode != MODE_BID || !st.use_list) return;
     constexpr int NCH = AUC_SEG_CAP / 32;
@@ -1603,6 +1617,8 @@ __global__ void __launch_bounds__(1024, 1)
 auction_sample_kernel(const __half* __restrict__ S, long long ld, long long N, int K, long long jpw, AuctionPtrs p,
                       unsigned short* __restrict__ collect_out, int collect_n,
                       const unsigned short* __restrict__ ext_keys, int ext_n, int ext_cnt, PeerCtx peers, int peer_par) {
+    pdl_launch_dependents();
+    pdl_wait();
     const AuctionState st = *p.st;
     if (st.mode != MODE_HIST || !st.need_sample) return;
     __shared__ unsigned short keys[AUC_SAMPLE];
@@ -1793,6 +1809,8 @@ auction_sample_kernel(const __half* __restrict__ S, long long ld, long long N, i
 // the values after this round's cost update.  Grid = K CTAs.
 __global__ void __launch_bounds__(AUC_MAX_CTAS, 1)
 auction_tieprefix_kernel(AuctionPtrs p, int K, int G) {
+    pdl_launch_dependents();
+    pdl_wait();
     if (p.st->mode != MODE_BID) return;
     const int w = blockIdx.x, tid = threadIdx.x;
     __shared__ unsigned int cnt[AUC_MAX_CTAS];
@@ -1862,8 +1880,27 @@ static int auction_prepare(int64_t n, int64_t ld, int32_t k, void* workspace, si
 // Enqueues the kernels of one pass; the device-side state machine makes those whose turn it is not return at
 // once.  which: bit 0 window sampling, bit 1 HIST, bit 2 BID (list replay + S scan), bit 3 tie prefix (between
 // HIST and BID; only meaningful with fused resolve).  fused: the last CTA of a pass kernel runs the resolve step.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_round_kernel(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem,
+                                       cudaStream_t stream, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 static int auction_launch(const AuctionArgs& a, const void* scores_t, int64_t ld, int64_t n, int32_t k, int64_t n_global,
                           int which, int fused, cudaStream_t stream) {
+    // the single-GPU driver (fused resolve) chains its round kernels with programmatic dependent launch
+    static const bool pdl_ok = [] { const char* e = getenv("RQK_NO_PDL"); return !(e && e[0] == '1'); }();
+    const bool pdl = fused != 0 && pdl_ok;
     auto kern = (a.J == 128) ? auction_pass_kernel<128> : auction_pass_kernel<64>;
     static size_t smem_set[2] = {0, 0};
     size_t& cur = smem_set[a.J == 128 ? 0 : 1];
@@ -1873,7 +1910,9 @@ static int auction_launch(const AuctionArgs& a, const void* scores_t, int64_t ld
     }
     const int spc = auction_spc(n, k);
     if (which & 1)
-        auction_sample_kernel<<<k, 1024, 0, stream>>>((const __half*)scores_t, ld, n, k, n_global / k, a.p, nullptr, 0, nullptr, 0, 1, PeerCtx{}, 0);
+        RQK_CUDA_OK(launch_round_kernel(auction_sample_kernel, (unsigned)k, 1024u, 0, stream, pdl, (const __half*)scores_t,
+                                        (long long)ld, (long long)n, (int)k, (long long)(n_global / k), a.p,
+                                        (unsigned short*)nullptr, 0, (const unsigned short*)nullptr, 0, 1, PeerCtx{}, 0));
     if (which & 2) {
         static size_t hs_set = 0;
         const size_t hs = auction_hist_smem(k);
@@ -1881,12 +1920,19 @@ static int auction_launch(const AuctionArgs& a, const void* scores_t, int64_t ld
             RQK_CUDA_OK(cudaFuncSetAttribute(auction_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
             hs_set = hs;
         }
-        auction_hist_kernel<<<a.G, AUC_THREADS, hs, stream>>>((const __half*)scores_t, ld, n, k, a.J, spc, a.p, n_global, fused);
+        RQK_CUDA_OK(launch_round_kernel(auction_hist_kernel, (unsigned)a.G, (unsigned)AUC_THREADS, hs, stream, pdl,
+                                        (const __half*)scores_t, (long long)ld, (long long)n, (int)k, a.J, spc, a.p,
+                                        (long long)n_global, fused));
     }
-    if (which & 8) auction_tieprefix_kernel<<<k, AUC_MAX_CTAS, 0, stream>>>(a.p, k, a.G);
+    if (which & 8)
+        RQK_CUDA_OK(launch_round_kernel(auction_tieprefix_kernel, (unsigned)k, (unsigned)AUC_MAX_CTAS, 0, stream, pdl, a.p, (int)k, a.G));
     if (which & 4) {
-        auction_bidlist_kernel<<<a.G, AUC_THREADS, 0, stream>>>((const __half*)scores_t, ld, n, k, a.J, spc, a.p, n_global, fused);
-        kern<<<a.G, AUC_THREADS, a.smem, stream>>>((const __half*)scores_t, ld, n, k, n_global / k, a.p, n_global, fused);
+        RQK_CUDA_OK(launch_round_kernel(auction_bidlist_kernel, (unsigned)a.G, (unsigned)AUC_THREADS, 0, stream, pdl,
+                                        (const __half*)scores_t, (long long)ld, (long long)n, (int)k, a.J, spc, a.p,
+                                        (long long)n_global, fused));
+        RQK_CUDA_OK(launch_round_kernel(kern, (unsigned)a.G, (unsigned)AUC_THREADS, a.smem, stream, pdl,
+                                        (const __half*)scores_t, (long long)ld, (long long)n, (int)k, (long long)(n_global / k),
+                                        a.p, (long long)n_global, fused));
     }
     RQK_LAUNCH_OK();
     return 0;
