@@ -370,6 +370,10 @@ __device__ __noinline__ void auction_resolve_body(AuctionPtrs p, long long N, in
         }
         if (tid == 0) s_unresolved = 1;
     } else if (!jump) {
+        // the next worker's bins are loaded while the current worker is resolved (one CTA: latency is all there is)
+        unsigned int hn[AUC_BPL];
+#pragma unroll
+        for (int i = 0; i < AUC_BPL; ++i) hn[i] = (warp < K) ? __ldcg(p.hist_g + warp * AUC_W + lane * AUC_BPL + i) : 0u;
         for (int w = warp; w < K; w += NWARPS) {
             const int base = p.win_base[w], shift = p.win_shift[w];
             const int hbase = p.win_hbase[w], nlo = (shift == 0) ? p.win_nlo[w] : 0;
@@ -377,7 +381,11 @@ __device__ __noinline__ void auction_resolve_body(AuctionPtrs p, long long N, in
             unsigned int h[AUC_BPL];
             unsigned int lsum = 0;
 #pragma unroll
-            for (int i = 0; i < AUC_BPL; ++i) { h[i] = p.hist_g[w * AUC_W + lane * AUC_BPL + i]; lsum += h[i]; }
+            for (int i = 0; i < AUC_BPL; ++i) { h[i] = hn[i]; lsum += h[i]; }
+            if (w + NWARPS < K) {
+#pragma unroll
+                for (int i = 0; i < AUC_BPL; ++i) hn[i] = __ldcg(p.hist_g + (w + NWARPS) * AUC_W + lane * AUC_BPL + i);
+            }
             // suffix sums over lanes (bins above mine)
             unsigned int suf = lsum;
 #pragma unroll
