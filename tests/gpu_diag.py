@@ -1,5 +1,5 @@
 """Bring-up diagnostics for the GPU box: each section runs in its own process under a timeout and
-prints what it finds instead of stopping at the first mismatch.  `python tools/gpu_diag.py [section..]`"""
+prints what it finds instead of stopping at the first mismatch.  `python tests/gpu_diag.py [section..]` (uses the oracle as its checker, hence it lives under tests/)"""
 import os
 import subprocess
 import sys
