@@ -49,6 +49,13 @@ class ShardGroup:
         self.nccl = self.active and dist.get_backend(group) == "nccl"
         self._peer = None
         self._seq = 0
+        self._mailbox = None
+
+    def mailbox(self) -> torch.Tensor:
+        """Pinned host copy of the auction state, two slots (engine.auction polls one batch behind)."""
+        if self._mailbox is None:
+            self._mailbox = torch.zeros((2, 32), dtype=torch.int32, pin_memory=True)
+        return self._mailbox
 
     def take_seq(self, count: int) -> int:
         """Reserves `count` exchange sequence numbers; returns the number before the first of them."""
@@ -114,7 +121,7 @@ def no_shard() -> ShardGroup:
     if _NO_SHARD is None:
         g = ShardGroup.__new__(ShardGroup)
         g.dist, g.group, g.active, g.world, g.rank, g.nccl = None, None, False, 1, 0, False
-        g._peer, g._seq = False, 0
+        g._peer, g._seq, g._mailbox = False, 0, None
         _NO_SHARD = g
     return _NO_SHARD
 
@@ -239,6 +246,23 @@ def auction(scores_t: torch.Tensor, n: int, minmax: torch.Tensor,
     sess.init(mm)
     batch = 3
     info = None
+    # The host never waits for the batch it has just enqueued: the device state is copied to a pinned two-slot
+    # mailbox after every batch and the host looks at the copy of the batch BEFORE, so the GPUs always have work
+    # queued (rounds enqueued after the auction finished return at once, identically on every rank).
+    mailbox = shard.mailbox()
+    events = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def finished(b: int) -> bool:
+        mailbox[b & 1].copy_(sess.ws[:128].view(torch.int32), non_blocking=True)
+        events[b & 1].record()
+        if b == 0:
+            return False
+        events[(b - 1) & 1].synchronize()
+        st = mailbox[(b - 1) & 1]
+        if int(st[13]) != 0:                                          # AuctionState.error
+            sess.poll()                                               # raises with the library's message
+        return int(st[3]) != 0                                        # AuctionState.done
+
     peer = shard.peer_block(dev)
     if peer is not None:
         # Exchange through peer memory: the sums over ranks happen inside the sampling / resolve kernels
@@ -256,8 +280,8 @@ def auction(scores_t: torch.Tensor, n: int, minmax: torch.Tensor,
                     sess.peer_resolve(1, ptrs, shard.world, shard.rank, s0 + 3)
                 else:
                     sess.peer_round(count, ptrs, shard.world, shard.rank, shard.take_seq(3))
-            info = sess.poll()
-            if info.done:
+            if finished(_ // batch):
+                info = sess.poll()
                 break
         if info is None or not info.done:
             raise _lib.RqkError("sharded auction did not terminate")
@@ -279,8 +303,8 @@ def auction(scores_t: torch.Tensor, n: int, minmax: torch.Tensor,
             sess.do_pass(4)
             shard.all_reduce(tail, "sum")
             sess.resolve(1)
-        info = sess.poll()
-        if info.done:
+        if finished(_ // batch):
+            info = sess.poll()
             break
     if info is None or not info.done:
         raise _lib.RqkError("sharded auction did not terminate")
