@@ -114,6 +114,7 @@ class ShardGroup:
 
 _NO_SHARD = None
 _PEER_STEPS = __import__("os").environ.get("RQK_PEER_MODE", "round") == "steps"
+_SHARD_BATCH = max(1, int(__import__("os").environ.get("RQK_SHARD_BATCH", "3")))   # rounds enqueued per look at the state
 
 
 def no_shard() -> ShardGroup:
@@ -244,7 +245,7 @@ def auction(scores_t: torch.Tensor, n: int, minmax: torch.Tensor,
     shard.all_reduce(mm[0:1], "max")
     shard.all_reduce(mm[1:2], "min")
     sess.init(mm)
-    batch = 3
+    batch = _SHARD_BATCH
     info = None
     # The host never waits for the batch it has just enqueued: the device state is copied to a pinned two-slot
     # mailbox after every batch and the host looks at the copy of the batch BEFORE, so the GPUs always have work
