@@ -29,6 +29,7 @@ import torch
 
 from . import engine
 from .balancekmeans import KMeans, pairwise_distance_full  # noqa: F401  (re-exported like the reference, :27)
+from .balancekmeans import _SPECULATIVE
 
 logger = logging.getLogger(__name__)
 
@@ -263,6 +264,9 @@ class HierarchicalRQKMeans:
                 self._load_previous_checkpoints(start_layer)
 
         dev = torch.device(self.device)
+        if start_layer == 0:
+            # the first seed draw (a permutation of all row numbers on the host) runs while X travels to the device
+            _SPECULATIVE.start(self._n_global(len(X)))
         if start_layer > 0 and self.checkpoint_manager:
             checkpoint = self.checkpoint_manager.load_layer_checkpoint(start_layer - 1, dev)
             if checkpoint and "residual_data" in checkpoint:
@@ -327,7 +331,8 @@ class HierarchicalRQKMeans:
         if dev.type != "cuda":
             raise engine._lib.RqkError(f"device {dev}: HierarchicalRQKMeans runs on CUDA sm_100a only (no CPU fallback)")
         t = torch.from_numpy(np.ascontiguousarray(X.astype("float32", copy=False)))
-        return t.to(dev, non_blocking=False)
+        # page-locked host arrays (the driver knows, torch asks it) are DMA'd without a staging copy
+        return t.to(dev, non_blocking=t.is_pinned())
 
     def _train_layer_0(self, X: torch.Tensor, layer: int):                              # :606-669
         n_clusters = self.config.layer_clusters[layer]
