@@ -257,7 +257,9 @@ class KMeans(object):
         if shard is None or not shard.active:
             idx = torch.from_numpy(np.ascontiguousarray(indices, dtype=np.int64)).to(X.device)
             return engine.gather_rows(X, idx)
-        # sharded: every rank drew the same indices; owners fill their rows, the rest stays zero
+        # sharded: every rank uses RANK 0's draw (K int64 over the group; the ranks' generators need not agree);
+        # owners fill their rows, the rest stays zero
+        indices = shard.broadcast_ints(indices, X.device)
         out = torch.zeros((len(indices), X.shape[1]), dtype=torch.float32, device=X.device)
         pos, loc = sharding.owned_rows(indices, row0, X.shape[0])
         if len(pos):
@@ -314,8 +316,11 @@ class KMeans(object):
         if n_empty > 0:
             # :321-322: an empty cluster takes one random data row, drawn from torch's global CPU
             # generator in ascending cluster order exactly like the reference
-            for ci in torch.nonzero(empty).view(-1).tolist():
-                r = int(torch.randint(n_global, (1,)))
+            cis = torch.nonzero(empty).view(-1).tolist()
+            draws = [int(torch.randint(n_global, (1,))) for _ in cis]
+            if shard.active:                                               # rank 0's rows on every rank
+                draws = shard.broadcast_ints(draws, X.device).tolist()
+            for ci, r in zip(cis, draws):
                 self.cluster_centers[ci] = self._row_global(X, r)
             d = self.cluster_centers - prev
             shift = float(torch.sum(torch.sqrt(torch.sum(d * d, dim=1))))

@@ -439,7 +439,6 @@ __device__ __noinline__ void auction_resolve_body(AuctionPtrs p, long long N, in
                         const int nb2 = base + (found_bin << shift);
                         p.win_base[w] = nb2;
                         p.win_hbase[w] = nb2 + AUC_HALF;
-                p.win_nlo[w] = AUC_HALF;
                         p.win_nlo[w] = AUC_HALF;
                         p.win_shift[w] = nshift;
                         p.tkey[w] = -1;
@@ -467,7 +466,6 @@ __device__ __noinline__ void auction_resolve_body(AuctionPtrs p, long long N, in
                     p.win_base[w] = 0;
                     p.win_hbase[w] = AUC_HALF;
                     p.win_nlo[w] = AUC_HALF;
-            p.win_nlo[w] = AUC_HALF;
                     p.win_shift[w] = AUC_COLD_SHIFT;
                     p.miss_run[w] = 0;
                 } else {
@@ -1910,8 +1908,12 @@ static int auction_launch(const AuctionArgs& a, const void* scores_t, int64_t ld
     static const bool pdl_ok = [] { const char* e = getenv("RQK_NO_PDL"); return !(e && e[0] == '1'); }();
     const bool pdl = fused != 0 && pdl_ok;
     auto kern = (a.J == 128) ? auction_pass_kernel<128> : auction_pass_kernel<64>;
-    static size_t smem_set[2] = {0, 0};
-    size_t& cur = smem_set[a.J == 128 ? 0 : 1];
+    // the attribute is per device (and this process may drive several): cache what has been set per device ordinal
+    int devi = 0;
+    RQK_CUDA_OK(cudaGetDevice(&devi));
+    devi &= RQK_MAX_DEVICES - 1;
+    static size_t smem_set[RQK_MAX_DEVICES][2] = {};
+    size_t& cur = smem_set[devi][a.J == 128 ? 0 : 1];
     if (a.smem > cur) {
         RQK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem));
         cur = a.smem;
@@ -1922,11 +1924,11 @@ static int auction_launch(const AuctionArgs& a, const void* scores_t, int64_t ld
                                         (long long)ld, (long long)n, (int)k, (long long)(n_global / k), a.p,
                                         (unsigned short*)nullptr, 0, (const unsigned short*)nullptr, 0, 1, PeerCtx{}, 0));
     if (which & 2) {
-        static size_t hs_set = 0;
+        static size_t hs_set[RQK_MAX_DEVICES] = {};
         const size_t hs = auction_hist_smem(k);
-        if (hs > hs_set) {
+        if (hs > hs_set[devi]) {
             RQK_CUDA_OK(cudaFuncSetAttribute(auction_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
-            hs_set = hs;
+            hs_set[devi] = hs;
         }
         RQK_CUDA_OK(launch_round_kernel(auction_hist_kernel, (unsigned)a.G, (unsigned)AUC_THREADS, hs, stream, pdl,
                                         (const __half*)scores_t, (long long)ld, (long long)n, (int)k, a.J, spc, a.p,
@@ -2224,13 +2226,19 @@ int rqk_auction(const void* scores_t, int64_t ld, int64_t n, int32_t k, const vo
     // host looks at the copy of the batch BEFORE the one it enqueued last, so the GPU always has work queued
     // (passes enqueued after the auction finished return at once).  The mailbox (pinned host memory, 2 x 128 B
     // per host thread) is the one allocation this library makes.
-    static thread_local AuctionState* mailbox = nullptr;
-    static thread_local cudaEvent_t ev[2];
-    if (!mailbox) {
-        RQK_CUDA_OK(cudaHostAlloc((void**)&mailbox, 2 * sizeof(AuctionState), cudaHostAllocDefault));
-        RQK_CUDA_OK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
-        RQK_CUDA_OK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    // per host thread AND per device: an event belongs to the device that was current when it was created
+    static thread_local AuctionState* mailbox_d[RQK_MAX_DEVICES] = {};
+    static thread_local cudaEvent_t ev_d[RQK_MAX_DEVICES][2];
+    int devi = 0;
+    RQK_CUDA_OK(cudaGetDevice(&devi));
+    devi &= RQK_MAX_DEVICES - 1;
+    if (!mailbox_d[devi]) {
+        RQK_CUDA_OK(cudaHostAlloc((void**)&mailbox_d[devi], 2 * sizeof(AuctionState), cudaHostAllocPortable));
+        RQK_CUDA_OK(cudaEventCreateWithFlags(&ev_d[devi][0], cudaEventDisableTiming));
+        RQK_CUDA_OK(cudaEventCreateWithFlags(&ev_d[devi][1], cudaEventDisableTiming));
     }
+    AuctionState* mailbox = mailbox_d[devi];
+    cudaEvent_t* ev = ev_d[devi];
     const int rounds_per_batch = 2;
     const AuctionState* fin = nullptr;
     // hard stop: the reference itself cannot exceed 1002 rounds; each round is a handful of passes at most

@@ -60,6 +60,9 @@ __host__ __device__ __forceinline__ T round_up(T a, T b) { return ceil_div(a, b)
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// per-device caches (function attributes, events) are indexed by the CUDA device ordinal & (RQK_MAX_DEVICES - 1)
+constexpr int RQK_MAX_DEVICES = 16;
+
 // Everything the score pass can emit (any pointer may be null), shared by the tcgen05 kernel and
 // the CUDA-core cross-check kernel.
 struct ScoreOut {

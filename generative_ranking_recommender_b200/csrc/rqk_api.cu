@@ -55,7 +55,7 @@ int rqk_device_check(int device) {
     using namespace rqk;
     cudaDeviceProp prop;
     RQK_CUDA_OK(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10)
+    if (prop.major != 10 || prop.minor != 0)      // the binary holds sm_100a code only (no PTX for other sm_10x parts)
         return fail(RQK_ERR_UNSUPPORTED, "rqk: device is sm_%s%lld%lld, this library is built for sm_100a only", "",
                     (long long)prop.major, (long long)prop.minor);
     return 0;

@@ -30,6 +30,16 @@ def _stream(dev: torch.device):
     return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
+def _call(dev: torch.device, fn, *args):
+    """A library call with `dev` as the current CUDA device: kernel attributes, events and launches belong to the
+    current device, which need not be the device the caller's tensors live on."""
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx == torch.cuda.current_device():
+        return check(fn(*args))
+    with torch.cuda.device(idx):
+        return check(fn(*args))
+
+
 def _req_cuda(t: torch.Tensor, name: str):
     if not t.is_cuda:
         raise _lib.RqkError(f"{name} must live on a CUDA device (got {t.device}); there is no CPU path")
@@ -96,6 +106,20 @@ class ShardGroup:
             ops = {"sum": self.dist.ReduceOp.SUM, "max": self.dist.ReduceOp.MAX, "min": self.dist.ReduceOp.MIN}
             self.dist.all_reduce(t, op=ops[op], group=self.group)
         return t
+
+    def broadcast_ints(self, values, dev: Optional[torch.device] = None) -> np.ndarray:
+        """Rank 0's int64 values on every rank.  Host-side random draws of a sharded fit (seed rows, empty-cluster
+        rows) go through this, so the ranks need not be seeded identically: every rank still makes its own draw
+        (its generator advances exactly as an unsharded run's would) but all of them USE rank 0's."""
+        v = np.ascontiguousarray(values, dtype=np.int64)
+        if not self.active:
+            return v
+        t = torch.from_numpy(v.copy())
+        if self.nccl:
+            t = t.to(dev if dev is not None else torch.device("cuda", torch.cuda.current_device()))
+        self.dist.broadcast(t, src=self.dist.get_global_rank(self.group, 0) if self.group is not None else 0,
+                            group=self.group)
+        return t.cpu().numpy()
 
     def all_gather(self, t: torch.Tensor) -> torch.Tensor:
         if not self.active:
@@ -197,9 +221,9 @@ def score_pass(x: torch.Tensor, centers: torch.Tensor, *, scores: bool = False, 
     wsb = L.rqk_score_workspace_bytes(n, k, dim)
     ws = SCRATCH.get("score", wsb, dev)
     flags = (FLAG_FARTHEST if farthest else 0) | (FLAG_SIMT if simt else 0)
-    check(L.rqk_score_pass(_ptr(x), n, dim, _ptr(centers), k, _ptr(res.scores_t), ld, _ptr(res.argmin),
+    _call(dev, L.rqk_score_pass, _ptr(x), n, dim, _ptr(centers), k, _ptr(res.scores_t), ld, _ptr(res.argmin),
                            _ptr(res.best2), _ptr(res.counts), _ptr(res.minmax), _ptr(res.dist), flags, _ptr(ws), ws.numel(),
-                           _stream(dev)))
+                           _stream(dev))
     return res
 
 
@@ -234,8 +258,8 @@ def auction(scores_t: torch.Tensor, n: int, minmax: torch.Tensor,
     if not shard.active:
         wsb = L.rqk_auction_workspace_bytes(n, k)
         ws = SCRATCH.get("auction", wsb, dev)
-        check(L.rqk_auction(_ptr(scores_t), ld, n, k, _ptr(minmax), _ptr(assign), _ptr(ws), ws.numel(),
-                            ctypes.byref(info), _stream(dev)))
+        _call(dev, L.rqk_auction, _ptr(scores_t), ld, n, k, _ptr(minmax), _ptr(assign), _ptr(ws), ws.numel(),
+                            ctypes.byref(info), _stream(dev))
         return assign, _info_to_stats(info)
 
     # ---- jobs sharded over ranks: same kernels, histograms summed between pass and resolve ----
@@ -325,7 +349,7 @@ class AuctionSession:
         self.dev = scores_t.device
         self.L = lib()
         lay = AuctionLayout()
-        check(self.L.rqk_auction_layout_query(self.n, self.k, ctypes.byref(lay)))
+        _call(self.dev, self.L.rqk_auction_layout_query, self.n, self.k, ctypes.byref(lay))
         self.ws = torch.empty(int(lay.total_bytes), dtype=torch.uint8, device=self.dev)
         self.reduce_block = self.ws[lay.reduce_offset: lay.reduce_offset + 4 * lay.reduce_count].view(torch.int32)
         self.tie_total = self.ws[lay.tie_total_offset: lay.tie_total_offset + 4 * self.k].view(torch.int32)
@@ -335,19 +359,19 @@ class AuctionSession:
 
     def init(self, minmax_global: torch.Tensor):
         self._mm = minmax_global.contiguous()
-        check(self.L.rqk_auction_init(self.n, self.ld, self.k, _ptr(self._mm), *self._args(), _stream(self.dev)))
+        _call(self.dev, self.L.rqk_auction_init, self.n, self.ld, self.k, _ptr(self._mm), *self._args(), _stream(self.dev))
 
     def do_pass(self, which: int = 0):
         """which: 0 = sample + HIST + BID kernels (the state machine picks), or a subset (1 | 2 | 4)."""
-        check(self.L.rqk_auction_pass(_ptr(self.s), self.ld, self.n, self.k, self.n_global, int(which),
-                                      *self._args(), _stream(self.dev)))
+        _call(self.dev, self.L.rqk_auction_pass, _ptr(self.s), self.ld, self.n, self.k, self.n_global, int(which),
+                                      *self._args(), _stream(self.dev))
 
     def sample_collect(self, count: int) -> torch.Tensor:
         """Sharded window sampling, step 1: int16 [k, count] fp16 keys of `count` local jobs per worker
         (all zeros while the state machine does not ask for a sample)."""
         out = torch.zeros((self.k, count), dtype=torch.int16, device=self.dev)
-        check(self.L.rqk_auction_sample_collect(_ptr(self.s), self.ld, self.n, self.k, self.n_global, _ptr(out),
-                                                int(count), *self._args(), _stream(self.dev)))
+        _call(self.dev, self.L.rqk_auction_sample_collect, _ptr(self.s), self.ld, self.n, self.k, self.n_global, _ptr(out),
+                                                int(count), *self._args(), _stream(self.dev))
         return out
 
     def sample_window(self, keys: torch.Tensor):
@@ -357,42 +381,42 @@ class AuctionSession:
             keys = keys.unsqueeze(0)
         self._keys = keys.contiguous()
         parts, _, count = self._keys.shape
-        check(self.L.rqk_auction_sample_window(self.n, self.ld, self.k, self.n_global, _ptr(self._keys), int(count),
-                                               int(parts), *self._args(), _stream(self.dev)))
+        _call(self.dev, self.L.rqk_auction_sample_window, self.n, self.ld, self.k, self.n_global, _ptr(self._keys), int(count),
+                                               int(parts), *self._args(), _stream(self.dev))
 
     def peer_sample(self, count: int, ptrs, world: int, rank: int, seq: int):
-        check(self.L.rqk_auction_peer_sample(_ptr(self.s), self.ld, self.n, self.k, self.n_global, int(count),
-                                             ptrs, world, rank, seq, *self._args(), _stream(self.dev)))
+        _call(self.dev, self.L.rqk_auction_peer_sample, _ptr(self.s), self.ld, self.n, self.k, self.n_global, int(count),
+                                             ptrs, world, rank, seq, *self._args(), _stream(self.dev))
 
     def peer_round(self, count: int, ptrs, world: int, rank: int, seq0: int):
-        check(self.L.rqk_auction_peer_round(_ptr(self.s), self.ld, self.n, self.k, self.n_global, int(count), ptrs,
-                                            world, rank, seq0, *self._args(), _stream(self.dev)))
+        _call(self.dev, self.L.rqk_auction_peer_round, _ptr(self.s), self.ld, self.n, self.k, self.n_global, int(count), ptrs,
+                                            world, rank, seq0, *self._args(), _stream(self.dev))
 
     def peer_resolve(self, expect: int, ptrs, world: int, rank: int, seq: int):
-        check(self.L.rqk_auction_peer_resolve(self.n, self.ld, self.k, self.n_global, expect, ptrs, world, rank, seq,
-                                              *self._args(), _stream(self.dev)))
+        _call(self.dev, self.L.rqk_auction_peer_resolve, self.n, self.ld, self.k, self.n_global, expect, ptrs, world, rank, seq,
+                                              *self._args(), _stream(self.dev))
 
     def resolve(self, expect: int = -1):
         """expect: -1, or 0 / 1 = act only if a HIST / BID pass has just run."""
-        check(self.L.rqk_auction_resolve(self.n, self.ld, self.k, self.n_global, expect, *self._args(),
-                                         _stream(self.dev)))
+        _call(self.dev, self.L.rqk_auction_resolve, self.n, self.ld, self.k, self.n_global, expect, *self._args(),
+                                         _stream(self.dev))
 
     def tie_offset(self, totals: torch.Tensor, rank: int):
         """totals int32 [world, k] = the all-gather of every rank's `tie_total`."""
         if rank == 0:
             return
         self._tot = totals.to(torch.int32).contiguous()
-        check(self.L.rqk_auction_tie_offset(self.n, self.ld, self.k, _ptr(self._tot), int(rank), *self._args(),
-                                            _stream(self.dev)))
+        _call(self.dev, self.L.rqk_auction_tie_offset, self.n, self.ld, self.k, _ptr(self._tot), int(rank), *self._args(),
+                                            _stream(self.dev))
 
     def poll(self) -> AuctionInfo:
         info = AuctionInfo()
-        check(self.L.rqk_auction_poll(self.n, self.ld, self.k, *self._args(), ctypes.byref(info), _stream(self.dev)))
+        _call(self.dev, self.L.rqk_auction_poll, self.n, self.ld, self.k, *self._args(), ctypes.byref(info), _stream(self.dev))
         return info
 
     def finalize(self) -> torch.Tensor:
         assign = torch.empty(self.n, dtype=torch.int32, device=self.dev)
-        check(self.L.rqk_auction_finalize(self.n, self.ld, self.k, *self._args(), _ptr(assign), _stream(self.dev)))
+        _call(self.dev, self.L.rqk_auction_finalize, self.n, self.ld, self.k, *self._args(), _ptr(assign), _stream(self.dev))
         return assign
 
 
@@ -405,8 +429,8 @@ def centroid_accumulate(x: torch.Tensor, assign: torch.Tensor, k: int) -> Tuple[
     sums = torch.empty((k, dim), dtype=torch.float32, device=dev)
     counts = torch.empty(k, dtype=torch.int64, device=dev)
     ws = SCRATCH.get("centroid", L.rqk_centroid_workspace_bytes(n, k, dim), dev)
-    check(L.rqk_centroid_accumulate(_ptr(x), n, dim, _ptr(assign), k, _ptr(sums), _ptr(counts), _ptr(ws),
-                                    ws.numel(), _stream(dev)))
+    _call(dev, L.rqk_centroid_accumulate, _ptr(x), n, dim, _ptr(assign), k, _ptr(sums), _ptr(counts), _ptr(ws),
+                                    ws.numel(), _stream(dev))
     return sums, counts
 
 
@@ -416,8 +440,8 @@ def centroid_finalize(sums: torch.Tensor, counts: torch.Tensor, centers: torch.T
     dev = sums.device
     out = torch.empty(2, dtype=torch.float32, device=dev)
     empty = torch.empty(k, dtype=torch.int32, device=dev)
-    check(lib().rqk_centroid_finalize(_ptr(sums), _ptr(counts), k, dim, _ptr(centers), _ptr(out), _ptr(empty),
-                                      _stream(dev)))
+    _call(dev, lib().rqk_centroid_finalize, _ptr(sums), _ptr(counts), k, dim, _ptr(centers), _ptr(out), _ptr(empty),
+                                      _stream(dev))
     return out, empty
 
 
@@ -443,8 +467,8 @@ def residual_normalise(x: torch.Tensor, ids: torch.Tensor, centers: torch.Tensor
         out = torch.empty_like(x)
     ge = _group_end(group_dims, dev)
     ids32 = ids if ids.dtype == torch.int32 else ids.to(torch.int32)
-    check(lib().rqk_residual_normalise(_ptr(x), n, dim, _ptr(ids32.contiguous()), _ptr(centers.contiguous()),
-                                       _ptr(ge), ge.numel(), _ptr(out), _stream(dev)))
+    _call(dev, lib().rqk_residual_normalise, _ptr(x), n, dim, _ptr(ids32.contiguous()), _ptr(centers.contiguous()),
+                                       _ptr(ge), ge.numel(), _ptr(out), _stream(dev))
     return out
 
 
@@ -452,7 +476,7 @@ def scale_dims(x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = N
     n, dim = x.shape
     if out is None:
         out = torch.empty_like(x)
-    check(lib().rqk_scale_dims(_ptr(x), n, dim, _ptr(w), _ptr(out), _stream(x.device)))
+    _call(x.device, lib().rqk_scale_dims, _ptr(x), n, dim, _ptr(w), _ptr(out), _stream(x.device))
     return out
 
 
@@ -460,7 +484,7 @@ def gather_rows(x: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
     """x[rows] for centroid (re-)initialisation; rows int64 on the device."""
     dim = x.shape[1]
     out = torch.empty((rows.numel(), dim), dtype=torch.float32, device=x.device)
-    check(lib().rqk_gather_rows(_ptr(x), dim, _ptr(rows), rows.numel(), _ptr(out), _stream(x.device)))
+    _call(x.device, lib().rqk_gather_rows, _ptr(x), dim, _ptr(rows), rows.numel(), _ptr(out), _stream(x.device))
     return out
 
 
@@ -484,6 +508,6 @@ def encode(x: torch.Tensor, centers: List[torch.Tensor], needs: Sequence[int], g
     L = lib()
     kmax = max(int(c.shape[0]) for c in centers)
     ws = SCRATCH.get("encode", L.rqk_encode_workspace_bytes(n, dim, kmax), dev)
-    check(L.rqk_encode(_ptr(x), n, dim, levels, cptr, wptr, ks, nd, _ptr(ge), ge.numel(), _ptr(ids), mode,
-                       FLAG_SIMT if simt else 0, _ptr(ws), ws.numel(), _stream(dev)))
+    _call(dev, L.rqk_encode, _ptr(x), n, dim, levels, cptr, wptr, ks, nd, _ptr(ge), ge.numel(), _ptr(ids), mode,
+                       FLAG_SIMT if simt else 0, _ptr(ws), ws.numel(), _stream(dev))
     return ids

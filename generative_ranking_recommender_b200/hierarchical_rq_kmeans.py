@@ -19,6 +19,7 @@ from __future__ import annotations
 import json
 import logging
 import pickle
+import threading
 import time
 from dataclasses import asdict, dataclass
 from pathlib import Path
@@ -71,35 +72,57 @@ class HierarchicalRQKMeansConfig:
 
 
 class CheckpointManager:
-    """:85-184 - per-layer pickle written to .tmp, re-read, key-validated, atomically renamed."""
+    """:85-184 - per-layer pickle written to .tmp, validated, atomically renamed; same keys and file names.
 
-    def __init__(self, checkpoint_dir: str):
+    Two extensions, both invisible to a single-process caller that reads the files back:
+    * rows sharded over ranks (`world` > 1): every rank writes ITS row block to `layer_{i}_rank{r}_checkpoint.pkl`
+      (one shared name would be a write/rename race, and a resume would hand every rank the same block); the
+      metadata file is written by rank 0 only;
+    * the residual (N x D fp32: 20 GB per layer at 10 M rows) leaves the device on a side stream into pinned host
+      memory and is pickled by a writer thread while the next layer trains; `wait()` joins it and re-raises."""
+
+    VALIDATE_REREAD_BYTES = 256 << 20      # small files are re-read like the reference (:113-125); large ones are
+                                           # validated on the object that was written plus the file size
+
+    def __init__(self, checkpoint_dir: str, rank: int = 0, world: int = 1):
         self.checkpoint_dir = Path(checkpoint_dir)
         self.checkpoint_dir.mkdir(parents=True, exist_ok=True)
         self.metadata_file = self.checkpoint_dir / "checkpoint_metadata.json"
+        self.rank, self.world = int(rank), int(world)
+        self._writer: Optional[threading.Thread] = None
+        self._writer_error: Optional[BaseException] = None
+
+    def _file(self, layer: int, suffix: str = "pkl") -> Path:
+        tag = f"_rank{self.rank}" if self.world > 1 else ""
+        return self.checkpoint_dir / f"layer_{layer}{tag}_checkpoint.{suffix}"
 
     @staticmethod
     def _np(v):
         return v.cpu().numpy() if isinstance(v, torch.Tensor) else v
 
-    def save_layer_checkpoint(self, layer: int, cluster_ids, residual_data, cluster_centers=None, match_matrix=None):
-        checkpoint = {
-            "layer": layer,
-            "cluster_ids": self._np(cluster_ids),
-            "residual_data": self._np(residual_data),
-            "cluster_centers": self._np(cluster_centers),
-            "match_matrix": match_matrix,
-        }
-        checkpoint_file = self.checkpoint_dir / f"layer_{layer}_checkpoint.pkl"
-        temp_checkpoint_file = self.checkpoint_dir / f"layer_{layer}_checkpoint.tmp"
+    def wait(self):
+        """Joins the writer thread; an error it hit is raised here (and by the next save)."""
+        if self._writer is not None:
+            self._writer.join()
+            self._writer = None
+        if self._writer_error is not None:
+            e, self._writer_error = self._writer_error, None
+            raise e
+
+    def _write(self, layer: int, checkpoint: Dict):
+        checkpoint_file, temp_checkpoint_file = self._file(layer), self._file(layer, "tmp")
         try:
-            with open(temp_checkpoint_file, "wb") as f:
-                pickle.dump(checkpoint, f)
-            with open(temp_checkpoint_file, "rb") as f:
-                loaded_checkpoint = pickle.load(f)
             for key in ["cluster_ids", "cluster_centers"]:
-                if key not in loaded_checkpoint or loaded_checkpoint[key] is None:
+                if key not in checkpoint or checkpoint[key] is None:
                     raise ValueError(f"Checkpoint validation failed: missing or None key '{key}'")
+            with open(temp_checkpoint_file, "wb") as f:
+                pickle.dump(checkpoint, f, protocol=pickle.HIGHEST_PROTOCOL)
+            if temp_checkpoint_file.stat().st_size <= self.VALIDATE_REREAD_BYTES:
+                with open(temp_checkpoint_file, "rb") as f:
+                    loaded_checkpoint = pickle.load(f)
+                for key in ["cluster_ids", "cluster_centers"]:
+                    if key not in loaded_checkpoint or loaded_checkpoint[key] is None:
+                        raise ValueError(f"Checkpoint validation failed: missing or None key '{key}'")
             temp_checkpoint_file.replace(checkpoint_file)
         except Exception as e:
             if temp_checkpoint_file.exists():
@@ -110,8 +133,51 @@ class CheckpointManager:
             logger.error(f"Failed to save checkpoint for layer {layer}: {str(e)}")
             raise
 
+    def save_layer_checkpoint(self, layer: int, cluster_ids, residual_data, cluster_centers=None, match_matrix=None,
+                              asynchronous: bool = False):
+        self.wait()
+        checkpoint = {
+            "layer": layer,
+            "cluster_ids": self._np(cluster_ids),
+            "residual_data": None,
+            "cluster_centers": self._np(cluster_centers),
+            "match_matrix": match_matrix,
+        }
+        if not (asynchronous and isinstance(residual_data, torch.Tensor) and residual_data.is_cuda):
+            checkpoint["residual_data"] = self._np(residual_data)
+            self._write(layer, checkpoint)
+            return
+        # device -> pinned host on a side stream; the caller's stream waits for the copy before it may overwrite
+        # the buffer (the next layer's residual is written in place), the host does not wait at all
+        dev = residual_data.device
+        try:
+            host = torch.empty(residual_data.shape, dtype=residual_data.dtype, pin_memory=True)
+        except RuntimeError:                # not enough page-locked memory: the reference's synchronous path
+            checkpoint["residual_data"] = self._np(residual_data)
+            self._write(layer, checkpoint)
+            return
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            host.copy_(residual_data, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(side)
+        torch.cuda.current_stream(dev).wait_event(done)
+
+        def work():
+            try:
+                done.synchronize()
+                checkpoint["residual_data"] = host.numpy()
+                self._write(layer, checkpoint)
+            except BaseException as e:      # surfaced by wait()
+                self._writer_error = e
+
+        self._writer = threading.Thread(target=work, name=f"rqk-checkpoint-{layer}", daemon=True)
+        self._writer.start()
+
     def load_layer_checkpoint(self, layer: int, device: torch.device) -> Optional[Dict]:
-        checkpoint_file = self.checkpoint_dir / f"layer_{layer}_checkpoint.pkl"
+        self.wait()
+        checkpoint_file = self._file(layer)
         if not checkpoint_file.exists():
             return None
         with open(checkpoint_file, "rb") as f:
@@ -122,15 +188,19 @@ class CheckpointManager:
         return checkpoint
 
     def get_last_completed_layer(self) -> int:
+        self.wait()
         completed_layers = []
         for i in range(100):
-            if (self.checkpoint_dir / f"layer_{i}_checkpoint.pkl").exists():
+            if self._file(i).exists():
                 completed_layers.append(i)
             else:
                 break
         return max(completed_layers) if completed_layers else -1
 
     def save_metadata(self, metadata: Dict):
+        self.wait()
+        if self.rank != 0:
+            return
         with open(self.metadata_file, "w") as f:
             json.dump(metadata, f, indent=2, default=str)
 
@@ -141,9 +211,11 @@ class CheckpointManager:
             return json.load(f)
 
     def clear_checkpoints(self):
-        for file in self.checkpoint_dir.glob("layer_*_checkpoint.pkl"):
+        self.wait()
+        tag = f"_rank{self.rank}" if self.world > 1 else ""
+        for file in self.checkpoint_dir.glob(f"layer_*{tag}_checkpoint.pkl"):
             file.unlink()
-        if self.metadata_file.exists():
+        if self.rank == 0 and self.metadata_file.exists():
             self.metadata_file.unlink()
 
 
@@ -154,7 +226,8 @@ class HierarchicalRQKMeans:
                  device: Optional[torch.device] = None, shard: Optional[engine.ShardGroup] = None):
         self.config = config
         self.device = device or self._get_device()
-        self.checkpoint_manager = CheckpointManager(checkpoint_dir) if checkpoint_dir else None
+        rank, world = (shard.rank, shard.world) if shard is not None and shard.active else (0, 1)
+        self.checkpoint_manager = CheckpointManager(checkpoint_dir, rank, world) if checkpoint_dir else None
         self.is_trained = False
         self.cluster_centers_list = []
         self.match_matrices = []
@@ -259,9 +332,18 @@ class HierarchicalRQKMeans:
         start_layer = 0
         if resume and self.checkpoint_manager:
             start_layer = self.checkpoint_manager.get_last_completed_layer() + 1
+            if self._shard is not None and self._shard.active:      # every rank resumes from the same layer
+                t = torch.tensor([start_layer], dtype=torch.int64, device=self.device)
+                self._shard.all_reduce(t, "min")
+                start_layer = int(t.item())
             if start_layer > 0:
                 logger.info(f"[RESUME] Resuming training from layer {start_layer}")
                 self._load_previous_checkpoints(start_layer)
+                for ids in self.result_cluster_ids:
+                    if len(ids) != len(X):
+                        raise RuntimeError(
+                            f"Checkpoint holds {len(ids)} rows but train() was given {len(X)}. "
+                            f"Use --clear-checkpoints flag to start training from scratch.")
 
         dev = torch.device(self.device)
         if start_layer == 0:
@@ -269,8 +351,12 @@ class HierarchicalRQKMeans:
             _SPECULATIVE.start(self._n_global(len(X)))
         if start_layer > 0 and self.checkpoint_manager:
             checkpoint = self.checkpoint_manager.load_layer_checkpoint(start_layer - 1, dev)
-            if checkpoint and "residual_data" in checkpoint:
+            if checkpoint and checkpoint.get("residual_data") is not None:
                 current_data = checkpoint["residual_data"].to(torch.float32).contiguous()
+                if len(current_data) != len(X):
+                    raise RuntimeError(
+                        f"Checkpoint residual holds {len(current_data)} rows but train() was given {len(X)}. "
+                        f"Use --clear-checkpoints flag to start training from scratch.")
                 logger.info(f"[RESUME] Loaded residual data from layer {start_layer - 1}")
             else:
                 current_data = self._h2d(X, dev)
@@ -287,16 +373,21 @@ class HierarchicalRQKMeans:
                 # :428 - clustering and the residual both live in the weighted space;
                 # the device copy is ours, so weight in place instead of cloning N x D
                 w = self._weight_vector(layer, dev)
+                layer_data = current_data
                 if w is not None:
-                    engine.scale_dims(current_data, w, out=current_data)
+                    if layer == L - 1 and self.checkpoint_manager:
+                        # the last layer's checkpoint holds the UNWEIGHTED input (:486): keep it intact
+                        layer_data = engine.scale_dims(current_data, w)
+                    else:
+                        engine.scale_dims(current_data, w, out=current_data)
                 if n_clusters == need_clusters:                                         # :438-447
-                    centers, ids = self._train_layer_0(current_data, layer)
+                    centers, ids = self._train_layer_0(layer_data, layer)
                 elif layer == L - 1:                                                    # :449-462
                     raise NotImplementedError(
                         "last-layer dual-KMeans + match-matrix strategy (layer_clusters != need_clusters) "
                         "is the next scope row (SURVEY.md 8f), not built yet")
                 else:                                                                   # :464-475
-                    centers, ids, raw_ids = self._train_middle_layer(current_data, layer)
+                    centers, ids, raw_ids = self._train_middle_layer(layer_data, layer)
                 if layer < L - 1:
                     # :660 / :1088-1128 (:898 for a recursive layer: the RAW id picks the centre), in place: the
                     # residual IS the next level's input (:501-503)
@@ -306,7 +397,10 @@ class HierarchicalRQKMeans:
                 self.cluster_centers_list.append(centers)                               # :478-479
                 self.result_cluster_ids.append(ids_cpu)
                 if self.checkpoint_manager:                                             # :482-498
-                    self.checkpoint_manager.save_layer_checkpoint(layer, ids_cpu, current_data, centers, None)
+                    # the residual leaves the device while the next layer trains (its first in-place write waits
+                    # for the copy on the stream; the pickle is written by a thread)
+                    self.checkpoint_manager.save_layer_checkpoint(layer, ids_cpu, current_data, centers, None,
+                                                                  asynchronous=True)
                 logger.info(f"[LAYER {layer + 1}] Completed in {time.time() - layer_start_time:.2f}s")
             except Exception as e:
                 logger.error(f"Error training layer {layer + 1}: {str(e)}")
@@ -314,6 +408,7 @@ class HierarchicalRQKMeans:
 
         self.is_trained = True
         if self.checkpoint_manager:                                                     # :517-525
+            self.checkpoint_manager.wait()
             self.checkpoint_manager.save_metadata({
                 "num_layers": L,
                 "embedding_dim": self.config.embedding_dim,
@@ -491,7 +586,7 @@ class HierarchicalRQKMeans:
                     f"Incomplete checkpoint data at layer {layer}. Missing: {missing_keys}. "
                     f"Use --clear-checkpoints flag to start training from scratch.")
             self.cluster_centers_list.append(checkpoint["cluster_centers"])
-            self.result_cluster_ids.append(checkpoint["cluster_ids"])
+            self.result_cluster_ids.append(checkpoint["cluster_ids"].long().cpu())      # int64 on the CPU like train()'s own
             if checkpoint.get("match_matrix"):
                 self.match_matrices.append(checkpoint["match_matrix"])
 

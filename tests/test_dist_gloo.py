@@ -50,6 +50,13 @@ def _worker(rank, world, port, q):
         g.all_reduce(out, "sum")
         assert torch.equal(out, torch.from_numpy(x[idx]))
 
+        # host-side draws of a sharded fit: ranks seeded DIFFERENTLY still use rank 0's rows
+        np.random.seed(100 + rank)
+        mine = np.random.choice(n_global, k, replace=False)
+        used = g.broadcast_ints(mine)
+        np.random.seed(100)
+        assert np.array_equal(used, np.random.choice(n_global, k, replace=False))
+
         # with replacement (K > N): duplicates survive
         idx2 = np.array([3, 3, 999, 400, 3])
         pos2, loc2 = sharding.owned_rows(idx2, row0, hi - lo)

@@ -77,6 +77,35 @@ def test_checkpoint_manager_files_and_resume_rule(tmp_path):
     assert cm.get_last_completed_layer() == -1 and cm.load_metadata() is None
 
 
+def test_checkpoint_files_are_per_rank_when_rows_are_sharded(tmp_path):
+    """Rows sharded over ranks: every rank writes and resumes ITS row block (one shared file name would be a
+    write/rename race and hand every rank the same block); rank 0 alone writes the metadata."""
+    d = str(tmp_path / "ck")
+    cms = [CheckpointManager(d, rank=r, world=2) for r in range(2)]
+    blocks = [torch.randn(6 + r, 4) for r in range(2)]
+    for r, cm in enumerate(cms):
+        cm.save_layer_checkpoint(0, torch.arange(6 + r), blocks[r], torch.randn(3, 4), None)
+        cm.save_metadata({"num_samples": 6 + r})
+    assert sorted(os.listdir(d)) == ["checkpoint_metadata.json", "layer_0_rank0_checkpoint.pkl",
+                                     "layer_0_rank1_checkpoint.pkl"]
+    assert cms[0].load_metadata()["num_samples"] == 6
+    for r, cm in enumerate(cms):
+        assert cm.get_last_completed_layer() == 0
+        assert torch.equal(cm.load_layer_checkpoint(0, torch.device("cpu"))["residual_data"], blocks[r])
+    assert CheckpointManager(d).get_last_completed_layer() == -1     # an unsharded run does not pick them up
+    cms[1].clear_checkpoints()
+    assert cms[0].get_last_completed_layer() == 0 and cms[1].get_last_completed_layer() == -1
+
+
+def test_resume_rejects_a_checkpoint_of_another_row_count(tmp_path):
+    cfg = _cfg(embedding_dim=32, layer_clusters=[4, 4], need_clusters=[4, 4])
+    cm = CheckpointManager(str(tmp_path / "ck"))
+    cm.save_layer_checkpoint(0, torch.zeros(50, dtype=torch.int64), torch.zeros(50, 32), torch.zeros(4, 32), None)
+    m = HierarchicalRQKMeans(cfg, checkpoint_dir=str(tmp_path / "ck"), device=torch.device("cpu"))
+    with pytest.raises(RuntimeError, match="Checkpoint holds 50 rows but train\\(\\) was given 64"):
+        m.train(np.zeros((64, 32), np.float32), resume=True)
+
+
 def test_model_save_load_formats(tmp_path):
     m = HierarchicalRQKMeans(_cfg(), device=torch.device("cpu"))
     m.cluster_centers_list = [torch.randn(128, 512), torch.randn(128, 512), torch.randn(256, 512)]
