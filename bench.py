@@ -161,70 +161,285 @@ def recorded_traffic(kernel):
 
 
 # --------------------------------------------------------------------------------------------
-def cpu_baseline_port(sample_rows, seed=1234):
-    """One fit_by_min_loss iteration of the oracle port per level on a bounded sample, all host threads.
-    Same regime as the bench workload (N % K != 0 -> the reference's 1002-round fallback)."""
+# synthetic inputs.  S-mix is the primary one (song-like: 1024 modes, row norms ~1.1),
+# S-iso (no structure) the stress case.  Device-side generation (throughput runs); the CPU arm uses the same formulas.
+def synth_device(kind, n, dev, rank=0, chunk=1 << 20):
+    import math
+    import torch
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + 1000003 * rank)
+    x = torch.empty((n, DIM), dtype=torch.float32, device=dev)
+    if kind == "iso":
+        for i in range(0, n, chunk):
+            m = min(chunk, n - i)
+            x[i:i + m] = torch.randn((m, DIM), device=dev, generator=g)
+        return x
+    gc = torch.Generator(device=dev)
+    gc.manual_seed(1234)                                       # the mode centres are the same on every rank
+    c = torch.randn((1024, DIM), device=dev, generator=gc)
+    for i in range(0, n, chunk):
+        m = min(chunk, n - i)
+        j = torch.randint(0, 1024, (m,), device=dev, generator=g)
+        x[i:i + m] = (c[j] + 0.5 * torch.randn((m, DIM), device=dev, generator=g)) * (1.0 / math.sqrt(DIM))
+    return x
+
+
+def synth_host(kind, n, seed=1234):
     import numpy as np
-    from oracle import rqk_oracle as O
     rng = np.random.default_rng(seed)
-    x = rng.standard_normal((sample_rows, DIM), dtype=np.float32)
-    per_level, rounds = [], []
-    cur = x
-    for lvl, k in enumerate(CLUSTERS):
-        c = cur[rng.choice(sample_rows, k, replace=False)].copy()
-        t0 = time.perf_counter()
+    if kind == "iso":
+        return rng.standard_normal((n, DIM), dtype=np.float32)
+    c = rng.standard_normal((1024, DIM), dtype=np.float32)
+    j = rng.integers(0, 1024, n)
+    return ((c[j] + np.float32(0.5) * rng.standard_normal((n, DIM), dtype=np.float32)) / np.float32(np.sqrt(DIM))).astype(np.float32)
+
+
+def composite_bytes(n, k, rounds_executed):
+    """algorithmic bytes of ONE fit iteration = (8*D + 2*K + 2*K*R) per vector: X read by the score
+    pass and by the centroid accumulate, the fp16 scores written once, and one read of them per auction round."""
+    return float(n) * (8 * DIM + 2 * k + 2 * k * rounds_executed)
+
+
+# --------------------------------------------------------------------------------------------
+class CpuWorkload:
+    """The CPU arm: the oracle port of the reference (C/OpenMP auction + numpy) on a bounded S-mix sample of the
+    workload, built exactly like the GPU arm's (level inputs prepared once, untimed; a step = ONE fit iteration of
+    balancekmeans/__init__.py:304-362 at level step % 3).  N % K != 0 as in the full workload: the reference's
+    1002-round regime, every round simulated."""
+
+    def __init__(self, rows, kind="mix", seed=1234):
+        import numpy as np
+        from oracle import rqk_oracle as O
+        O.set_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1: use the box's cores anyway
+        self.O, self.np, self.rows, self.kind = O, np, rows, kind
+        rng = np.random.default_rng(seed)
+        cur = synth_host(kind, rows, seed)
+        self.levels = []
+        for lvl, k in enumerate(CLUSTERS):
+            c = cur[rng.choice(rows, k, replace=False)].copy()
+            self.levels.append([k, cur, c])
+            if lvl < len(CLUSTERS) - 1:
+                c1, ids, _ = self.iterate(cur, c, k)
+                self.levels[-1][2] = c1
+                cur = O.residual_normalised(cur, ids, c1, [DIM])
+        self.rounds, self.seconds = [], []
+
+    def iterate(self, cur, c, k):
+        O, np = self.O, self.np
         d = O.pairwise_distance_full(cur, c, 100000)                     # :308
         res = O.auction_lap_half(-d)                                     # :310
         c1 = O.update_centers(cur, res.assignment, c)                    # :314-324
         d2 = O.pairwise_distance_full(cur, c1, 100000)                   # :327
-        cnt = np.bincount(np.argmin(d2, axis=1), minlength=k)            # :328-329
-        O.overflow_loss(cnt, 1 << 30)
-        O.center_shift(c1, c)
-        per_level.append(time.perf_counter() - t0)
-        rounds.append(res.rounds)
-        if lvl < len(CLUSTERS) - 1:
-            cur = O.residual_normalised(cur, np.argmin(d2, axis=1), c1, [DIM])
-    total = sum(per_level)
-    return {"value": sample_rows * len(CLUSTERS) / total, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
-            "sample": f"{sample_rows} x {DIM} fp32 S-iso rows, one fit iteration per level {CLUSTERS}, "
-                      f"auction rounds {rounds}, {total:.1f} s CPU",
-            "seconds_per_level": [round(t, 2) for t in per_level]}
+        ids = np.argmin(d2, axis=1)
+        cnt = np.bincount(ids, minlength=k)                              # :328-329
+        O.overflow_loss(cnt, 1 << 30)                                    # :333-336
+        O.center_shift(c1, c)                                            # :343-346
+        return c1, ids, res.rounds
+
+    def step(self, i):
+        lvl = i % len(self.levels)
+        k, cur, c = self.levels[lvl]
+        t0 = time.perf_counter()
+        c1, _, r = self.iterate(cur, c, k)
+        dt = time.perf_counter() - t0
+        self.levels[lvl][2] = c1
+        self.rounds.append(r)
+        self.seconds.append(dt)
+        return dt
+
+    def record(self, first=0):
+        sec, rounds = self.seconds[first:], self.rounds[first:]
+        total = sum(sec)
+        return {"value": self.rows * len(sec) / total, "unit": UNIT, "cores": self.O.num_threads(), "kind": "port",
+                "sample": f"{self.rows} x {DIM} fp32 S-{self.kind} rows, {len(sec)} fit iterations (levels cycled over "
+                          f"{CLUSTERS}), auction rounds {sorted(set(rounds))}, {total:.1f} s CPU",
+                "sample_rows": self.rows, "seconds_per_step": [round(t, 2) for t in sec]}
+
+
+def cpu_baseline_port(sample_rows):
+    w = CpuWorkload(sample_rows)
+    for i in range(len(CLUSTERS)):
+        w.step(i)
+    return w.record()
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU path (oracle port; the reference itself is Python + torch CPU
-    and does not exist on the GPU box) on the box's host cores, same metric/unit/config."""
+    and does not exist on the GPU box) on the box's host cores, same metric/unit/config and the same step
+    definition as the GPU arm; exactly --steps steps are timed after --warmup."""
     rank = _env_int("RANK", 0)
     if rank != 0:
         return
     rows = args.cpu_rows
-    vals = []
-    base = None
-    for i in range(args.warmup + args.steps):
-        base = cpu_baseline_port(rows, seed=1234 + i)
-        if i >= args.warmup:
-            vals.append(base["value"])
-        if sum(base["seconds_per_level"]) * (args.warmup + args.steps - i - 1) > 240:
-            break
-    v = sum(vals) / max(len(vals), 1) if vals else base["value"]
-    steps = max(len(vals), 1)
-    base["value"] = v
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+    w = CpuWorkload(rows)
+    dt = w.step(0) if args.warmup > 0 else None
+    if dt is not None and dt * (args.warmup + args.steps) * 1.4 > 300 and rows > 4096:
+        rows = max(4096, rows // 2 // 128 * 128 + 64)          # a slow box: keep the step COUNT, shrink the sample
+        w = CpuWorkload(rows)
+        w.step(0)
+    for i in range(1, args.warmup):
+        w.step(i)
+    first = len(w.seconds)
+    for i in range(args.steps):
+        w.step(args.warmup + i)
+    base = w.record(first)
+    v = base["value"]
+    cfg = workload_config(args, args.gpus)
+    cfg["sample_rows"] = rows
+    cfg["sample"] = "each step runs on a bounded sample of the workload (cpu_baseline.sample), not on all its rows"
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * rows / v, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp32 distance / fp16 auction (CPU)", "data": "synthetic",
-            "config": workload_config(args, args.gpus), "cpu_baseline": base,
+            "config": cfg, "cpu_baseline": base,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 def workload_config(args, world):
-    return {"workload": f"{args.rows} x {DIM} fp32 rows per GPU, 3-level RQ-KMeans {CLUSTERS} balanced fit iteration "
-                        f"(score pass + auction + centroid update), levels cycled",
+    return {"workload": f"{args.rows} x {DIM} fp32 rows per GPU (S-mix: 1024-mode mixture, SURVEY.md 8d), 3-level RQ-KMeans "
+                        f"{CLUSTERS} balanced fit iteration (score pass + auction + centroid update), levels cycled",
             "rows_per_gpu": args.rows, "rows_total": args.rows * world, "dim": DIM, "codebook": CLUSTERS,
-            "sharding": f"rows x{world}", "l2": "inputs (2 GB X + 256/512 MB scores per level) exceed the 126 MB L2"}
+            "input": "S-mix", "sharding": f"rows x{world}",
+            "l2": "inputs (2 GB X + 256/512 MB scores per level) exceed the 126 MB L2"}
 
 
 # --------------------------------------------------------------------------------------------
+class Workload:
+    """The three level inputs of one synthetic data set, resident in HBM, and the timed step over them."""
+
+    def __init__(self, kind, n, world, rank, dev, shard, engine, KMeans):
+        import numpy as np
+        import torch
+        self.n, self.n_global, self.shard, self.engine = n, n * world, shard, engine
+        self.x0 = synth_device(kind, n, dev, rank)
+        np.random.seed(42)
+        torch.manual_seed(42)
+        self.levels = []
+        cur = self.x0
+        for lvl, k in enumerate(CLUSTERS):
+            km = KMeans(n_clusters=k, device=dev, balanced=True, shard=shard)
+            km.cluster_centers = km.initialize(cur)
+            self.levels.append((km, cur))
+            if lvl < len(CLUSTERS) - 1:
+                km._iterate(cur, self.n_global)                  # one real iteration to get sensible centroids
+                ids = engine.score_pass(cur, km.cluster_centers, argmin=True).argmin
+                cur = engine.residual_normalise(cur, ids, km.cluster_centers, [DIM])
+        self.bufs = [None] * len(self.levels)
+        self.stats = []
+
+    def step(self, i):
+        import torch
+        lvl = i % len(self.levels)
+        km, xl = self.levels[lvl]
+        score, _assign, stats, _shift = km._iterate(xl, self.n_global, self.bufs[lvl])
+        self.bufs[lvl] = score.scores_t
+        c = score.counts.to(torch.int64)
+        if self.shard is not None:
+            self.shard.all_reduce(c, "sum")
+        c.cpu()                                              # loss read-back of the fit loop (:333-341)
+        if stats is not None:
+            self.stats.append((CLUSTERS[lvl], stats))
+
+    def timed(self, warmup, steps, barrier, sampler=None):
+        import torch
+        for i in range(warmup):
+            self.step(i)
+        self.stats.clear()
+        barrier()
+        if sampler:
+            sampler.mark_begin()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(steps):
+            self.step(warmup + i)
+        ev1.record()
+        barrier()
+        if sampler:
+            sampler.mark_end()
+        return ev0.elapsed_time(ev1)
+
+    def composite(self, ms, peak, how):
+        """Per-iteration composite roofline: sum over the timed steps of (8D + 2K + 2K*R) * N bytes
+        / time, with R = bidding rounds actually EXECUTED (the reference's count is 1002 in this regime; the exact
+        fast-forward skips the rest).  Sharded runs: all ranks' bytes, against all ranks' peak."""
+        r_exec = [st.passes - st.cold_passes for _, st in self.stats]
+        by = [composite_bytes(self.n_global, k, r) for (k, _), r in zip(self.stats, r_exec)]
+        world = self.n_global // self.n
+        ach = sum(by) / (ms * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": ach, "peak": peak * world, "unit": "GB/s", "frac": ach / (peak * world),
+                "bytes_per_vector": "8*D + 2*K + 2*K*R (SURVEY.md 8d), R = bidding rounds executed",
+                "rounds_executed_per_step": r_exec, "passes_per_step": [st.passes for _, st in self.stats],
+                "list_rounds_per_step": [st.list_passes for _, st in self.stats],
+                "window_misses_per_step": [st.window_misses for _, st in self.stats],
+                "reference_rounds_per_step": [st.rounds for _, st in self.stats], "peak_source": how}
+
+
+def fit_10m_record(dev, engine, KMeans, peak, how, rows=10000000, iters=3):
+    """North-star size on ONE GPU: 10 M x 512 S-mix rows, K = 128 on the raw rows and K = 256 on their normalised
+    level-0 residual; `iters` timed fit iterations each after one warm-up iteration (generated on the device)."""
+    import numpy as np
+    import torch
+    out = {"rows": rows, "input": "S-mix (device-generated)", "iterations_timed": iters, "levels": []}
+    x = synth_device("mix", rows, dev, 0)
+    np.random.seed(42)
+    torch.manual_seed(42)
+    for k, what in ((128, "level 0 (raw rows)"), (256, "level 2 shape (normalised residual)")):
+        km = KMeans(n_clusters=k, device=dev, balanced=True)
+        km.cluster_centers = km.initialize(x)
+        sc, _, _, _ = km._iterate(x, rows)
+        buf = sc.scores_t
+        stats = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            sc, _, st, _ = km._iterate(x, rows, buf)
+            sc.counts.cpu()
+            stats.append(st)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        r_exec = [st.passes - st.cold_passes for st in stats]
+        by = sum(composite_bytes(rows, k, r) for r in r_exec)
+        ach = by / (ms * 1e-3) / 1e9
+        out["levels"].append({"k": k, "what": what, "ms_per_iteration": ms / iters, "vectors_per_s": rows * iters / (ms * 1e-3),
+                              "rounds_executed": r_exec, "reference_rounds": [st.rounds for st in stats],
+                              "list_rounds": [st.list_passes for st in stats],
+                              "composite": {"achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}})
+        if k == 128:
+            ids = engine.score_pass(x, km.cluster_centers, argmin=True).argmin
+            engine.residual_normalise(x, ids, km.cluster_centers, [DIM], out=x)
+        del buf, sc
+    out["peak_source"] = how
+    del x
+    engine.SCRATCH.clear()
+    torch.cuda.empty_cache()
+    return out
+
+
+def tf32_peak(dev):
+    """Dense TF32 tensor throughput of this GPU (cuBLAS, 8192^3), the yardstick of the 3xTF32 score pass."""
+    import torch
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn((8192, 8192), device=dev)
+        b = torch.randn((8192, 8192), device=dev)
+        for _ in range(2):
+            a @ b
+        best = 1e9
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -235,9 +450,13 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=20032, help="rows of the CPU baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-10m", action="store_true", help="skip the 10 M-row single-GPU record")
+    ap.add_argument("--no-extras", action="store_true", help="only the headline step timing (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.no_extras:
+        args.no_e2e = args.no_cpu = args.no_10m = True
 
     import numpy as np
     import torch
@@ -255,85 +474,59 @@ def main():
     shard = engine.ShardGroup() if world > 1 else None
     n = args.rows
     n_global = n * world
+    peak, how = measured_peaks()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- synthetic level inputs, resident in HBM before anything is timed ----
-    g = torch.Generator(device=dev)
-    g.manual_seed(1234 + rank)
-    x0 = torch.randn((n, DIM), device=dev, generator=g)
-    np.random.seed(42)
-    torch.manual_seed(42)
-    levels = []
-    cur = x0
-    for lvl, k in enumerate(CLUSTERS):
-        km = KMeans(n_clusters=k, device=dev, balanced=True, shard=shard)
-        km.cluster_centers = km.initialize(cur)
-        levels.append((km, cur))
-        if lvl < len(CLUSTERS) - 1:
-            km._iterate(cur, n_global)                       # one real iteration to get sensible centroids
-            ids = engine.score_pass(cur, km.cluster_centers, argmin=True).argmin
-            cur = engine.residual_normalise(cur, ids, km.cluster_centers, [DIM])
-    bufs = [None] * len(levels)
-    passes, rounds = [], []
-
-    def step(i):
-        lvl = i % len(levels)
-        km, xl = levels[lvl]
-        score, _assign, stats, _shift = km._iterate(xl, n_global, bufs[lvl])
-        bufs[lvl] = score.scores_t
-        c = score.counts.to(torch.int64)
-        if shard is not None:
-            shard.all_reduce(c, "sum")
-        c.cpu()                                              # loss read-back of the fit loop (:333-341)
-        if stats is not None:
-            passes.append(stats.passes)
-            rounds.append(stats.rounds)
-
+    # ---- headline: S-mix level inputs resident in HBM before anything is timed ----
+    wl = Workload("mix", n, world, rank, dev, shard, engine, KMeans)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()                                      # before the warm-up: it is streaming when the timed region starts
-    for i in range(args.warmup):
-        step(i)
-    passes.clear()
-    rounds.clear()
-    barrier()
-    if rank == 0:
-        sampler.mark_begin()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for i in range(args.steps):
-        step(args.warmup + i)
-    ev1.record()
-    barrier()
-    if rank == 0:
-        sampler.mark_end()
-    ms = ev0.elapsed_time(ev1)
+    ms = wl.timed(args.warmup, args.steps, barrier, sampler if rank == 0 else None)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     value = n_global * args.steps / (ms / 1e3)
+    composite = wl.composite(ms, peak, how)
+    passes = [st.passes for _, st in wl.stats]
+    rounds = [st.rounds for _, st in wl.stats]
 
     # launches of our kernels inside the timed region: per step score pass (pad, minmax, split, tc) = 4,
-    # auction init (memset + init) 2 + 5 per round (window sampling, HIST + resolve, tie prefix, bid-list replay +
-    # resolve, S-scanning BID fallback; a round = 2 passes; rounds are enqueued two at a time, one batch ahead
-    # of the host's look at the state) + finalize 1, centroid update 8
-    def auction_launches(p):
-        rounds_ = (p + 1) // 2
-        return 5 * 2 * (-(-rounds_ // 2) + 1)
-    gpu_launches = int(sum(4 + 2 + auction_launches(p) + 1 + 8 for p in passes)) if passes else 0
+    # auction init (memset + init) 2 + ROUND_LAUNCHES per enqueued round (rounds are enqueued two at a time, one
+    # batch ahead of the host's look at the state) + finalize 1, centroid update 8
+    ROUND_LAUNCHES = 5 if world == 1 else 9
+
+    def auction_launches(st):
+        rounds_ = st.passes - st.cold_passes
+        return ROUND_LAUNCHES * 2 * (-(-rounds_ // 2) + 1)
+    gpu_launches = int(sum(4 + 2 + auction_launches(st) + 1 + 8 for _, st in wl.stats))
+
+    # ---- second record: the same step on S-iso (no structure; narrower windows, fewer survivors) ----
+    s_iso = None
+    if not args.no_extras:
+        wl_iso = Workload("iso", n, world, rank, dev, shard, engine, KMeans)
+        ms_iso = wl_iso.timed(args.warmup, args.steps, barrier)
+        t = torch.tensor([ms_iso], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_iso = float(t.item())
+        s_iso = {"input": "S-iso", "value": n_global * args.steps / (ms_iso / 1e3), "unit": UNIT,
+                 "ms_per_step": ms_iso / args.steps, "composite": wl_iso.composite(ms_iso, peak, how)}
+        del wl_iso
+        torch.cuda.empty_cache()
 
     # ---- roofline of the dominant kernel: the auction's streaming HIST pass at level 0 (K=128) ----
     # It reads the K x N fp16 score matrix exactly once: 2*K bytes per vector.  The bidding half of
     # a round replays the HIST pass's survivor lists (L2-resident) and is reported beside it.
     roofline = None
     if rank == 0:
-        km, xl = levels[0]
+        km, xl = wl.levels[0]
         sc = engine.score_pass(xl, km.cluster_centers, scores=True, argmin=False)
         sess = engine.AuctionSession(sc.scores_t, n, n)
         sess.init(sc.minmax)
@@ -359,7 +552,6 @@ def main():
             prev = cur
         k0 = CLUSTERS[0]
         alg_bytes = 2.0 * k0 * n
-        peak, how = measured_peaks()
 
         def line(name, ts):
             if not ts:
@@ -371,24 +563,34 @@ def main():
                     "ms_per_launch": t, "launches_timed": len(ts), "peak_source": how}
 
         roofline = line("auction_hist_kernel (threshold select, K=128)", t_hist)
-        if roofline is not None and t_bid:
-            roofline["other_kernel"] = {
-                "kernel": "auction_bidlist_kernel (bids replayed from the HIST pass's survivor lists, K=128)",
-                "ms_per_launch": sum(t_bid) / len(t_bid), "launches_timed": len(t_bid),
-                "note": "not a stream over S: reads ~2 % of it as L2-resident lists plus cost/owner of every job; "
-                        "timed together with the early-exiting S-scanning fallback kernel"}
+        if roofline is not None:
+            if t_bid:
+                roofline["other_kernel"] = {
+                    "kernel": "auction_bidlist_kernel (bids replayed from the HIST pass's survivor lists, K=128)",
+                    "ms_per_launch": sum(t_bid) / len(t_bid), "launches_timed": len(t_bid),
+                    "note": "not a stream over S: reads ~2 % of it as L2-resident lists plus cost/owner of every job; "
+                            "timed together with the early-exiting S-scanning fallback kernel"}
+            roofline["composite"] = composite                # the per-ITERATION figure of SURVEY.md 8(d)
+            try:
+                tf = tf32_peak(dev)
+                roofline["tensor"] = {"tf32_tflops_measured": tf, "how": "torch.matmul tf32 8192^3, best of 5 (cuBLAS)",
+                                      "note": "the 3xTF32 score pass issues 3 MMAs per product: its floor is "
+                                              "3*2*K*(D+2)*N / this"}
+            except Exception as e:
+                roofline["tensor"] = {"error": repr(e)}
+        del sess, sc
 
     # ---- encode (the KMeans.predict + residual chain train() emits its ids with), rows resident in HBM ----
     encode = None
-    if rank == 0:
+    if rank == 0 and not args.no_extras:
         try:
-            cs = [km.cluster_centers for km, _ in levels]
+            cs = [km.cluster_centers for km, _ in wl.levels]
             for _ in range(2):
-                engine.encode(x0, cs, CLUSTERS, [DIM], mode=0)
+                engine.encode(wl.x0, cs, CLUSTERS, [DIM], mode=0)
             ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ee0.record()
             for _ in range(3):
-                engine.encode(x0, cs, CLUSTERS, [DIM], mode=0)
+                engine.encode(wl.x0, cs, CLUSTERS, [DIM], mode=0)
             ee1.record()
             torch.cuda.synchronize()
             t_enc = ee0.elapsed_time(ee1) / 3
@@ -398,34 +600,57 @@ def main():
             encode = {"error": repr(e)}
 
     # ---- end to end through the public API: host array in, ids out ----
+    # Headline e2e: a PAGEABLE np.ndarray, as train_semantic_ids.py:152 passes it (np.vstack of the CSV rows);
+    # `pinned` repeats it from page-locked memory.  H2D of X and D2H of the ids are inside the timed region.
     e2e = None
     if not args.no_e2e:
-        xh = torch.empty((n, DIM), dtype=torch.float32, pin_memory=True)
-        xh.copy_(x0)
-        x_np = xh.numpy()
-        del levels, bufs, cur, x0
+        x_np = wl.x0.cpu().numpy()                           # pageable
+        del wl
         engine.SCRATCH.clear()
         torch.cuda.empty_cache()
         cfg = HierarchicalRQKMeansConfig(layer_clusters=CLUSTERS, need_clusters=CLUSTERS, embedding_dim=DIM,
                                          group_dims=[DIM], hierarchical_weights=[[1.0]] * 3, iter_limit=20)
-        np.random.seed(42)
-        torch.manual_seed(42)
-        model = HierarchicalRQKMeans(cfg, device=dev, shard=shard)
-        barrier()
-        t0 = time.perf_counter()
-        out = model.train(x_np, resume=False)
-        barrier()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        iters = sum(len(s) for s in model.fit_stats)
-        ids_bytes = sum(t.numel() * t.element_size() for t in out["cluster_ids"])
-        e2e = {"value": n_global * iters / dt, "unit": UNIT, "h2d_bytes_per_step": x_np.nbytes * world / max(iters, 1),
-               "d2h_bytes_per_step": ids_bytes * world / max(iters, 1), "seconds": dt, "iterations": iters,
-               "iterations_per_level": [len(s) for s in model.fit_stats],
-               "api": "HierarchicalRQKMeans.train(np.ndarray) -> cluster_ids (int64, host), iter_limit=20"}
+
+        def run_train(x_host):
+            np.random.seed(42)
+            torch.manual_seed(42)
+            model = HierarchicalRQKMeans(cfg, device=dev, shard=shard)
+            barrier()
+            t0 = time.perf_counter()
+            out = model.train(x_host, resume=False)
+            barrier()
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+            iters = sum(len(s) for s in model.fit_stats)
+            ids_bytes = sum(t.numel() * t.element_size() for t in out["cluster_ids"])
+            return {"value": n_global * iters / dt, "unit": UNIT,
+                    "h2d_bytes_per_step": x_host.nbytes * world / max(iters, 1),
+                    "d2h_bytes_per_step": ids_bytes * world / max(iters, 1), "seconds": dt, "iterations": iters,
+                    "iterations_per_level": [len(s) for s in model.fit_stats]}
+
+        e2e = run_train(x_np)
+        e2e["host_memory"] = "pageable np.ndarray"
+        e2e["api"] = "HierarchicalRQKMeans.train(np.ndarray) -> cluster_ids (int64, host), iter_limit=20"
+        xh = torch.empty((n, DIM), dtype=torch.float32, pin_memory=True)
+        xh.copy_(torch.from_numpy(x_np))
+        del x_np
+        pinned = run_train(xh.numpy())
+        e2e["pinned"] = {"value": pinned["value"], "seconds": pinned["seconds"], "host_memory": "page-locked"}
+        del xh
+    else:
+        del wl
+    engine.SCRATCH.clear()
+    torch.cuda.empty_cache()
+
+    fit_10m = None
+    if rank == 0 and world == 1 and not args.no_10m:
+        try:
+            fit_10m = fit_10m_record(dev, engine, KMeans, peak, how)
+        except Exception as e:
+            fit_10m = {"error": repr(e)}
 
     if rank == 0:
         cpu = None
@@ -436,7 +661,9 @@ def main():
                 "vs_baseline": None, "dtype": "3xTF32 distance (fp32 accumulate), fp16 auction, fp32 centroids",
                 "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
                 "gpu_launches": gpu_launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
-                "auction": {"passes_per_step": passes, "reference_rounds_per_step": rounds}, "encode": encode}
+                "auction": {"passes_per_step": passes, "reference_rounds_per_step": rounds,
+                            "rounds_executed_per_step": composite["rounds_executed_per_step"]},
+                "s_iso": s_iso, "fit_10m": fit_10m, "encode": encode}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -379,14 +379,26 @@ class KMeans(object):
         min_loss, best = float("inf"), None
         pending = None      # centroids of the previous iteration whose loss is not known yet
         self.last_fit_stats = []
+        # tests: `trace_fit = True` records, per iteration, the centroids it produced, their loss (:326-336) and whether
+        # they became the running best (:338-341), so the deferred loss scheme can be checked against direct passes
+        trace = [] if getattr(self, "trace_fit", False) else None
+        self.last_fit_trace = trace
         scores_buf = None
+
+        def settle(loss: int, centers: torch.Tensor, idx: int):
+            """:338-341 for iteration `idx` (`<=`: a later iteration with an equal loss wins)."""
+            nonlocal min_loss, best
+            took = loss <= min_loss
+            if took:
+                min_loss, best = loss, centers
+            if trace is not None:
+                trace[idx].update(loss=loss, became_best=took)
+
         while True:
             reinit = iteration > 0 and iteration % 10 == 0             # :305
             if reinit:
                 if pending is not None:                                # loss of the centres we are about to drop
-                    loss = loss_of(counts_of(pending))
-                    if loss <= min_loss:
-                        min_loss, best = loss, pending
+                    settle(loss_of(counts_of(pending)), pending, iteration - 1)
                     pending = None
                 self.cluster_centers = self._rows(X, self._draw(n_global), n_global, row0)
             score, assign, stats, shift = self._iterate(X, n_global, scores_buf)
@@ -394,11 +406,11 @@ class KMeans(object):
             if pending is not None:                                    # :327-341 for the previous iteration
                 c = score.counts.to(torch.int64)
                 shard.all_reduce(c, "sum")
-                loss = loss_of(c.cpu().numpy())
-                if loss <= min_loss:                                   # `<=`: later ties win
-                    min_loss, best = loss, pending
+                settle(loss_of(c.cpu().numpy()), pending, iteration - 1)
                 pending = None
             pending = self.cluster_centers.clone()
+            if trace is not None:
+                trace.append({"iteration": iteration, "reinit": reinit, "centers": pending, "shift": shift})
             iteration += 1
             self.last_fit_stats.append({"iteration": iteration, "shift": shift,
                                         "rounds": stats.rounds if stats else 0,
@@ -407,9 +419,7 @@ class KMeans(object):
                 break
             if iter_limit != 0 and iteration >= iter_limit:            # :361
                 break
-        loss = loss_of(counts_of(pending))                                 # loss of the final iteration
-        if loss <= min_loss:
-            min_loss, best = loss, pending
+        settle(loss_of(counts_of(pending)), pending, iteration - 1)        # loss of the final iteration
         self.cluster_centers = best                                        # :364
         self.min_loss = min_loss
         return

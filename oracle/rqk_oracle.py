@@ -62,6 +62,8 @@ def lib():
         L.rqk_oracle_auction_half.restype = ctypes.c_int
         L.rqk_oracle_auction_half_t.argtypes = [p, i64, i64, p, i64, ctypes.POINTER(_AuctionInfo)]
         L.rqk_oracle_auction_half_t.restype = ctypes.c_int
+        L.rqk_oracle_auction_half_t_fast.argtypes = [p, i64, i64, p, i64, ctypes.POINTER(_AuctionInfo)]
+        L.rqk_oracle_auction_half_t_fast.restype = ctypes.c_int
         for name in ("rqk_oracle_f2h", "rqk_oracle_h2f"):
             getattr(L, name).argtypes = [p, p, i64]
             getattr(L, name).restype = None
@@ -197,16 +199,18 @@ def auction_lap_half(scores: np.ndarray, max_rounds: int = 0) -> AuctionResult:
                          bool(info.fallback_used), eps)
 
 
-def auction_lap_half_t(s_bits_t: np.ndarray, max_rounds: int = 0) -> AuctionResult:
+def auction_lap_half_t(s_bits_t: np.ndarray, max_rounds: int = 0, fast: bool = False) -> AuctionResult:
     """Same, on an already rounded and transposed [K, N] fp16 bit matrix (teacher-forced input for
-    the GPU auction: identical fp16 in, identical int64 out)."""
+    the GPU auction: identical fp16 in, identical int64 out).  fast=True: the bookkeeping-only variant
+    `rqk_oracle_auction_half_t_fast` (no materialised bid matrix, hardware fp16 conversion), pinned bit for
+    bit to the literal one by tests/test_oracle_golden.py; the BASELINE-size GPU tests use it."""
     s = np.ascontiguousarray(s_bits_t, dtype=np.uint16)
     k, n = s.shape
     assert n >= k
     assign = np.empty(n, dtype=np.int64)
     info = _AuctionInfo()
-    rc = lib().rqk_oracle_auction_half_t(s.ctypes.data, k, n, assign.ctypes.data, max_rounds,
-                                         ctypes.byref(info))
+    fn = lib().rqk_oracle_auction_half_t_fast if fast else lib().rqk_oracle_auction_half_t
+    rc = fn(s.ctypes.data, k, n, assign.ctypes.data, max_rounds, ctypes.byref(info))
     if rc not in (0, -2):
         raise RuntimeError(f"oracle auction failed rc={rc}")
     eps = float(h2f(np.array([info.eps_bits], dtype=np.uint16))[0])

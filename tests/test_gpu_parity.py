@@ -95,7 +95,11 @@ def test_score_pass_farthest_quirk(dev, engine):
     c = O.synth_mix(64, 64, seed=4)
     r = engine.score_pass(torch.from_numpy(x).to(dev), torch.from_numpy(c).to(dev), argmin=True, farthest=True)
     want = O.auction_lap_half(-O.pairwise_distance_full(x, c)).assignment
-    assert (r.argmin.cpu().numpy() == want).mean() > 0.98
+    got = r.argmin.cpu().numpy()
+    d64 = np.sort(O.distance_exact64(x, c), axis=1)
+    near = (d64[:, -1] - d64[:, -2]) / d64[:, -1] < NEAR_TIE             # top-2 LARGEST distances within 1e-5
+    print(f"farthest quirk: {near.sum()} near-ties excluded of {len(x)}")
+    assert ((got != want) & ~near).sum() == 0
 
 
 def test_score_rows_do_not_depend_on_tile_position(dev, engine):
@@ -362,17 +366,22 @@ def test_residual_normalise(dev, engine, n, dim, groups):
 # ------------------------------------------------------------------------------------------------
 # encode / predict against the reference's own outputs
 # ------------------------------------------------------------------------------------------------
-def test_encode_matches_reference_fixture(dev, engine, golden_dir):
+def test_encode_matches_reference_fixture(dev, engine, golden_dir, record_property):
+    """ids of the reference's own train() chain and predict() (fixture): bit-exact outside near-ties, which are
+    excluded by the fp64 rule of tests/_parity_util.py and COUNTED (a flip at level l excuses later levels)."""
+    import _parity_util as P
     g = np.load(os.path.join(golden_dir, "encode.npz"))
     x = O.synth_mix(int(g["n"]), int(g["dim"]), seed=int(g["seed"]), modes=int(g["modes"]))
     centers = [g["c0"], g["c1"], g["c2"]]
     cd = [torch.from_numpy(c).to(dev) for c in centers]
     xd = torch.from_numpy(x).to(dev)
-    dim = int(g["dim"])
+    dim, needs = int(g["dim"]), [int(v) for v in g["clusters"]]
     for mode, key in ((0, "train_ids"), (1, "predict_ids")):
-        ids = engine.encode(xd, cd, [int(v) for v in g["clusters"]], [dim], None, mode=mode).t().cpu().numpy()
-        ok = np.cumprod(ids == g[key], axis=1).astype(bool)       # a flip at level l excuses later levels
-        assert ok[:, 0].mean() >= 0.9998 and ok[:, 2].mean() >= 0.999, (mode, ok.mean(0))
+        ids = engine.encode(xd, cd, needs, [dim], None, mode=mode).t().cpu().numpy()
+        res = P.chain_mismatches(x, centers, ids, g[key], [dim], None, predict_mode=(mode == 1), needs=needs)
+        P.report(record_property, f"encode_fixture_{key}", res)
+        assert sum(res["bad"]) == 0, res
+        assert sum(res["excluded"]) <= 0.002 * len(x), res
     assert (g["predict_ids"][:, 1] != g["train_ids"][:, 1]).any()   # the +10000 quirk is really exercised
 
 
@@ -390,14 +399,18 @@ def test_predict_api_and_weights(dev, engine):
     ids = np.column_stack([t.numpy() for t in out["cluster_ids"]])
     assert ids.dtype == np.int64 and ids.shape == (n, 3) and not out["cluster_ids"][0].is_cuda
     centers = [c.cpu().numpy() for c in out["cluster_centers"]]
+    import _parity_util as P
     chain = np.column_stack(O.encode_train_chain(x, centers, cfg.group_dims, cfg.hierarchical_weights))
-    ok = np.cumprod(ids == chain, axis=1).astype(bool)
-    assert ok[:, 0].mean() > 0.999 and ok[:, 2].mean() > 0.99
+    res = P.chain_mismatches(x, centers, ids, chain, cfg.group_dims, cfg.hierarchical_weights)
+    P.report(None, "train_ids_weighted", res)
+    assert sum(res["bad"]) == 0 and sum(res["excluded"]) <= 0.005 * n, res
     assert np.array_equal(m.encode_like_train(x), ids)
     pred = m.predict(x)
     want = O.predict_hierarchy(x, centers, cfg.need_clusters, cfg.group_dims, cfg.hierarchical_weights)
-    okp = np.cumprod(pred == want, axis=1).astype(bool)
-    assert pred.dtype == np.int64 and okp[:, 0].mean() > 0.999 and okp[:, 2].mean() > 0.98
+    resp = P.chain_mismatches(x, centers, pred, want, cfg.group_dims, cfg.hierarchical_weights, predict_mode=True,
+                              needs=cfg.need_clusters)
+    P.report(None, "predict_ids_weighted", resp)
+    assert pred.dtype == np.int64 and sum(resp["bad"]) == 0 and sum(resp["excluded"]) <= 0.01 * n, resp
 
 
 # ------------------------------------------------------------------------------------------------

@@ -1,0 +1,289 @@
+"""Parity at BASELINE sizes: the CUDA path against the CPU oracle (not against properties) at the sizes the
+reference's own configurations name - 100 000 x 512 (BASELINE config 1: N % K = 32 / 160, the 1002-round regime),
+1 000 000 x 128 scores (config 2), K*N > 2^31 (config 3/5: 64-bit offsets, > 296 CTAs), and the 4-level
+[256,256,256,256] codebook (config 5) - on both synthetic inputs of SURVEY.md section 8d (S-mix primary, S-iso).
+
+The oracle simulates every one of the reference's 1002 auction rounds (tens of seconds per case on the box's host
+cores; the 1 M case minutes), so the results of one oracle run are shared by the two bidding paths."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import _parity_util as P
+from oracle import rqk_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from generative_ranking_recommender_b200 import _lib
+    _lib.require_device(0)
+    O.set_threads(os.cpu_count() or 1)        # torchrun / the harness may have set OMP_NUM_THREADS=1
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def engine(dev):
+    from generative_ranking_recommender_b200 import engine as e
+    return e
+
+
+def _synth(kind: str, n: int, dim: int = 512) -> np.ndarray:
+    return O.synth_mix(n, dim) if kind == "mix" else O.synth_iso(n, dim)
+
+
+_CACHE = {}
+
+
+def _stage(dev, engine, kind, n, k):
+    """GPU score pass + the oracle's answers for it, computed once per (input, n, k)."""
+    key = (kind, n, k)
+    if key not in _CACHE:
+        _CACHE.clear()                                   # one case resident at a time
+        x = _synth(kind, n)
+        c0 = x[np.random.default_rng(k).choice(n, k, replace=False)].copy()
+        xd, cd = torch.from_numpy(x).to(dev), torch.from_numpy(c0).to(dev)
+        r = engine.score_pass(xd, cd, scores=True, argmin=True, counts=True)
+        s_gpu = np.ascontiguousarray(r.scores_t[:, :n].cpu().numpy().view(np.uint16))
+        ref = O.auction_lap_half_t(s_gpu, fast=True)     # identical fp16 in; simulates every round
+        _CACHE[key] = dict(x=x, c0=c0, xd=xd, cd=cd, r=r, s_gpu=s_gpu, ref=ref)
+    return _CACHE[key]
+
+
+@pytest.fixture(params=["lists", "scan"])
+def bid_path(request, monkeypatch):
+    if request.param == "scan":
+        monkeypatch.setenv("RQK_AUCTION_NO_LIST", "1")
+    else:
+        monkeypatch.delenv("RQK_AUCTION_NO_LIST", raising=False)
+    return request.param
+
+
+@pytest.mark.parametrize("k", [128, 256])
+@pytest.mark.parametrize("kind", ["mix", "iso"])
+def test_iteration_teacher_forced_at_config1_size(dev, engine, kind, k, bid_path, record_property):
+    """One full fit iteration at 100 000 x 512 (N % K != 0), stage by stage against the oracle."""
+    n = 100000
+    st = _stage(dev, engine, kind, n, k)
+    x, c0, r, ref = st["x"], st["c0"], st["r"], st["ref"]
+    # -- score pass vs the reference's distance: fp16 entries equal up to rounding-boundary cases, never > 1 ulp
+    d = O.pairwise_distance_full(x, c0, 100000)
+    s_ref = O.score_matrix_half_t(d)
+    same = (st["s_gpu"] == s_ref)
+    d64 = O.distance_exact64(x, c0)
+    scale = (x.astype(np.float64) ** 2).sum(1)[:, None] + (c0.astype(np.float64) ** 2).sum(1)[None, :]
+    well = (d64 ** 2 >= 0.05 * scale).T
+    assert same[well].mean() >= 0.999
+    assert np.abs(st["s_gpu"].astype(np.int32) - s_ref.astype(np.int32))[well].max() <= 1
+    res = P.count_mismatch_report(r.argmin.cpu().numpy(), d, x, c0)
+    P.report(record_property, f"argmin_{kind}_{k}", res)
+    assert res["bad"] == [0]
+    # -- auction: bit-exact on the identical fp16 matrix, through this bidding path
+    a, stats = engine.auction(r.scores_t, n, r.minmax)
+    a = a.cpu().numpy().astype(np.int64)
+    record_property(f"auction_{kind}_{k}_{bid_path}",
+                    f"passes {stats.passes}, list passes {stats.list_passes}, window misses {stats.window_misses}, "
+                    f"oracle ambiguous (round, worker) pairs {ref.ambiguous_rounds}")
+    print(f"auction {kind} K={k} {bid_path}: passes {stats.passes}, list passes {stats.list_passes}, "
+          f"window misses {stats.window_misses}")
+    assert np.array_equal(a, ref.assignment), f"{(a != ref.assignment).sum()} of {n} assignments differ"
+    assert stats.rounds == ref.rounds == 1002 and stats.frozen_exit and abs(stats.eps - ref.eps) == 0
+    sizes = np.bincount(a, minlength=k)
+    assert sizes[0] == n // k + n % k and (sizes[1:] == n // k).all()
+    if bid_path == "scan":
+        return                                           # the rest does not depend on the bidding path
+    # -- centroid update on that assignment: <= 1e-6 of fp64, and the oracle's fp32 result within the north-star 1e-4
+    ad = torch.from_numpy(ref.assignment.astype(np.int32)).to(dev)
+    sums, counts = engine.centroid_accumulate(st["xd"], ad, k)
+    c1d = st["cd"].clone()
+    out, _ = engine.centroid_finalize(sums, counts, c1d)
+    c1 = O.update_centers(x, ref.assignment, c0)
+    got = c1d.cpu().numpy()
+    ref64 = np.stack([x[ref.assignment == i].astype(np.float64).mean(0) for i in range(k)])
+    assert np.abs(got - ref64).max() <= 1e-6 * np.abs(ref64).max()
+    assert np.abs(got - c1).max() <= 1e-4 * np.abs(c1).max()
+    assert abs(out[0].item() - O.center_shift(c1, c0)) <= 1e-5 * O.center_shift(c1, c0)
+    # -- loss evaluation (:326-336) on the new centres: argmin counts exact outside near-ties
+    r2 = engine.score_pass(st["xd"], torch.from_numpy(c1).to(dev), argmin=True, counts=True)
+    d2 = O.pairwise_distance_full(x, c1, 100000)
+    res = P.count_mismatch_report(r2.argmin.cpu().numpy(), d2, x, c1)
+    P.report(record_property, f"loss_argmin_{kind}_{k}", res)
+    assert res["bad"] == [0]
+    cnt_ref = np.bincount(np.argmin(d2, axis=1), minlength=k)
+    assert np.abs(r2.counts.cpu().numpy() - cnt_ref).sum() <= 2 * res["excluded"][0]
+
+
+def test_auction_bit_exact_at_one_million_jobs(dev, engine, record_property):
+    """1 000 000 x 128 (BASELINE config 2, N % K = 64): the GPU's fp16 score matrix through the oracle's 1002
+    simulated rounds (minutes of host time) and through the GPU auction (tens of milliseconds)."""
+    n, k = 1000000, 128
+    st = _stage(dev, engine, "mix", n, k)
+    a, stats = engine.auction(st["r"].scores_t, n, st["r"].minmax)
+    a = a.cpu().numpy().astype(np.int64)
+    ref = st["ref"]
+    print(f"1M auction: passes {stats.passes}, list passes {stats.list_passes}, misses {stats.window_misses}")
+    record_property("auction_1m", f"passes {stats.passes}, list passes {stats.list_passes}, window misses "
+                                  f"{stats.window_misses}, ambiguous {ref.ambiguous_rounds}")
+    assert np.array_equal(a, ref.assignment), f"{(a != ref.assignment).sum()} of {n} assignments differ"
+    assert stats.rounds == ref.rounds == 1002 and stats.frozen_exit
+    _CACHE.clear()
+
+
+def _emulate_sharded(engine, scores_t, n, k, minmax, split, dev):
+    """The multi-GPU step-function protocol for `split` virtual ranks on one GPU (each owns a column block of the
+    score matrix, so every block has K*n_local < 2^31: an independent route to the same assignment)."""
+    bounds = np.linspace(0, n, split + 1).astype(np.int64)
+    bounds[1:-1] += 37
+    sess = []
+    for r in range(split):
+        lo, hi = int(bounds[r]), int(bounds[r + 1])
+        blk = torch.full((k, engine.pad_ld(hi - lo)), float("-inf"), dtype=torch.float16, device=dev)
+        blk[:, :hi - lo] = scores_t[:, lo:hi]
+        sess.append(engine.AuctionSession(blk, hi - lo, n))
+        sess[-1].init(minmax)
+    for _ in range(3000):
+        allk = torch.stack([q.sample_collect(4096 // split) for q in sess])
+        for q in sess:
+            q.sample_window(allk)
+        for q in sess:
+            q.do_pass(2)
+        total = sum(q.reduce_block.clone() for q in sess)
+        for q in sess:
+            q.reduce_block.copy_(total)
+            q.resolve(0)
+        tt = torch.stack([q.tie_total.clone() for q in sess])
+        for r, q in enumerate(sess):
+            q.tie_offset(tt, r)
+            q.do_pass(4)
+        tail = sum(q.reduce_block[-2:].clone() for q in sess)
+        for q in sess:
+            q.reduce_block[-2:].copy_(tail)
+            q.resolve(1)
+        info = sess[0].poll()
+        if info.done:
+            return torch.cat([q.finalize() for q in sess]), info
+    raise AssertionError("sharded emulation did not terminate")
+
+
+@pytest.mark.parametrize("n,k,split", [(8400077, 256, 3), (20000100, 128, 4)])
+def test_routes_agree_beyond_2_to_31_entries(dev, engine, n, k, split, monkeypatch, record_property):
+    """K*N > 2^31 (64-bit offsets into S; at 20 M jobs also more than 296 CTA ranges with 16-bit per-CTA counters).
+    The oracle would need ~30 min here, so oracle equality is pinned at 1 M jobs (above) and this size is checked
+    by bit-equality of three independent GPU routes: survivor-list replay, the S-scanning bidding kernel, and the
+    sharded protocol over virtual ranks whose blocks all stay below 2^31 entries."""
+    assert n * k > 2 ** 31
+    g = torch.Generator(device=dev)
+    g.manual_seed(n)
+    x = torch.randn((n, 512), device=dev, generator=g)
+    c = x[torch.randperm(n, device=dev, generator=g)[:k]].clone()
+    sc = engine.score_pass(x, c, scores=True, argmin=False)
+    del x
+    torch.cuda.empty_cache()
+    monkeypatch.delenv("RQK_AUCTION_NO_LIST", raising=False)
+    a1, s1 = engine.auction(sc.scores_t, n, sc.minmax)
+    monkeypatch.setenv("RQK_AUCTION_NO_LIST", "1")
+    a2, s2 = engine.auction(sc.scores_t, n, sc.minmax)
+    monkeypatch.delenv("RQK_AUCTION_NO_LIST", raising=False)
+    a3, i3 = _emulate_sharded(engine, sc.scores_t, n, k, sc.minmax, split, dev)
+    record_property(f"routes_{n}_{k}", f"lists: passes {s1.passes} (list {s1.list_passes}); scan: passes {s2.passes}; "
+                                       f"sharded x{split}: passes {i3.passes}")
+    print(f"n={n} k={k}: list route {s1.passes} passes ({s1.list_passes} from lists), scan route {s2.passes}, "
+          f"sharded x{split} {i3.passes}")
+    assert s1.list_passes > 0 and s2.list_passes == 0
+    assert torch.equal(a1, a2), "list replay and S scan disagree"
+    assert torch.equal(a1, a3), "unsharded and sharded routes disagree"
+    assert s1.rounds == s2.rounds == i3.rounds
+    sizes = torch.bincount(a1.long(), minlength=k)
+    assert sizes[0].item() == n // k + n % k and (sizes[1:] == n // k).all()
+
+
+def test_four_level_256_codebook(dev, engine, record_property):
+    """BASELINE config 5's codebook [256,256,256,256] through train() + predict() at 100 000 x 512 (S-mix):
+    ids bit-exact to the oracle's chains on the trained centroids outside counted near-ties (protocol P1)."""
+    from generative_ranking_recommender_b200 import HierarchicalRQKMeans, HierarchicalRQKMeansConfig
+    n, dim, cl = 100000, 512, [256, 256, 256, 256]
+    x = O.synth_mix(n, dim)
+    cfg = HierarchicalRQKMeansConfig(layer_clusters=cl, need_clusters=cl, embedding_dim=dim, group_dims=[dim],
+                                     hierarchical_weights=[[1.0]] * 4, iter_limit=20)
+    np.random.seed(42)
+    torch.manual_seed(42)
+    m = HierarchicalRQKMeans(cfg, device=dev)
+    out = m.train(x, resume=False)
+    assert [len(s) for s in m.fit_stats] == [20, 20, 18, 18]               # :288-366 at 100 k rows, base 20
+    assert all(s["rounds"] == 1002 for lvl in m.fit_stats for s in lvl)    # N % 256 = 160: the fallback regime
+    ids = np.column_stack([t.numpy() for t in out["cluster_ids"]])
+    assert ids.shape == (n, 4) and ids.dtype == np.int64 and ids.min() == 0 and ids.max() == 255
+    centers = [c.cpu().numpy() for c in out["cluster_centers"]]
+    w = [[1.0]] * 4
+    chain = np.column_stack(O.encode_train_chain(x, centers, [dim], w))
+    res = P.chain_mismatches(x, centers, ids, chain, [dim], w)
+    P.report(record_property, "train_ids_256x4", res)
+    assert sum(res["bad"]) == 0 and sum(res["excluded"]) <= 0.002 * n
+    pred = m.predict(x)
+    want = O.predict_hierarchy(x, centers, cl, [dim], w)
+    resp = P.chain_mismatches(x, centers, pred, want, [dim], w, predict_mode=True, needs=cl)
+    P.report(record_property, "predict_ids_256x4", resp)
+    assert sum(resp["bad"]) == 0 and sum(resp["excluded"]) <= 0.01 * n
+    st = O.collision_stats(ids)
+    record_property("collisions_256x4", str(st))
+    assert st["unique_ids"] >= 0.999 * n                                   # 2^32 codes for 1e5 songs
+
+
+def test_four_level_fit_statistics_overlap_oracle(dev, engine, record_property):
+    """Protocol P3 for a 4-level codebook at a size the oracle fits in seconds (N % K == 0: terminating auctions):
+    collision statistics of the GPU fit inside the oracle's spread over seeds."""
+    from generative_ranking_recommender_b200 import HierarchicalRQKMeans, HierarchicalRQKMeansConfig
+    n, dim, cl = 8192, 64, [16, 16, 16, 16]
+    x = O.synth_mix(n, dim, seed=77, modes=256)
+    w = [[1.0]] * 4
+    mine, ref = [], []
+    for seed in (1, 2, 3):
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+        ids_o, _, _ = O.train_direct(x, cl, [dim], w, iter_limit=20)
+        so = O.collision_stats(np.column_stack(ids_o))
+        ref.append([so["unique_ids"], so["colliding_ids"], so["max_collision"]])
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+        cfg = HierarchicalRQKMeansConfig(layer_clusters=cl, need_clusters=cl, embedding_dim=dim, iter_limit=20)
+        out = HierarchicalRQKMeans(cfg, device=dev).train(x, resume=False)
+        sg = O.collision_stats(np.column_stack([t.numpy() for t in out["cluster_ids"]]))
+        mine.append([sg["unique_ids"], sg["colliding_ids"], sg["max_collision"]])
+    mine, ref = np.array(mine, float), np.array(ref, float)
+    record_property("fit_stats_16x4", f"gpu {mine.tolist()} oracle {ref.tolist()}")
+    print("gpu", mine.tolist(), "oracle", ref.tolist())
+    assert abs(mine[:, 0].mean() - ref[:, 0].mean()) < 0.02 * n
+    assert 0.5 * ref[:, 1].min() <= mine[:, 1].mean() <= 2.0 * ref[:, 1].max() + 8
+    assert mine[:, 2].max() <= 2 * ref[:, 2].max() + 2
+
+
+def test_deferred_loss_equals_direct_evaluation(dev, engine):
+    """fit_by_min_loss reads the loss of iteration i from the score pass of iteration i+1 (or an extra pass at a
+    re-initialisation / at the end).  On real data, with re-inits inside the run: every recorded loss must equal
+    the loss recomputed directly from that iteration's recorded centroids (:326-336), the returned centroids must
+    be the LAST iteration attaining the minimum (:338 `<=`), and the iteration count must follow :359-362."""
+    from generative_ranking_recommender_b200.balancekmeans import KMeans
+    n, k, target = 30000, 32, 900                     # 30000 / 32 = 937.5: losses are sensitive and non-trivial
+    x = torch.from_numpy(O.synth_mix(n, 128, seed=5, modes=96)).to(dev)
+    np.random.seed(9)
+    torch.manual_seed(9)
+    km = KMeans(n_clusters=k, device=dev, balanced=True)
+    km.trace_fit = True
+    km.fit_by_min_loss(x, target_nodes_num=target, iter_limit=25, tqdm_flag=False)
+    tr = km.last_fit_trace
+    assert len(tr) > 11 and [t["reinit"] for t in tr] == [i in (10, 20) for i in range(len(tr))]
+    assert len(tr) == 25 or tr[-1]["shift"] ** 2 < 1e-3                    # :359-362
+    direct = []
+    for t in tr:
+        cnt = engine.score_pass(x, t["centers"], argmin=True, counts=True).counts.cpu().numpy().astype(np.int64)
+        direct.append(int(np.maximum(cnt - target, 0).sum()))
+    assert [t["loss"] for t in tr] == direct
+    assert len(set(direct)) > 3, "losses must vary for the test to mean anything"
+    best = max(i for i, v in enumerate(direct) if v == min(direct))
+    assert torch.equal(km.cluster_centers, tr[best]["centers"]) and km.min_loss == direct[best]
+    assert all(t["shift"] ** 2 >= 1e-3 for t in tr[:-1])

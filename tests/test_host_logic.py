@@ -198,3 +198,79 @@ def test_legacy_choice_is_numpy_global_choice(n, k, seed):
     assert np.array_equal(got1, want1) and np.array_equal(got2, want2)
     np.random.set_state(st)
     assert np.array_equal(np.random.rand(4), tail)
+
+
+# ------------------------------------------------------------------------------------------------
+# fit_by_min_loss loop control (reference balancekmeans/__init__.py:304-364), deterministic: the device work is
+# scripted, so only the control flow is under test - the loss of iteration i is read one iteration later from the
+# fused score pass, through an extra pass when a re-initialisation (:305-306) or the end of the loop intervenes
+# ------------------------------------------------------------------------------------------------
+def _reference_control(losses, shifts, tol, iter_limit):
+    """:304-364 restated: (index of the iteration whose centroids are returned, number of iterations run)."""
+    best, min_loss, it = None, float("inf"), 0
+    while True:
+        if losses[it] <= min_loss:                                         # :338 (ties: the later iteration wins)
+            min_loss, best = losses[it], it
+        it += 1
+        if shifts[it - 1] ** 2 < tol:                                      # :359
+            break
+        if iter_limit != 0 and it >= iter_limit:                           # :361
+            break
+    return best, it
+
+
+@pytest.mark.parametrize("case", [
+    dict(losses=[9, 7, 7, 8, 5, 5, 6, 9, 9, 9, 4, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 3, 3, 9], limit=24),   # two re-inits
+    dict(losses=[5, 4, 3, 2, 1, 1, 1, 1, 1, 1, 7, 7], limit=12),          # best sits right before a re-init
+    dict(losses=[5, 5, 5, 5, 5, 5, 5, 5, 5, 5], limit=10),                # all equal: the last one wins; loop ends ON a boundary
+    dict(losses=[3, 2, 9, 9, 9, 9], limit=0, stop_at=3),                  # tol stop, unlimited iterations
+    dict(losses=[0, 4, 4], limit=3),                                      # zero loss first
+    dict(losses=list(range(30, 0, -1)), limit=30),                        # monotone: the final extra pass decides
+])
+def test_fit_by_min_loss_loop_control_is_the_reference(case, monkeypatch):
+    from generative_ranking_recommender_b200 import balancekmeans as bk
+    from generative_ranking_recommender_b200 import engine
+
+    losses, limit = case["losses"], case["limit"]
+    shifts = [1.0] * len(losses)
+    if "stop_at" in case:
+        shifts[case["stop_at"]] = 1e-3                                     # shift^2 = 1e-6 < tol
+    target = 100
+
+    def counts_for(tag: float) -> torch.Tensor:
+        # centroids produced by iteration t are tagged t >= 0; seed rows are tagged < 0 and would read as loss 0
+        # ("always best") if the loop ever mistook the fused pass over fresh seeds for a loss evaluation
+        loss = losses[int(tag)] if tag >= 0 else 0
+        return torch.tensor([target + loss, 0], dtype=torch.int32)
+
+    class Scripted(bk.KMeans):
+        it, inits = 0, 0
+
+        def _global_rows(self, n_local):
+            return n_local, 0
+
+        def _draw(self, n):
+            return np.zeros(2, dtype=np.int64)
+
+        def _rows(self, X, idx, n_global, row0):
+            self.inits += 1
+            return torch.full((2, 1), -float(self.inits))
+
+        def _iterate(self, X, n_global, scores_buf=None):
+            counts = counts_for(float(self.cluster_centers[0, 0]))          # fused pass: counts of the CURRENT centres
+            self.cluster_centers = torch.full((2, 1), float(self.it))       # ... then the update
+            self.it += 1
+            return engine.ScoreResult(counts=counts), None, None, shifts[self.it - 1]
+
+    monkeypatch.setattr(bk, "_cuda_device", lambda d: torch.device("cpu"))
+    monkeypatch.setattr(bk.engine, "score_pass",
+                        lambda X, c, **kw: engine.ScoreResult(counts=counts_for(float(c[0, 0]))))
+    km = Scripted(n_clusters=2, device=torch.device("cpu"), balanced=True)
+    km.trace_fit = True
+    km.fit_by_min_loss(torch.zeros(8, 1), target_nodes_num=target, tol=1e-3, tqdm_flag=False, iter_limit=limit)
+    want_best, want_iters = _reference_control(losses, shifts, 1e-3, limit)
+    assert km.it == want_iters
+    assert int(km.cluster_centers[0, 0]) == want_best and km.min_loss == losses[want_best]
+    assert km.inits == 1 + (want_iters - 1) // 10                           # :295 + one re-init per 10 iterations (:305)
+    assert [t["loss"] for t in km.last_fit_trace] == losses[:want_iters]    # every iteration's loss was evaluated, once
+    assert [t["reinit"] for t in km.last_fit_trace] == [i > 0 and i % 10 == 0 for i in range(want_iters)]

@@ -65,6 +65,41 @@ def test_auction_matches_reference_on_tie_free_inputs(golden_dir):
     assert n_nondiv >= 5 and n_small >= 3
 
 
+def test_fast_auction_variant_is_the_literal_one(golden_dir):
+    """`rqk_oracle_auction_half_t_fast` (no materialised bid matrix, hardware fp16 conversion; what the
+    BASELINE-size GPU tests use) against the literal restatement, bit for bit - assignment, rounds, the number
+    of canonical-tie decisions, the fallback flag, eps - and against the reference's own golden vectors."""
+    rng = np.random.default_rng(3)
+
+    def both(s):
+        a, b = O.auction_lap_half_t(s), O.auction_lap_half_t(s, fast=True)
+        assert np.array_equal(a.assignment, b.assignment)
+        assert (a.rounds, a.ambiguous_rounds, a.fallback_used, a.eps) == (b.rounds, b.ambiguous_rounds, b.fallback_used, b.eps)
+        return a
+
+    regimes = set()
+    for n, k, dim in [(64, 4, 16), (130, 4, 16), (1000, 8, 32), (4100, 16, 32), (4096, 16, 32), (6001, 32, 32),
+                      (2600, 256, 16), (300, 256, 16), (256, 256, 16)]:
+        x = O.synth_mix(n, dim, seed=n, modes=max(8, k))
+        c = x[rng.choice(n, k, replace=False)]
+        r = both(O.score_matrix_half_t(O.pairwise_distance_full(x, c)))
+        regimes.add((r.rounds == 1002, r.ambiguous_rounds > 0))
+    assert regimes >= {(True, True), (False, True), (True, False)}
+    for n, k in [(3000, 16), (3003, 16), (1024, 8)]:                     # few distinct values: ties decide everything
+        both(-(rng.integers(0, 12, size=(k, n)) * 0.25).astype(np.float16).view(np.uint16))
+    both(np.full((8, 1024), np.float16(-1.5)).view(np.uint16))
+    g = _load(golden_dir, "auction.npz")
+    so = ao = 0
+    for (n, k), rounds in zip(g["shapes"], g["rounds"]):
+        sc = g["scores"][so:so + n * k].reshape(n, k)
+        ref = g["assign"][ao:ao + n]
+        so += n * k
+        ao += n
+        if n >= k:
+            res = O.auction_lap_half_t(O.score_matrix_half_t(-sc), fast=True)
+            assert np.array_equal(res.assignment, ref) and res.rounds == rounds
+
+
 def test_distance_matches_reference(golden_dir):
     g = _load(golden_dir, "distance.npz")
     d = O.pairwise_distance_full(g["x"], g["c"])
