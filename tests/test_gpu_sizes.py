@@ -231,7 +231,9 @@ def test_four_level_256_codebook(dev, engine, record_property):
     assert sum(resp["bad"]) == 0 and sum(resp["excluded"]) <= 0.01 * n
     st = O.collision_stats(ids)
     record_property("collisions_256x4", str(st))
-    assert st["unique_ids"] >= 0.999 * n                                   # 2^32 codes for 1e5 songs
+    # S-mix has 1024 modes and the noise is isotropic, so every level's clustering follows the mode: the number of
+    # distinct codes is of the order of the number of modes - for the oracle's chain on these centroids just the same
+    assert st == O.collision_stats(chain) and st["unique_ids"] >= 1024
 
 
 def test_four_level_fit_statistics_overlap_oracle(dev, engine, record_property):
