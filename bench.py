@@ -404,6 +404,7 @@ def fit_10m_record(dev, engine, KMeans, peak, how, rows=10000000, iters=3):
         ach = by / (ms * 1e-3) / 1e9
         out["levels"].append({"k": k, "what": what, "ms_per_iteration": ms / iters, "vectors_per_s": rows * iters / (ms * 1e-3),
                               "rounds_executed": r_exec, "reference_rounds": [st.rounds for st in stats],
+                              "passes": [st.passes for st in stats], "window_misses": [st.window_misses for st in stats],
                               "list_rounds": [st.list_passes for st in stats],
                               "composite": {"achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}})
         if k == 128:

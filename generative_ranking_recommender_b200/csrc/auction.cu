@@ -60,7 +60,7 @@ constexpr int AUC_MIN_TILES_PER_CTA = 2;
 constexpr int AUC_COLD_SHIFT = 8;  // 256 bins x 256 keys cover all 65536 fp16 keys
 constexpr int AUC_MIN_KEY = 0x0400; // key of the most negative finite half: fine windows never reach -inf
 constexpr int AUC_SUB = 4096;      // jobs whose cost / owner are staged in shared memory at a time
-constexpr int AUC_QCAP = 128;      // per-warp survivor queue of the HIST kernel
+constexpr int AUC_QCAP = 256;      // per-warp survivor queue of the HIST kernel (one row segment; = AUC_SEG_CAP)
 constexpr int AUC_SAMPLE_MAX = 4096; // window-sampling jobs per worker (all ranks together)
 constexpr int AUC_SEG_CAP = 256;   // survivor-list entries per (sub-range, worker); ~60 expected
 
@@ -124,6 +124,7 @@ struct AuctionPtrs {
     int* list_ok;             // [1] cleared by a HIST CTA whose segment overflowed
     unsigned int* rank_off;   // [K] ties at the threshold held by lower ranks (peer-memory sharding; else 0)
     unsigned int* ticket;     // [1] CTAs finished in the running pass kernel (fused resolve)
+    int* res_pass;            // [K] value of AuctionState.passes when the worker's threshold was resolved
 };
 
 static inline int auction_tile_cols(int K) { return K <= 128 ? 128 : 64; }
@@ -176,6 +177,7 @@ static inline size_t auction_ws_layout(long long N, long long ld, int K, Auction
     size_t o_lo = take_(4);
     size_t o_ro = take_((size_t)K * 4);
     size_t o_tk2 = take_(4);
+    size_t o_rp = take_((size_t)K * 4);
     if (reduce_off) *reduce_off = o_hist;
     if (tie_total_off) *tie_total_off = o_tt;
     if (p) {
@@ -204,6 +206,7 @@ static inline size_t auction_ws_layout(long long N, long long ld, int K, Auction
         p->list_ok = (int*)(base + o_lo);
         p->rank_off = (unsigned int*)(base + o_ro);
         p->ticket = (unsigned int*)(base + o_tk2);
+        p->res_pass = (int*)(base + o_rp);
     }
     return off;
 }
@@ -229,6 +232,7 @@ __global__ void auction_init_kernel(AuctionPtrs p, long long ld, int K, const un
         p.tprev[j] = -1;
         p.miss_run[j] = 0;
         p.rank_off[j] = 0;
+        p.res_pass[j] = -1;
     }
     if (i == 0) {
         AuctionState s;
@@ -375,6 +379,7 @@ __device__ __noinline__ void auction_resolve_body(AuctionPtrs p, long long N, in
 #pragma unroll
         for (int i = 0; i < AUC_BPL; ++i) hn[i] = (warp < K) ? __ldcg(p.hist_g + warp * AUC_W + lane * AUC_BPL + i) : 0u;
         for (int w = warp; w < K; w += NWARPS) {
+            const bool settled = p.tkey[w] >= 0;      // resolved by an earlier pass of this round: not streamed again
             const int base = p.win_base[w], shift = p.win_shift[w];
             const int hbase = p.win_hbase[w], nlo = (shift == 0) ? p.win_nlo[w] : 0;
             const unsigned long long gap = (shift == 0) ? p.gap_g[w] : 0ull;
@@ -386,6 +391,7 @@ __device__ __noinline__ void auction_resolve_body(AuctionPtrs p, long long N, in
 #pragma unroll
                 for (int i = 0; i < AUC_BPL; ++i) hn[i] = __ldcg(p.hist_g + (w + NWARPS) * AUC_W + lane * AUC_BPL + i);
             }
+            if (settled) continue;
             // suffix sums over lanes (bins above mine)
             unsigned int suf = lsum;
 #pragma unroll
@@ -434,6 +440,7 @@ __device__ __noinline__ void auction_resolve_body(AuctionPtrs p, long long N, in
                         }
                         p.tkey[w] = found_bin >= nlo ? hbase + found_bin - nlo : base + found_bin;
                         p.take[w] = (int)(jpw - (long long)g_above);
+                        p.res_pass[w] = s.passes;
                     } else {   // refine inside the bin that holds the threshold
                         int nshift = shift >= 8 ? shift - 8 : 0;
                         const int nb2 = base + (found_bin << shift);
@@ -492,10 +499,10 @@ __device__ __noinline__ void auction_resolve_body(AuctionPtrs p, long long N, in
         s.ff_pending = 0;
         s.need_sample = was_bid ? 1 : 0;
         if (was_bid && s.use_list) s.list_passes += 1;
-        if (!was_bid) {      // lists of the pass that just ran: complete unless a segment overflowed
-            s.use_list = (*p.list_ok != 0 && !s.force_scan) ? 1 : 0;
-            *p.list_ok = 1;
-        }
+        // survivor lists of this round's HIST passes (a worker's segments come from the pass that resolved it):
+        // complete unless a segment overflowed in any of them
+        if (!was_bid) s.use_list = (*p.list_ok != 0 && !s.force_scan) ? 1 : 0;
+        else *p.list_ok = 1;
         if (jump) {
             // frozen at counter c (already incremented to c+1): rounds c+1..99 add eps each
             s.ff_pending = 100 - s.counter;
@@ -572,10 +579,15 @@ auction_resolve_peer_kernel(AuctionPtrs p, long long N, int K, long long jpw, in
             }
         }
         __syncthreads();
+        const int this_pass = p.st->passes;
+        __syncthreads();
         auction_resolve_body(p, N, K, jpw, expect);
         __syncthreads();
-        if (p.st->mode == MODE_BID) {
+        {
+            // rank-major tie offsets of the workers THIS pass resolved (a partial pass after a window miss streams
+            // only the workers that missed; the peers' blocks of this exchange hold nothing for the others)
             for (int w = tid; w < K; w += NT) {
+                if (p.res_pass[w] != this_pass || p.tkey[w] < 0) continue;
                 const int base = p.win_base[w], hbase = p.win_hbase[w], nlo = p.win_nlo[w], tk = p.tkey[w];
                 const int bin = tk >= hbase ? nlo + tk - hbase : tk - base;
                 unsigned int part[PEER_MAX];
@@ -1012,7 +1024,8 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pdl_launch_dependents();
     // nothing below depends on earlier kernels until pdl_wait(): the 64 KB histogram is cleared while they finish
-    for (int i = threadIdx.x; i < K * AUC_W / 2; i += AUC_THREADS) reinterpret_cast<unsigned int*>(smem_raw)[i] = 0;
+    for (int i = threadIdx.x; i < K * AUC_W * 2 / 16; i += AUC_THREADS)
+        reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0u, 0u, 0u, 0u);
     pdl_wait();
     const AuctionState st = *p.st;
     if (st.mode != MODE_HIST) return;
@@ -1035,8 +1048,12 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
         sm.r_lo2 = (unsigned int*)q;         q += (size_t)K * 4;
         sm.r_shift = (unsigned char*)q;      q += (size_t)K;
     }
-    unsigned int* seg_cnt_s = reinterpret_cast<unsigned int*>(smem_raw + auction_hist_smem_fixed(K));   // [K]
-    unsigned short* hq = reinterpret_cast<unsigned short*>(seg_cnt_s + K);                             // [AUC_NW][AUC_QCAP]
+    unsigned char* xq = smem_raw + auction_hist_smem_fixed(K);
+    unsigned int* seg_cnt_s = reinterpret_cast<unsigned int*>(xq);          xq += (size_t)K * 4;                 // [K]
+    unsigned int* wacc_all = reinterpret_cast<unsigned int*>(xq);           xq += (size_t)AUC_NW * 4 * 32 * 4;   // [NW][4][32]
+    unsigned short* hq = reinterpret_cast<unsigned short*>(xq);             xq += (size_t)AUC_NW * AUC_QCAP * 2; // [NW][QCAP]
+    unsigned short* act = reinterpret_cast<unsigned short*>(xq);                                                  // [K]
+    __shared__ int s_nact, s_any_cold, s_wcnt[AUC_NW];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned int lt = (1u << lane) - 1u;
     const int G = gridDim.x, b = blockIdx.x;
@@ -1045,6 +1062,10 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
     long long c_end = (tiles_total * (b + 1) / G) * J;
     if (c_end > N) c_end = N;
 
+    // Rows (workers) of this pass.  A worker whose threshold an earlier pass of the SAME round resolved keeps what
+    // that pass produced (threshold, survivor lists, per-CTA dump) and is skipped: after a window miss only the
+    // workers that missed are streamed again, spread over the warps (act[] = the unresolved workers, ascending).
+    if (tid == 0) { s_nact = 0; s_any_cold = 0; }
     for (int i = tid; i < K; i += AUC_THREADS) {
         sm.above[i] = 0;
         sm.gap[i] = 0;
@@ -1052,12 +1073,31 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
         sm.r_base[i] = base;
         sm.r_hbase[i] = p.win_hbase[i];
         sm.r_nlo[i] = p.win_nlo[i];
-        sm.r_shift[i] = (unsigned char)p.win_shift[i];
+        sm.r_shift[i] = (p.tkey[i] >= 0) ? (unsigned char)0xff : (unsigned char)p.win_shift[i];   // 0xff: resolved
         const unsigned int lob = base > 0 ? key2h((unsigned)base) : 0x7c00u;   // cold rows: direct path below
         sm.r_lo2[i] = lob | (lob << 16);
     }
     __syncthreads();
-    const int any_cold = __syncthreads_or(tid < K && sm.r_base[tid] <= 0);   // cold rows take the unpipelined path
+    for (int i0 = 0; i0 < K; i0 += AUC_THREADS) {          // ordered compaction (K <= 256: one round)
+        const int i = i0 + tid;
+        const bool a = i < K && sm.r_shift[i] != 0xff;
+        const unsigned int m = __ballot_sync(0xffffffffu, a);
+        if (lane == 0) s_wcnt[warp] = __popc(m);
+        __syncthreads();
+        int off = s_nact;
+        for (int q = 0; q < warp; ++q) off += s_wcnt[q];
+        if (a) {
+            act[off + __popc(m & lt)] = (unsigned short)i;
+            if (sm.r_base[i] <= 0) s_any_cold = 1;
+        }
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int q = 0; q < AUC_NW; ++q) t += s_wcnt[q]; s_nact += t; }
+        __syncthreads();
+    }
+    const int nact = s_nact;
+    const int any_cold = s_any_cold;                         // cold rows take the unpipelined path
+    unsigned int* wacc = wacc_all + warp * (4 * 32);
+    unsigned short* wq = hq + warp * AUC_QCAP;
 
     int seg = b * spc;
     for (long long sub = c_begin; sub < c_end; sub += HS_SUB, ++seg) {
@@ -1091,7 +1131,7 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
         for (int it = 0; it < HS_SUB / AUC_THREADS; ++it) {
             const int i = tid + it * AUC_THREADS;
             const int o = (i < sublen) ? own_s[i] : -1;
-            if (o >= 0 && sm.r_base[o] > 0) {
+            if (o >= 0 && sm.r_base[o] > 0 && sm.r_shift[o] != 0xff) {
                 const int key = (int)h2key((unsigned)so_r[it]);
                 window_count(sm, o, key);
                 if (key >= sm.r_base[o]) {
@@ -1100,51 +1140,20 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
                 }
             }
         }
-        // ---- the sweep: rows of this warp, 4 x 256 jobs per step ----
-        auto load4 = [&](const __half* srow, int c0, uint4 (&sv)[4]) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int cc = c0 + q * 256 + lane * 8;
-                if (cc < sublen) sv[q] = ldg_stream128(srow + cc);               // ld is a multiple of 128: in bounds
-                else sv[q] = make_uint4(0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u);
+        // One survivor: exact value -> key -> survivor list + window histogram.  Called with all 32 lanes.
+        auto emit = [&](int w, const __half* srow, bool live, int cc, int wbase, int whb, int wnlo, int wshift) {
+            live = live && own_s[cc] != w;                                   // owner entry: counted above
+            int key = 0;
+            if (live) key = (int)h2key(h2bits(__hsub(srow[cc], __ushort_as_half(cost_s[cc]))));
+            const unsigned int m = __ballot_sync(0xffffffffu, live);
+            if (m) {
+                unsigned int slot0 = 0;
+                if (lane == 0) slot0 = atomicAdd(&seg_cnt_s[w], (unsigned)__popc(m));
+                slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+                const unsigned int slot = slot0 + __popc(m & lt);
+                if (live && slot < AUC_SEG_CAP) seg_lists[(size_t)w * AUC_SEG_CAP + slot] = ((unsigned)cc << 16) | (unsigned)key;
             }
-        };
-        auto process = [&](int w, const __half* srow, int c0, const uint4 (&sv)[4]) {
-            const int wbase = sm.r_base[w];
-            const __half2 f2 = u2h2(sm.r_lo2[w]);
-            unsigned int acc = 0;   // low half bit 4q+h: job 2h of load q survives; high half: job 2h+1
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int cc = c0 + q * 256 + lane * 8;
-                const uint4 cv = (cc < HS_SUB) ? *reinterpret_cast<const uint4*>(cost_s + cc) : make_uint4(0, 0, 0, 0);
-                const unsigned int sw[4] = {sv[q].x, sv[q].y, sv[q].z, sv[q].w};
-                const unsigned int cw[4] = {cv.x, cv.y, cv.z, cv.w};
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    const __half2 v2 = __hsub2(u2h2(sw[h]), u2h2(cw[h]));
-                    acc |= __hge2_mask(v2, f2) & ((1u << (4 * q + h)) | (1u << (16 + 4 * q + h)));
-                }
-            }
-            if (!__any_sync(0xffffffffu, acc != 0)) return;
-            const int whb = sm.r_hbase[w], wnlo = sm.r_nlo[w], wshift = sm.r_shift[w];
-            while (acc) {
-                const int bpos = __ffs(acc) - 1;
-                acc &= acc - 1;
-                const int pq = bpos & 15;
-                const int cc = c0 + (pq >> 2) * 256 + lane * 8 + 2 * (pq & 3) + (bpos >> 4);
-                if (cc >= sublen || own_s[cc] == w) continue;                    // owner entry: counted above
-                const __half v = __hsub(srow[cc], __ushort_as_half(cost_s[cc]));
-                const int key = (int)h2key(h2bits(v));
-                if (key < wbase) continue;
-                {   // survivor list for the BID pass (warp-aggregated slot allocation)
-                    const unsigned int act = __activemask();
-                    const int leader = __ffs(act) - 1;
-                    unsigned int slot0 = 0;
-                    if (lane == leader) slot0 = atomicAdd(&seg_cnt_s[w], (unsigned)__popc(act));
-                    slot0 = __shfl_sync(act, slot0, leader);
-                    const unsigned int slot = slot0 + __popc(act & lt);
-                    if (slot < AUC_SEG_CAP) seg_lists[(size_t)w * AUC_SEG_CAP + slot] = ((unsigned)cc << 16) | (unsigned)key;
-                }
+            if (live) {
                 if (wshift == 0) {
                     if (key >= whb) {
                         if (key - whb >= AUC_W - wnlo) atomicAdd(&sm.above[w], 1u);
@@ -1162,113 +1171,85 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
             }
         };
         if (!any_cold) {
-            // Fast path (every row has a fine window).  Software-pipelined: the next step's four 16-byte loads
-            // are in flight while this step is filtered, across row boundaries too.  Survivors are not
-            // handled by the lane that found them (a divergent loop, ~5 of 32 lanes busy) but pushed as
-            // job offsets into a per-warp queue and handled 32 at a time when the queue fills / the row ends.
-            unsigned short* wq = hq + warp * AUC_QCAP;
-            int qn = 0;
-            const int nfull = sublen >> 10, nsteps = (sublen + 1023) >> 10;
-            auto load_step = [&](int w, int st, uint4 (&sv)[4]) {
-                const uint4* rp = reinterpret_cast<const uint4*>(S + (size_t)w * ld + sub) + (st << 7) + lane;
-                if (st < nfull) {
+            // Fast path (every active row has a fine window).  A warp streams its rows of the sub-range in steps of
+            // 1024 jobs (four 16-byte loads per lane), software-pipelined one step ahead across row boundaries
+            // (two register buffers, ping-pong).  The filter leaves one 32-bit survivor mask per lane and step;
+            // the masks of a row's (up to four) steps are parked in shared memory and handled ONCE per row: one
+            // prefix sum over the lanes' counts, the survivors' job offsets pushed into the warp's queue, and the
+            // queue drained 32 entries at a time with all lanes busy.
+            // Loads are valid below `lim` (whole 16-byte groups): the sub-range's end, or - in the last sub-range
+            // of the matrix - the padded row end, whose columns >= N hold -inf and never survive.
+            const int lim = (int)((((sub + sublen == N) ? ld : c_end) - sub) < HS_SUB ? (((sub + sublen == N) ? ld : c_end) - sub) : HS_SUB);
+            const int nsteps = (lim + 1023) >> 10;
+            const int plane = lim - lane * 8;                                // load (st, q) valid iff (st<<10)+(q<<8) < plane
+            const uint4* cbase = reinterpret_cast<const uint4*>(cost_s) + lane;
+            // load cursor
+            int la = warp, lst = 0;
+            const uint4* lrp = nullptr;
+            if (la < nact) lrp = reinterpret_cast<const uint4*>(S + (size_t)act[la] * ld + sub) + lane;
+            auto issue = [&](uint4 (&sv)[4]) {
+                if (la >= nact) return;
+                const int room = plane - (lst << 10);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) sv[q] = ldg_stream128(rp + q * 32);
-                } else {   // tail step; columns >= N of S hold -inf and their staged cost is 0: they never survive
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        sv[q] = make_uint4(0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u);
-                        if ((st << 10) + q * 256 + lane * 8 < sublen) sv[q] = ldg_stream128(rp + q * 32);
-                    }
+                for (int q = 0; q < 4; ++q)
+                    if ((q << 8) < room) sv[q] = ldg_stream128(lrp + q * 32);
+                    else sv[q] = make_uint4(0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u);
+                ++lst;
+                lrp += 128;
+                if (lst == nsteps) {
+                    lst = 0;
+                    la += AUC_NW;
+                    if (la < nact) lrp = reinterpret_cast<const uint4*>(S + (size_t)act[la] * ld + sub) + lane;
                 }
             };
-            auto flush = [&](int w) {
+            // process cursor
+            int pa = warp, pst = 0;
+            auto row_end = [&](int w) {
                 const __half* srow = S + (size_t)w * ld + sub;
                 const int wbase = sm.r_base[w], whb = sm.r_hbase[w], wnlo = sm.r_nlo[w], wshift = sm.r_shift[w];
-                unsigned int* lw = seg_lists + (size_t)w * AUC_SEG_CAP;
                 __syncwarp();
-                for (int i0 = 0; i0 < qn; i0 += 32) {
-                    const int i = i0 + lane;
-                    bool live = i < qn;
-                    const int cc = live ? (int)wq[i] : 0;
-                    live = live && own_s[cc] != w;                               // owner entry: counted above
-                    int key = 0;
-                    if (live) key = (int)h2key(h2bits(__hsub(srow[cc], __ushort_as_half(cost_s[cc]))));
-                    const unsigned int m = __ballot_sync(0xffffffffu, live);
-                    if (m) {
-                        unsigned int slot0 = 0;
-                        if (lane == 0) slot0 = atomicAdd(&seg_cnt_s[w], (unsigned)__popc(m));
-                        slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-                        const unsigned int slot = slot0 + __popc(m & lt);
-                        if (live && slot < AUC_SEG_CAP) lw[slot] = ((unsigned)cc << 16) | (unsigned)key;
-                    }
-                    if (live) {
-                        if (wshift == 0) {
-                            if (key >= whb) {
-                                if (key - whb >= AUC_W - wnlo) atomicAdd(&sm.above[w], 1u);
-                                else hist_add(sm.hist, w, wnlo + key - whb);
-                            } else if (key >= wbase + wnlo) {
-                                atomicAdd(&sm.gap[w], 1u);
-                            } else {
-                                hist_add(sm.hist, w, key - wbase);
-                            }
-                        } else {
-                            const int bin = (key - wbase) >> wshift;
-                            if (bin >= AUC_W) atomicAdd(&sm.above[w], 1u);
-                            else hist_add(sm.hist, w, bin);
-                        }
-                    }
-                }
-                qn = 0;
-                __syncwarp();
-            };
-            uint4 cur[4], nxt[4];
-            int w = warp, st = 0;
-            if (w < K) load_step(w, 0, cur);
-            while (w < K) {
-                int wn = w, sn = st + 1;
-                if (sn == nsteps) { wn = w + AUC_NW; sn = 0; }
-                if (wn < K) load_step(wn, sn, nxt);
-                // ---- filter: v = S - cost against the window's low edge ----
-                const __half2 f2 = u2h2(sm.r_lo2[w]);
-                const uint4* cp = reinterpret_cast<const uint4*>(cost_s) + (st << 7) + lane;
-                unsigned int acc = 0;   // low half bit 4q+h: job 2h of load q survives; high half: job 2h+1
+                unsigned int m[4];
+                int cnt = 0;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint4 cv = cp[q * 32];
-                    const unsigned int sw[4] = {cur[q].x, cur[q].y, cur[q].z, cur[q].w};
-                    const unsigned int cw[4] = {cv.x, cv.y, cv.z, cv.w};
-#pragma unroll
-                    for (int h = 0; h < 4; ++h) {
-                        const __half2 v2 = __hsub2(u2h2(sw[h]), u2h2(cw[h]));
-                        acc |= __hge2_mask(v2, f2) & ((1u << (4 * q + h)) | (1u << (16 + 4 * q + h)));
-                    }
-                }
-                // ---- push the survivors' job offsets ----
-                const int mine = __popc(acc);
-                int incl = mine;
+                for (int s = 0; s < 4; ++s) { m[s] = (s < nsteps) ? wacc[s * 32 + lane] : 0u; cnt += __popc(m[s]); }
+                int incl = cnt;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
                     const int o = __shfl_up_sync(0xffffffffu, incl, d);
                     if (lane >= d) incl += o;
                 }
                 const int total = __shfl_sync(0xffffffffu, incl, 31);
-                if (total) {
-                    const int cbase = (st << 10) + lane * 8;
-                    if (qn + total > AUC_QCAP) flush(w);
-                    if (total <= AUC_QCAP) {
-                        int pos = qn + incl - mine;
-                        while (acc) {
-                            const int bpos = __ffs(acc) - 1;
-                            acc &= acc - 1;
-                            const int pq = bpos & 15;
-                            wq[pos++] = (unsigned short)(cbase + ((pq >> 2) << 8) + ((pq & 3) << 1) + (bpos >> 4));
+                if (total == 0) return;
+                auto drain = [&](int qn) {
+                    __syncwarp();
+                    for (int i0 = 0; i0 < qn; i0 += 32) {
+                        const int i = i0 + lane;
+                        const bool live = i < qn;
+                        emit(w, srow, live, live ? (int)wq[i] : 0, wbase, whb, wnlo, wshift);
+                    }
+                    __syncwarp();
+                };
+                if (total <= AUC_QCAP) {
+                    int pos = incl - cnt;
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        unsigned int a = m[s];
+                        const int cb = (s << 10) + lane * 8;
+                        while (a) {
+                            const int bpos = __ffs(a) - 1;
+                            a &= a - 1;
+                            wq[pos++] = (unsigned short)(cb + ((bpos & 12) << 6) + ((bpos & 3) << 1) + (bpos >> 4));
                         }
-                        qn += total;
-                    } else {
-                        // more than a queue's worth in one step (only with very wide windows): 4 per lane per round
-                        while (__any_sync(0xffffffffu, acc != 0)) {
-                            const int pc = __popc(acc);
+                    }
+                    drain(total);
+                } else {
+                    // more than a queue's worth in one row segment (very wide windows): up to 4 per lane per round
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        unsigned int a = m[s];
+                        const int cb = (s << 10) + lane * 8;
+                        while (__any_sync(0xffffffffu, a != 0)) {
+                            const int pc = __popc(a);
                             const int take = pc < 4 ? pc : 4;
                             int in2 = take;
 #pragma unroll
@@ -1278,79 +1259,112 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
                             }
                             int pos = in2 - take;
                             for (int r = 0; r < take; ++r) {
-                                const int bpos = __ffs(acc) - 1;
-                                acc &= acc - 1;
-                                const int pq = bpos & 15;
-                                wq[pos++] = (unsigned short)(cbase + ((pq >> 2) << 8) + ((pq & 3) << 1) + (bpos >> 4));
+                                const int bpos = __ffs(a) - 1;
+                                a &= a - 1;
+                                wq[pos++] = (unsigned short)(cb + ((bpos & 12) << 6) + ((bpos & 3) << 1) + (bpos >> 4));
                             }
-                            qn = __shfl_sync(0xffffffffu, in2, 31);
-                            flush(w);
+                            drain(__shfl_sync(0xffffffffu, in2, 31));
                         }
                     }
                 }
-                if (sn == 0 && qn) flush(w);                                     // the queue is per row
+            };
+            auto filter = [&](const uint4 (&sv)[4]) {
+                const int w = act[pa];
+                const __half2 f2 = u2h2(sm.r_lo2[w]);
+                const uint4* cp = cbase + (pst << 7);
+                unsigned int acc = 0;   // low half bit 4q+h: job 2h of load q survives; high half: job 2h+1
 #pragma unroll
-                for (int q = 0; q < 4; ++q) cur[q] = nxt[q];
-                w = wn;
-                st = sn;
-            }
-        } else
-        for (int w = warp; w < K; w += AUC_NW) {
-            const __half* srow = S + (size_t)w * ld + sub;
-            const int wbase = sm.r_base[w];
-            if (wbase > 0) {
-                for (int c0 = 0; c0 < sublen; c0 += 1024) {
-                    uint4 sv[4];
-                    load4(srow, c0, sv);
-                    process(w, srow, c0, sv);
-                }
-            } else {
-                // cold row (all 65536 keys in 128 coarse bins): exact values, every element
-                const int shift = sm.r_shift[w];
-                for (int c0 = 0; c0 < sublen; c0 += 32) {
-                    const int cc = c0 + lane;
-                    const bool valid = cc < sublen;
-                    __half v = __ushort_as_half(0xfc00);
-                    if (valid) {
-                        const __half sx = srow[cc];
-                        v = (own_s[cc] == w) ? sx : __hsub(sx, __ushort_as_half(cost_s[cc]));
+                for (int q = 0; q < 4; ++q) {
+                    const uint4 cv = cp[q * 32];
+                    const unsigned int sw[4] = {sv[q].x, sv[q].y, sv[q].z, sv[q].w};
+                    const unsigned int cw[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        const __half2 v2 = __hsub2(u2h2(sw[h]), u2h2(cw[h]));
+                        acc |= __hge2_mask(v2, f2) & ((1u << (4 * q + h)) | (1u << (16 + 4 * q + h)));
                     }
-                    const int bin = (int)h2key(h2bits(v)) >> shift;
-                    const bool hb = valid && bin < AUC_W;
-                    const bool ab = valid && bin >= AUC_W;
-                    unsigned int na = __popc(__ballot_sync(0xffffffffu, ab));
-                    if (lane == 0 && na) atomicAdd(&sm.above[w], na);
-                    unsigned int act = __ballot_sync(0xffffffffu, hb);
-                    if (act) {
-                        int lead = __ffs(act) - 1;
-                        int lbin = __shfl_sync(0xffffffffu, bin, lead);
-                        unsigned int same = __ballot_sync(0xffffffffu, hb && bin == lbin);
-                        if (same == act) {
-                            if (lane == lead) hist_add(sm.hist, w, lbin, __popc(act));
-                        } else if (hb) {
-                            hist_add(sm.hist, w, bin);
+                }
+                wacc[pst * 32 + lane] = acc;
+                ++pst;
+                if (pst == nsteps) {
+                    row_end(w);
+                    pst = 0;
+                    pa += AUC_NW;
+                }
+            };
+            uint4 bufA[4], bufB[4];
+            issue(bufA);
+            while (pa < nact) {
+                issue(bufB);
+                filter(bufA);
+                if (pa >= nact) break;
+                issue(bufA);
+                filter(bufB);
+            }
+        } else {
+            for (int a = warp; a < nact; a += AUC_NW) {
+                const int w = act[a];
+                const __half* srow = S + (size_t)w * ld + sub;
+                const int wbase = sm.r_base[w];
+                if (wbase > 0) {
+                    const int whb = sm.r_hbase[w], wnlo = sm.r_nlo[w], wshift = sm.r_shift[w];
+                    const __half lo = bits2h(key2h((unsigned)wbase));
+                    for (int c0 = 0; c0 < sublen; c0 += 32) {
+                        const int cc = c0 + lane;
+                        bool live = cc < sublen;
+                        if (live) live = __hge(__hsub(srow[cc], __ushort_as_half(cost_s[cc])), lo);
+                        if (__any_sync(0xffffffffu, live)) emit(w, srow, live, live ? cc : 0, wbase, whb, wnlo, wshift);
+                    }
+                } else {
+                    // cold row (all 65536 keys in 256 coarse bins): exact values, every element
+                    const int shift = sm.r_shift[w];
+                    for (int c0 = 0; c0 < sublen; c0 += 32) {
+                        const int cc = c0 + lane;
+                        const bool valid = cc < sublen;
+                        __half v = __ushort_as_half(0xfc00);
+                        if (valid) {
+                            const __half sx = srow[cc];
+                            v = (own_s[cc] == w) ? sx : __hsub(sx, __ushort_as_half(cost_s[cc]));
+                        }
+                        const int bin = (int)h2key(h2bits(v)) >> shift;
+                        const bool hb = valid && bin < AUC_W;
+                        const bool ab = valid && bin >= AUC_W;
+                        unsigned int na = __popc(__ballot_sync(0xffffffffu, ab));
+                        if (lane == 0 && na) atomicAdd(&sm.above[w], na);
+                        unsigned int actm = __ballot_sync(0xffffffffu, hb);
+                        if (actm) {
+                            int lead = __ffs(actm) - 1;
+                            int lbin = __shfl_sync(0xffffffffu, bin, lead);
+                            unsigned int same = __ballot_sync(0xffffffffu, hb && bin == lbin);
+                            if (same == actm) {
+                                if (lane == lead) hist_add(sm.hist, w, lbin, __popc(actm));
+                            } else if (hb) {
+                                hist_add(sm.hist, w, bin);
+                            }
                         }
                     }
                 }
             }
         }
         __syncthreads();
-        if (tid < K) {
+        if (tid < K && sm.r_shift[tid] != 0xff) {
             const unsigned int c = seg_cnt_s[tid];
             p.seg_cnt[(size_t)seg * K + tid] = c;
             if (c > AUC_SEG_CAP) *p.list_ok = 0;
         }
     }
 
-    // ---- publish: per-CTA dump (for the tie prefix) + merge of non-empty bins ----
+    // ---- publish (active rows only): per-CTA dump (for the tie prefix) + merge of non-empty bins ----
     unsigned int* dump = reinterpret_cast<unsigned int*>(p.hist_cta + (size_t)b * K * AUC_W);
-    for (int i = tid; i < K * AUC_W / 2; i += AUC_THREADS) {
-        unsigned int h = sm.hist[i];
+    for (int a = tid >> 7; a < nact; a += AUC_THREADS >> 7) {                // AUC_W / 2 = 128 words per row
+        const int i = (int)act[a] * (AUC_W / 2) + (tid & 127);
+        const unsigned int h = sm.hist[i];
         dump[i] = h;
         if (h & 0xffffu) atomicAdd(&p.hist_g[2 * i], h & 0xffffu);
         if (h >> 16) atomicAdd(&p.hist_g[2 * i + 1], h >> 16);
     }
-    for (int i = tid; i < K; i += AUC_THREADS) {
+    for (int a = tid; a < nact; a += AUC_THREADS) {
+        const int i = act[a];
         if (sm.above[i]) atomicAdd(&p.above_g[i], sm.above[i]);
         if (sm.gap[i]) atomicAdd(&p.gap_g[i], sm.gap[i]);
     }
@@ -1373,10 +1387,9 @@ auction_bidlist_kernel(const __half* __restrict__ S, long long ld, long long N, 
     const AuctionState st = *p.st;
     if (st.mode != MODE_BID || !st.use_list) return;
     constexpr int NCH = AUC_SEG_CAP / 32;
-    __shared__ unsigned int colmax[AUC_SUB];
-    __shared__ unsigned short cost_s[AUC_SUB];
-    __shared__ short own_s[AUC_SUB];
-    __shared__ unsigned char colviol[AUC_SUB];
+    __shared__ __align__(16) unsigned int colmax[AUC_SUB];
+    __shared__ __align__(16) short own_s[AUC_SUB];
+    __shared__ __align__(16) unsigned char colviol[AUC_SUB];
     __shared__ unsigned int tie_seen[256];
     __shared__ int r_take[256], r_tk[256];
     __shared__ unsigned int s_nwith, s_nviol;
@@ -1403,29 +1416,33 @@ auction_bidlist_kernel(const __half* __restrict__ S, long long ld, long long N, 
     for (long long sub = c_begin; sub < c_end; sub += AUC_SUB, ++seg) {
         const int sublen = (int)((c_end - sub) < AUC_SUB ? (c_end - sub) : AUC_SUB);
         // ---- stage cost / owner; bids that do not depend on S (retain hack :87, fallback :89) ----
-        constexpr int PER = AUC_SUB / AUC_THREADS;
-        unsigned short c_r[PER];
-        short o_r[PER];
-#pragma unroll
-        for (int it = 0; it < PER; ++it) {                                       // all loads first: one latency, not PER
-            const int i = tid + it * AUC_THREADS;
-            c_r[it] = 0;
-            o_r[it] = -1;
-            if (i < sublen) { c_r[it] = __half_as_ushort(p.cost[sub + i]); o_r[it] = p.owner[sub + i]; }
+        // A thread owns 8 consecutive jobs (AUC_SUB = 8 * AUC_THREADS): one 16-byte access per array.  cost / owner /
+        // sown hold ld >= N entries (columns >= N: cost 0, owner -1, never touched), so whole groups are in bounds.
+        static_assert(AUC_SUB == 8 * AUC_THREADS, "one 8-job group per thread");
+        const int j0 = tid * 8;
+        const bool grp = j0 < sublen;                            // sublen is a multiple of 8 except at the matrix end
+        uint4 c8 = make_uint4(0u, 0u, 0u, 0u), o8 = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        if (grp) {
+            c8 = *reinterpret_cast<const uint4*>(p.cost + sub + j0);
+            o8 = *reinterpret_cast<const uint4*>(p.owner + sub + j0);
         }
+        {
+            const unsigned int ow[4] = {o8.x, o8.y, o8.z, o8.w};
+            unsigned int init[8];
 #pragma unroll
-        for (int it = 0; it < PER; ++it) {
-            const int i = tid + it * AUC_THREADS;
-            if (i >= sublen) break;
-            const unsigned short c = c_r[it];
-            const short o = o_r[it];
-            cost_s[i] = c;
-            own_s[i] = o;
-            unsigned int init = 0;
-            if (o >= 0) { if (retain) init = (eps_bits << 16) | (0xffffu - (unsigned)o); }
-            else if (fallback) init = (eps_bits << 16) | 0xffffu;
-            colmax[i] = init;
-            colviol[i] = 0;
+            for (int e = 0; e < 8; ++e) {
+                const int o = (int)(short)((ow[e >> 1] >> ((e & 1) * 16)) & 0xffffu);
+                unsigned int v = 0;
+                if (j0 + e < sublen) {
+                    if (o >= 0) { if (retain) v = (eps_bits << 16) | (0xffffu - (unsigned)o); }
+                    else if (fallback) v = (eps_bits << 16) | 0xffffu;
+                }
+                init[e] = v;
+            }
+            *reinterpret_cast<uint4*>(own_s + j0) = o8;
+            *reinterpret_cast<uint4*>(colmax + j0) = make_uint4(init[0], init[1], init[2], init[3]);
+            *reinterpret_cast<uint4*>(colmax + j0 + 4) = make_uint4(init[4], init[5], init[6], init[7]);
+            *reinterpret_cast<uint2*>(colviol + j0) = make_uint2(0u, 0u);
         }
         __syncthreads();
         // ---- segments: a warp per worker ----
@@ -1518,44 +1535,61 @@ auction_bidlist_kernel(const __half* __restrict__ S, long long ld, long long N, 
             if (lane == 0) tie_seen[w] = seen0 + n_ties;
         }
         __syncthreads();
-        // ---- highest bid per job, cost / owner update (:104, :118-123) ----
-        unsigned short sv_r[PER];
-        unsigned int pk_r[PER];
+        // ---- highest bid per job, cost / owner update (:104, :118-123): the thread's 8 jobs again ----
+        {
+            const uint4 pa = *reinterpret_cast<const uint4*>(colmax + j0), pb = *reinterpret_cast<const uint4*>(colmax + j0 + 4);
+            const uint2 vi = *reinterpret_cast<const uint2*>(colviol + j0);
+            const unsigned int pk[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+            const unsigned int cw[4] = {c8.x, c8.y, c8.z, c8.w}, ow[4] = {o8.x, o8.y, o8.z, o8.w};
+            unsigned short sv[8];
+            unsigned int changed = 0;                                            // bit e: job e has a new owner
 #pragma unroll
-        for (int it = 0; it < PER; ++it) {                                       // new owners' own values: loads first
-            const int i = tid + it * AUC_THREADS;
-            pk_r[it] = (i < sublen) ? colmax[i] : 0u;
-            sv_r[it] = 0;
-            if (pk_r[it]) {
-                const short wnr = (short)(0xffffu - (pk_r[it] & 0xffffu));
-                if (wnr != own_s[i]) sv_r[it] = __half_as_ushort(S[(size_t)wnr * ld + sub + i]);
-            }
-        }
-#pragma unroll
-        for (int it = 0; it < PER; ++it) {
-            const int i = tid + it * AUC_THREADS;
-            bool has = false, vv = false;
-            if (i < sublen) {
-                const unsigned int pk = pk_r[it];
-                const short old_owner = own_s[i];
-                vv = colviol[i] != 0;
-                if (pk) {
-                    has = true;
-                    const short wnr = (short)(0xffffu - (pk & 0xffffu));
-                    p.cost[sub + i] = __hadd(__ushort_as_half(cost_s[i]), bits2h(pk >> 16));
+            for (int e = 0; e < 8; ++e) {                                        // new owners' own values: loads first
+                sv[e] = 0;
+                const int old_owner = (int)(short)((ow[e >> 1] >> ((e & 1) * 16)) & 0xffffu);
+                if (pk[e]) {
+                    const int wnr = (int)(0xffffu - (pk[e] & 0xffffu));
                     if (wnr != old_owner) {
-                        p.owner[sub + i] = wnr;
-                        p.sown[sub + i] = __ushort_as_half(sv_r[it]);
+                        changed |= 1u << e;
+                        sv[e] = __half_as_ushort(S[(size_t)wnr * ld + sub + j0 + e]);
                     }
-                } else {
-                    if (old_owner >= 0) { p.owner[sub + i] = -1; vv = true; }    // an owned job lost its bidder
                 }
             }
-            const unsigned int mh = __ballot_sync(0xffffffffu, has);
-            const unsigned int mv = __ballot_sync(0xffffffffu, vv);
+            unsigned int nc[4], no[4];
+            int n_has = 0, n_vv = 0;
+            bool cost_dirty = false, own_dirty = false;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int sh = (e & 1) * 16;
+                unsigned int c = (cw[e >> 1] >> sh) & 0xffffu, o = (ow[e >> 1] >> sh) & 0xffffu;
+                const int old_owner = (int)(short)o;
+                bool vv = ((e < 4 ? vi.x >> (8 * e) : vi.y >> (8 * (e - 4))) & 0xffu) != 0;
+                if (pk[e]) {
+                    ++n_has;
+                    c = h2bits(__hadd(__ushort_as_half((unsigned short)c), bits2h(pk[e] >> 16)));
+                    cost_dirty = true;
+                    if ((changed >> e) & 1u) { o = 0xffffu - (pk[e] & 0xffffu); own_dirty = true; }
+                } else if (old_owner >= 0) {                                     // an owned job lost its bidder
+                    o = 0xffffu;
+                    own_dirty = true;
+                    vv = true;
+                }
+                n_vv += vv ? 1 : 0;
+                if (e & 1) { nc[e >> 1] |= c << 16; no[e >> 1] |= o << 16; }
+                else { nc[e >> 1] = c; no[e >> 1] = o; }
+            }
+            if (grp) {
+                if (cost_dirty) *reinterpret_cast<uint4*>(p.cost + sub + j0) = make_uint4(nc[0], nc[1], nc[2], nc[3]);
+                if (own_dirty) *reinterpret_cast<uint4*>(p.owner + sub + j0) = make_uint4(no[0], no[1], no[2], no[3]);
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    if ((changed >> e) & 1u) p.sown[sub + j0 + e] = __ushort_as_half(sv[e]);
+            }
+            n_has = __reduce_add_sync(0xffffffffu, n_has);
+            n_vv = __reduce_add_sync(0xffffffffu, n_vv);
             if (lane == 0) {
-                if (mh) atomicAdd(&s_nwith, __popc(mh));
-                if (mv) atomicAdd(&s_nviol, __popc(mv));
+                if (n_has) atomicAdd(&s_nwith, (unsigned)n_has);
+                if (n_vv) atomicAdd(&s_nviol, (unsigned)n_vv);
             }
         }
         __syncthreads();
@@ -1568,7 +1602,9 @@ auction_bidlist_kernel(const __half* __restrict__ S, long long ld, long long N, 
 }
 
 static inline size_t auction_hist_smem(int K) {
-    return auction_hist_smem_fixed(K) + (size_t)K * 4 + (size_t)AUC_NW * AUC_QCAP * 2;
+    // + seg_cnt_s [K], per-warp survivor masks [NW][4][32], per-warp queues [NW][QCAP], active-row list [K]
+    return auction_hist_smem_fixed(K) + (size_t)K * 4 + (size_t)AUC_NW * 4 * 32 * 4 + (size_t)AUC_NW * AUC_QCAP * 2 +
+           (size_t)K * 2 + 16;
 }
 
 static inline size_t auction_pass_smem(int K, int J) {

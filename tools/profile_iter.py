@@ -16,7 +16,21 @@ k = int(os.environ.get("PROF_K", 128))
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev)
 g.manual_seed(1234)
-x = torch.randn((n, 512), device=dev, generator=g)
+if os.environ.get("PROF_DATA", "iso") == "mix":      # S-mix, optionally as a level-2-like unit-norm residual
+    c = torch.randn((1024, 512), device=dev, generator=g)
+    j = torch.randint(0, 1024, (n,), device=dev, generator=g)
+    x = (c[j] + 0.5 * torch.randn((n, 512), device=dev, generator=g)) / 512 ** 0.5
+    if os.environ.get("PROF_RESIDUAL", "0") == "1":
+        from generative_ranking_recommender_b200 import engine as _e0
+        c0 = x[torch.randperm(n, device=dev, generator=g)[:128]].clone()
+        for _ in range(2):
+            ids = _e0.score_pass(x, c0, argmin=True).argmin
+            s_, cnt_ = _e0.centroid_accumulate(x, ids, 128)
+            _e0.centroid_finalize(s_, cnt_, c0)
+        ids = _e0.score_pass(x, c0, argmin=True).argmin
+        _e0.residual_normalise(x, ids, c0, [512], out=x)
+else:
+    x = torch.randn((n, 512), device=dev, generator=g)
 np.random.seed(42)
 km = KMeans(n_clusters=k, device=dev, balanced=True)
 km.cluster_centers = km.initialize(x)
