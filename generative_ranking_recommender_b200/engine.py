@@ -151,6 +151,76 @@ def no_shard() -> ShardGroup:
     return _NO_SHARD
 
 
+class _Uploader:
+    """Host -> device copy of a large PAGEABLE row matrix (what train_semantic_ids.py:152 hands to train(): the
+    np.vstack of the CSV rows).  A plain `tensor.to(device)` from pageable memory is one synchronous staged copy
+    (~7 GB/s measured on the B200 box); here a few host threads copy row chunks into page-locked staging buffers
+    (numpy copies run without the interpreter lock, and convert the dtype on the way if the input is not fp32)
+    while the previous chunks travel over PCIe on a copy stream."""
+
+    CHUNK_BYTES = 32 << 20
+    NBUF = 4
+    THREADS = 4
+
+    def __init__(self):
+        self.stage: List[torch.Tensor] = []
+        self.pool = None
+
+    def _setup(self):
+        if not self.stage:
+            from concurrent.futures import ThreadPoolExecutor
+            self.stage = [torch.empty(self.CHUNK_BYTES // 4, dtype=torch.float32, pin_memory=True) for _ in range(self.NBUF)]
+            self.pool = ThreadPoolExecutor(max_workers=self.THREADS, thread_name_prefix="rqk-h2d")
+
+    def upload(self, X: np.ndarray, dev: torch.device) -> torch.Tensor:
+        n, d = X.shape
+        dst = torch.empty((n, d), dtype=torch.float32, device=dev)
+        rows = max(1, self.CHUNK_BYTES // (4 * d))
+        nch = (n + rows - 1) // rows
+        self._setup()
+        views = [t.numpy() for t in self.stage]
+        stream = torch.cuda.Stream(dev)
+        events: List[Optional[torch.cuda.Event]] = [None] * self.NBUF
+
+        def host_copy(c: int):
+            i0, i1 = c * rows, min(n, (c + 1) * rows)
+            np.copyto(views[c % self.NBUF][:(i1 - i0) * d].reshape(i1 - i0, d), X[i0:i1], casting="unsafe")
+
+        pending, nxt = {}, 0
+        for c in range(nch):
+            while nxt < nch and nxt < c + self.NBUF:
+                if events[nxt % self.NBUF] is not None:
+                    events[nxt % self.NBUF].synchronize()          # the chunk that used this buffer has left it
+                pending[nxt] = self.pool.submit(host_copy, nxt)
+                nxt += 1
+            pending.pop(c).result()
+            i0, i1 = c * rows, min(n, (c + 1) * rows)
+            with torch.cuda.stream(stream):
+                dst[i0:i1].copy_(self.stage[c % self.NBUF][:(i1 - i0) * d].view(i1 - i0, d), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(stream)
+            events[c % self.NBUF] = ev
+        stream.synchronize()                                       # the staging buffers are free for the next call
+        return dst
+
+
+UPLOADER = _Uploader()
+
+
+def h2d_rows(X: np.ndarray, dev: torch.device) -> torch.Tensor:
+    """fp32 [N, D] on `dev` from a host array: page-locked memory is DMA'd as it is, large pageable arrays go through
+    the chunked uploader, small ones through torch."""
+    if dev.type != "cuda":
+        raise _lib.RqkError(f"device {dev}: this engine runs on CUDA sm_100a only (no CPU fallback)")
+    if X.dtype == np.float32 and X.flags["C_CONTIGUOUS"]:
+        t = torch.from_numpy(X)
+        if t.is_pinned():
+            return t.to(dev, non_blocking=True)
+    if X.ndim == 2 and X.size * 4 >= (64 << 20):
+        return UPLOADER.upload(X, dev)
+    return torch.from_numpy(np.ascontiguousarray(X.astype("float32", copy=False))).to(dev)
+
+
 class _Scratch:
     """Per-device cache of workspace buffers (the library never allocates)."""
 

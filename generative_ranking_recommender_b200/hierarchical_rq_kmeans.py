@@ -425,9 +425,7 @@ class HierarchicalRQKMeans:
     def _h2d(X: np.ndarray, dev: torch.device) -> torch.Tensor:
         if dev.type != "cuda":
             raise engine._lib.RqkError(f"device {dev}: HierarchicalRQKMeans runs on CUDA sm_100a only (no CPU fallback)")
-        t = torch.from_numpy(np.ascontiguousarray(X.astype("float32", copy=False)))
-        # page-locked host arrays (the driver knows, torch asks it) are DMA'd without a staging copy
-        return t.to(dev, non_blocking=t.is_pinned())
+        return engine.h2d_rows(np.asarray(X), dev)
 
     def _train_layer_0(self, X: torch.Tensor, layer: int):                              # :606-669
         n_clusters = self.config.layer_clusters[layer]

@@ -599,3 +599,20 @@ def test_middle_layer_training_structure(dev, engine, golden_dir):
     assert abs(unique - ref_unique) <= 0.06 * ref_unique, (unique, ref_unique)
     pred = m.predict(x)
     assert pred.shape == (len(x), 3) and np.array_equal(pred[:, 0], ids[0])
+
+
+def test_chunked_upload_of_pageable_rows(dev, engine):
+    """train() receives a pageable np.ndarray (train_semantic_ids.py:152); above 64 MB it travels through the
+    chunked uploader (host threads -> page-locked staging -> copy stream).  Same bytes as a plain copy, for fp32,
+    for other dtypes (converted on the way) and for strided views; twice in a row (the staging buffers are reused)."""
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((70001, 512), dtype=np.float32)                 # 143 MB: 5 chunks, ragged tail
+    for _ in range(2):
+        assert torch.equal(engine.h2d_rows(x, dev), torch.from_numpy(x).to(dev))
+    x64 = x[:40000].astype(np.float64)
+    assert torch.equal(engine.h2d_rows(x64, dev), torch.from_numpy(x64.astype(np.float32)).to(dev))
+    xs = x[::2]                                                              # strided rows
+    assert not xs.flags["C_CONTIGUOUS"]
+    assert torch.equal(engine.h2d_rows(xs, dev), torch.from_numpy(np.ascontiguousarray(xs)).to(dev))
+    small = x[:100]
+    assert torch.equal(engine.h2d_rows(small, dev), torch.from_numpy(small).to(dev))
