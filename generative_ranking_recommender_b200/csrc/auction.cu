@@ -1007,10 +1007,6 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
 // CTA b owns exactly the job range CTA b of the tiled BID kernel owns (the per-CTA dumps feed its tie prefix).
 // ------------------------------------------------------------------------------------------
 constexpr int HS_SUB = AUC_SUB;   // jobs staged (cost, owner) per sub-range
-__host__ __device__ inline size_t auction_hist_smem_fixed(int K) {
-    return ((size_t)K * AUC_W * 2 + (size_t)HS_SUB * 4 + (size_t)K * 25 + 63) / 16 * 16;
-}
-
 __device__ __forceinline__ uint4 ldg_stream128(const void* ptr) {
     uint4 r;
     asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
@@ -1018,13 +1014,36 @@ __device__ __forceinline__ uint4 ldg_stream128(const void* ptr) {
     return r;
 }
 
-__global__ void __launch_bounds__(AUC_THREADS, 2)
+// Shared-memory layout with compile-time offsets (KP = K rounded up to 128 or 256): with run-time offsets the
+// compiler re-derives the array bases inside the hot loops (64 registers per thread leave no room to keep them).
+template <int KP>
+struct HistSmem {
+    static constexpr int HIST = 0;                                    // [KP][W/2] two 16-bit counters per word
+    static constexpr int COST = HIST + KP * AUC_W * 2;                // [HS_SUB] fp16
+    static constexpr int OWN = COST + HS_SUB * 2;                     // [HS_SUB] int16
+    static constexpr int WACC = OWN + HS_SUB * 2;                     // [NW][4][32] survivor masks of a row's steps
+    static constexpr int HQ = WACC + AUC_NW * 4 * 32 * 4;             // [NW][QCAP] survivor queue
+    static constexpr int ABOVE = HQ + AUC_NW * AUC_QCAP * 2;          // [KP] u32 ...
+    static constexpr int GAP = ABOVE + KP * 4;
+    static constexpr int RBASE = GAP + KP * 4;
+    static constexpr int RHBASE = RBASE + KP * 4;
+    static constexpr int RNLO = RHBASE + KP * 4;
+    static constexpr int RLO2 = RNLO + KP * 4;
+    static constexpr int SEGCNT = RLO2 + KP * 4;
+    static constexpr int ACT = SEGCNT + KP * 4;                       // [KP] u16 unresolved workers, ascending
+    static constexpr int RSHIFT = ACT + KP * 2;                       // [KP] u8 (0xff: resolved by an earlier pass)
+    static constexpr int TOTAL = (RSHIFT + KP + 15) / 16 * 16;
+};
+
+template <int KP>
+__global__ void __launch_bounds__(AUC_THREADS, (KP <= 128 ? 2 : 1))
 auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int K, int J, int spc, AuctionPtrs p,
                     long long n_global, int fused) {
+    using L = HistSmem<KP>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     pdl_launch_dependents();
-    // nothing below depends on earlier kernels until pdl_wait(): the 64 KB histogram is cleared while they finish
-    for (int i = threadIdx.x; i < K * AUC_W * 2 / 16; i += AUC_THREADS)
+    // nothing below depends on earlier kernels until pdl_wait(): the histogram is cleared while they finish
+    for (int i = threadIdx.x; i < KP * AUC_W * 2 / 16; i += AUC_THREADS)
         reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0u, 0u, 0u, 0u);
     pdl_wait();
     const AuctionState st = *p.st;
@@ -1033,29 +1052,23 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
     const __half eps = bits2h(st.eps_bits);
 
     PassSmem sm;
-    unsigned short* cost_s;
-    short* own_s;
-    {
-        unsigned char* q = smem_raw;
-        sm.hist = (unsigned int*)q;          q += (size_t)K * AUC_W * 2;
-        cost_s = (unsigned short*)q;         q += (size_t)HS_SUB * 2;
-        own_s = (short*)q;                   q += (size_t)HS_SUB * 2;
-        sm.above = (unsigned int*)q;         q += (size_t)K * 4;
-        sm.gap = (unsigned int*)q;           q += (size_t)K * 4;
-        sm.r_base = (int*)q;                 q += (size_t)K * 4;
-        sm.r_hbase = (int*)q;                q += (size_t)K * 4;
-        sm.r_nlo = (int*)q;                  q += (size_t)K * 4;
-        sm.r_lo2 = (unsigned int*)q;         q += (size_t)K * 4;
-        sm.r_shift = (unsigned char*)q;      q += (size_t)K;
-    }
-    unsigned char* xq = smem_raw + auction_hist_smem_fixed(K);
-    unsigned int* seg_cnt_s = reinterpret_cast<unsigned int*>(xq);          xq += (size_t)K * 4;                 // [K]
-    unsigned int* wacc_all = reinterpret_cast<unsigned int*>(xq);           xq += (size_t)AUC_NW * 4 * 32 * 4;   // [NW][4][32]
-    unsigned short* hq = reinterpret_cast<unsigned short*>(xq);             xq += (size_t)AUC_NW * AUC_QCAP * 2; // [NW][QCAP]
-    unsigned short* act = reinterpret_cast<unsigned short*>(xq);                                                  // [K]
+    sm.hist = reinterpret_cast<unsigned int*>(smem_raw + L::HIST);
+    sm.above = reinterpret_cast<unsigned int*>(smem_raw + L::ABOVE);
+    sm.gap = reinterpret_cast<unsigned int*>(smem_raw + L::GAP);
+    sm.r_base = reinterpret_cast<int*>(smem_raw + L::RBASE);
+    sm.r_hbase = reinterpret_cast<int*>(smem_raw + L::RHBASE);
+    sm.r_nlo = reinterpret_cast<int*>(smem_raw + L::RNLO);
+    sm.r_lo2 = reinterpret_cast<unsigned int*>(smem_raw + L::RLO2);
+    sm.r_shift = smem_raw + L::RSHIFT;
+    unsigned short* const cost_s = reinterpret_cast<unsigned short*>(smem_raw + L::COST);
+    short* const own_s = reinterpret_cast<short*>(smem_raw + L::OWN);
+    unsigned int* const seg_cnt_s = reinterpret_cast<unsigned int*>(smem_raw + L::SEGCNT);
+    unsigned short* const act = reinterpret_cast<unsigned short*>(smem_raw + L::ACT);
     __shared__ int s_nact, s_any_cold, s_wcnt[AUC_NW];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned int lt = (1u << lane) - 1u;
+    unsigned int* const wacc = reinterpret_cast<unsigned int*>(smem_raw + L::WACC) + warp * (4 * 32);
+    unsigned short* const wq = reinterpret_cast<unsigned short*>(smem_raw + L::HQ) + warp * AUC_QCAP;
     const int G = gridDim.x, b = blockIdx.x;
     const long long tiles_total = (N + J - 1) / J;
     const long long c_begin = (tiles_total * b / G) * J;
@@ -1078,26 +1091,22 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
         sm.r_lo2[i] = lob | (lob << 16);
     }
     __syncthreads();
-    for (int i0 = 0; i0 < K; i0 += AUC_THREADS) {          // ordered compaction (K <= 256: one round)
-        const int i = i0 + tid;
-        const bool a = i < K && sm.r_shift[i] != 0xff;
+    {   // ordered compaction (K <= 256 < AUC_THREADS: one round)
+        const bool a = tid < K && sm.r_shift[tid] != 0xff;
         const unsigned int m = __ballot_sync(0xffffffffu, a);
         if (lane == 0) s_wcnt[warp] = __popc(m);
         __syncthreads();
-        int off = s_nact;
+        int off = 0;
         for (int q = 0; q < warp; ++q) off += s_wcnt[q];
         if (a) {
-            act[off + __popc(m & lt)] = (unsigned short)i;
-            if (sm.r_base[i] <= 0) s_any_cold = 1;
+            act[off + __popc(m & lt)] = (unsigned short)tid;
+            if (sm.r_base[tid] <= 0) s_any_cold = 1;
         }
-        __syncthreads();
-        if (tid == 0) { int t = 0; for (int q = 0; q < AUC_NW; ++q) t += s_wcnt[q]; s_nact += t; }
+        if (tid == 0) { int t = 0; for (int q = 0; q < AUC_NW; ++q) t += s_wcnt[q]; s_nact = t; }
         __syncthreads();
     }
     const int nact = s_nact;
     const int any_cold = s_any_cold;                         // cold rows take the unpipelined path
-    unsigned int* wacc = wacc_all + warp * (4 * 32);
-    unsigned short* wq = hq + warp * AUC_QCAP;
 
     int seg = b * spc;
     for (long long sub = c_begin; sub < c_end; sub += HS_SUB, ++seg) {
@@ -1140,7 +1149,7 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
                 }
             }
         }
-        // One survivor: exact value -> key -> survivor list + window histogram.  Called with all 32 lanes.
+        // One survivor per lane: exact value -> key -> survivor list + window histogram.  Called with all 32 lanes.
         auto emit = [&](int w, const __half* srow, bool live, int cc, int wbase, int whb, int wnlo, int wshift) {
             live = live && own_s[cc] != w;                                   // owner entry: counted above
             int key = 0;
@@ -1154,34 +1163,29 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
                 if (live && slot < AUC_SEG_CAP) seg_lists[(size_t)w * AUC_SEG_CAP + slot] = ((unsigned)cc << 16) | (unsigned)key;
             }
             if (live) {
-                if (wshift == 0) {
-                    if (key >= whb) {
-                        if (key - whb >= AUC_W - wnlo) atomicAdd(&sm.above[w], 1u);
-                        else hist_add(sm.hist, w, wnlo + key - whb);
-                    } else if (key >= wbase + wnlo) {
-                        atomicAdd(&sm.gap[w], 1u);
-                    } else {
-                        hist_add(sm.hist, w, key - wbase);
-                    }
-                } else {
-                    const int bin = (key - wbase) >> wshift;
-                    if (bin >= AUC_W) atomicAdd(&sm.above[w], 1u);
-                    else hist_add(sm.hist, w, bin);
-                }
+                int bin;
+                if (wshift == 0) bin = key >= whb ? (key - whb >= AUC_W - wnlo ? AUC_W : wnlo + key - whb)
+                                                  : (key >= wbase + wnlo ? -1 : key - wbase);
+                else { bin = (key - wbase) >> wshift; bin = bin > AUC_W ? AUC_W : bin; }
+                if (bin >= AUC_W) atomicAdd(&sm.above[w], 1u);
+                else if (bin < 0) atomicAdd(&sm.gap[w], 1u);
+                else hist_add(sm.hist, w, bin);
             }
         };
         if (!any_cold) {
             // Fast path (every active row has a fine window).  A warp streams its rows of the sub-range in steps of
             // 1024 jobs (four 16-byte loads per lane), software-pipelined one step ahead across row boundaries
             // (two register buffers, ping-pong).  The filter leaves one 32-bit survivor mask per lane and step;
-            // the masks of a row's (up to four) steps are parked in shared memory and handled ONCE per row: one
-            // prefix sum over the lanes' counts, the survivors' job offsets pushed into the warp's queue, and the
+            // the masks of a row's (up to four) steps are parked in shared memory and handled once per row: one
+            // prefix sum over the lanes' counts, the survivors' positions pushed into the warp's queue, and the
             // queue drained 32 entries at a time with all lanes busy.
             // Loads are valid below `lim` (whole 16-byte groups): the sub-range's end, or - in the last sub-range
             // of the matrix - the padded row end, whose columns >= N hold -inf and never survive.
-            const int lim = (int)((((sub + sublen == N) ? ld : c_end) - sub) < HS_SUB ? (((sub + sublen == N) ? ld : c_end) - sub) : HS_SUB);
+            const long long hard_end = (sub + sublen == N) ? ld : c_end;
+            const int lim = (int)((hard_end - sub) < HS_SUB ? (hard_end - sub) : HS_SUB);
             const int nsteps = (lim + 1023) >> 10;
-            const int plane = lim - lane * 8;                                // load (st, q) valid iff (st<<10)+(q<<8) < plane
+            const bool last_full = (lim & 1023) == 0;
+            const int plane = lim - ((nsteps - 1) << 10) - lane * 8;         // last step: load q valid iff (q<<8) < plane
             const uint4* cbase = reinterpret_cast<const uint4*>(cost_s) + lane;
             // load cursor
             int la = warp, lst = 0;
@@ -1189,11 +1193,16 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
             if (la < nact) lrp = reinterpret_cast<const uint4*>(S + (size_t)act[la] * ld + sub) + lane;
             auto issue = [&](uint4 (&sv)[4]) {
                 if (la >= nact) return;
-                const int room = plane - (lst << 10);
+                if (last_full || lst + 1 < nsteps) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if ((q << 8) < room) sv[q] = ldg_stream128(lrp + q * 32);
-                    else sv[q] = make_uint4(0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u);
+                    for (int q = 0; q < 4; ++q) sv[q] = ldg_stream128(lrp + q * 32);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        sv[q] = make_uint4(0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u);
+                        if ((q << 8) < plane) sv[q] = ldg_stream128(lrp + q * 32);
+                    }
+                }
                 ++lst;
                 lrp += 128;
                 if (lst == nsteps) {
@@ -1207,7 +1216,6 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
             auto row_end = [&](int w) {
                 const __half* srow = S + (size_t)w * ld + sub;
                 const int wbase = sm.r_base[w], whb = sm.r_hbase[w], wnlo = sm.r_nlo[w], wshift = sm.r_shift[w];
-                __syncwarp();
                 unsigned int m[4];
                 int cnt = 0;
 #pragma unroll
@@ -1220,25 +1228,30 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
                 }
                 const int total = __shfl_sync(0xffffffffu, incl, 31);
                 if (total == 0) return;
+                // queue entry = (step << 10) | (lane << 5) | bit position of the mask; decoded when drained
                 auto drain = [&](int qn) {
                     __syncwarp();
                     for (int i0 = 0; i0 < qn; i0 += 32) {
                         const int i = i0 + lane;
                         const bool live = i < qn;
-                        emit(w, srow, live, live ? (int)wq[i] : 0, wbase, whb, wnlo, wshift);
+                        const int e = live ? (int)wq[i] : 0;
+                        const int bpos = e & 31;
+                        const int cc = (e & 0xc00) + ((bpos & 12) << 6) + ((e & 0x3e0) >> 2) + ((bpos & 3) << 1) + (bpos >> 4);
+                        emit(w, srow, live, cc, wbase, whb, wnlo, wshift);
                     }
                     __syncwarp();
                 };
+                const unsigned int code0 = (unsigned)lane << 5;
                 if (total <= AUC_QCAP) {
                     int pos = incl - cnt;
 #pragma unroll
                     for (int s = 0; s < 4; ++s) {
                         unsigned int a = m[s];
-                        const int cb = (s << 10) + lane * 8;
+                        const unsigned int code = code0 | (s << 10);
                         while (a) {
                             const int bpos = __ffs(a) - 1;
                             a &= a - 1;
-                            wq[pos++] = (unsigned short)(cb + ((bpos & 12) << 6) + ((bpos & 3) << 1) + (bpos >> 4));
+                            wq[pos++] = (unsigned short)(code | bpos);
                         }
                     }
                     drain(total);
@@ -1247,7 +1260,7 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
 #pragma unroll
                     for (int s = 0; s < 4; ++s) {
                         unsigned int a = m[s];
-                        const int cb = (s << 10) + lane * 8;
+                        const unsigned int code = code0 | (s << 10);
                         while (__any_sync(0xffffffffu, a != 0)) {
                             const int pc = __popc(a);
                             const int take = pc < 4 ? pc : 4;
@@ -1261,7 +1274,7 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
                             for (int r = 0; r < take; ++r) {
                                 const int bpos = __ffs(a) - 1;
                                 a &= a - 1;
-                                wq[pos++] = (unsigned short)(cb + ((bpos & 12) << 6) + ((bpos & 3) << 1) + (bpos >> 4));
+                                wq[pos++] = (unsigned short)(code | bpos);
                             }
                             drain(__shfl_sync(0xffffffffu, in2, 31));
                         }
@@ -1601,11 +1614,7 @@ auction_bidlist_kernel(const __half* __restrict__ S, long long ld, long long N, 
     if (fused && auction_last_cta(p.ticket)) auction_resolve_body(p, n_global, K, n_global / K, MODE_BID);
 }
 
-static inline size_t auction_hist_smem(int K) {
-    // + seg_cnt_s [K], per-warp survivor masks [NW][4][32], per-warp queues [NW][QCAP], active-row list [K]
-    return auction_hist_smem_fixed(K) + (size_t)K * 4 + (size_t)AUC_NW * 4 * 32 * 4 + (size_t)AUC_NW * AUC_QCAP * 2 +
-           (size_t)K * 2 + 16;
-}
+static inline size_t auction_hist_smem(int K) { return K <= 128 ? HistSmem<128>::TOTAL : HistSmem<256>::TOTAL; }
 
 static inline size_t auction_pass_smem(int K, int J) {
     return (size_t)AUC_NBUF * K * J * 2 + (size_t)K * 16 + (size_t)J * 4 +
@@ -1960,13 +1969,14 @@ static int auction_launch(const AuctionArgs& a, const void* scores_t, int64_t ld
                                         (long long)ld, (long long)n, (int)k, (long long)(n_global / k), a.p,
                                         (unsigned short*)nullptr, 0, (const unsigned short*)nullptr, 0, 1, PeerCtx{}, 0));
     if (which & 2) {
-        static size_t hs_set[RQK_MAX_DEVICES] = {};
+        static bool hs_set[RQK_MAX_DEVICES][2] = {};
         const size_t hs = auction_hist_smem(k);
-        if (hs > hs_set[devi]) {
-            RQK_CUDA_OK(cudaFuncSetAttribute(auction_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
-            hs_set[devi] = hs;
+        auto hkern = (k <= 128) ? auction_hist_kernel<128> : auction_hist_kernel<256>;
+        if (!hs_set[devi][k <= 128 ? 0 : 1]) {
+            RQK_CUDA_OK(cudaFuncSetAttribute(hkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
+            hs_set[devi][k <= 128 ? 0 : 1] = true;
         }
-        RQK_CUDA_OK(launch_round_kernel(auction_hist_kernel, (unsigned)a.G, (unsigned)AUC_THREADS, hs, stream, pdl,
+        RQK_CUDA_OK(launch_round_kernel(hkern, (unsigned)a.G, (unsigned)AUC_THREADS, hs, stream, pdl,
                                         (const __half*)scores_t, (long long)ld, (long long)n, (int)k, a.J, spc, a.p,
                                         (long long)n_global, fused));
     }

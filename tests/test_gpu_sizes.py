@@ -276,10 +276,9 @@ def test_deferred_loss_equals_direct_evaluation(dev, engine):
     torch.manual_seed(9)
     km = KMeans(n_clusters=k, device=dev, balanced=True)
     km.trace_fit = True
-    km.fit_by_min_loss(x, target_nodes_num=target, iter_limit=25, tqdm_flag=False)
+    km.fit_by_min_loss(x, target_nodes_num=target, iter_limit=25, tol=0.0, tqdm_flag=False)   # tol 0: :359 never fires
     tr = km.last_fit_trace
-    assert len(tr) > 11 and [t["reinit"] for t in tr] == [i in (10, 20) for i in range(len(tr))]
-    assert len(tr) == 25 or tr[-1]["shift"] ** 2 < 1e-3                    # :359-362
+    assert len(tr) == 25 and [t["reinit"] for t in tr] == [i in (10, 20) for i in range(25)]   # :305, :361
     direct = []
     for t in tr:
         cnt = engine.score_pass(x, t["centers"], argmin=True, counts=True).counts.cpu().numpy().astype(np.int64)
@@ -288,4 +287,12 @@ def test_deferred_loss_equals_direct_evaluation(dev, engine):
     assert len(set(direct)) > 3, "losses must vary for the test to mean anything"
     best = max(i for i, v in enumerate(direct) if v == min(direct))
     assert torch.equal(km.cluster_centers, tr[best]["centers"]) and km.min_loss == direct[best]
-    assert all(t["shift"] ** 2 >= 1e-3 for t in tr[:-1])
+    # and with the default tolerance the loop stops at the first iteration whose shift^2 < tol (:359)
+    np.random.seed(9)
+    torch.manual_seed(9)
+    km2 = KMeans(n_clusters=k, device=dev, balanced=True)
+    km2.trace_fit = True
+    km2.fit_by_min_loss(x, target_nodes_num=target, iter_limit=25, tqdm_flag=False)
+    sh = [t["shift"] for t in km2.last_fit_trace]
+    stop = next((i for i, v in enumerate(sh) if v ** 2 < 1e-3), 24)
+    assert len(sh) == stop + 1 and sh[:len(sh)] == [t["shift"] for t in tr[:len(sh)]]
