@@ -1021,8 +1021,7 @@ struct HistSmem {
     static constexpr int HIST = 0;                                    // [KP][W/2] two 16-bit counters per word
     static constexpr int COST = HIST + KP * AUC_W * 2;                // [HS_SUB] fp16
     static constexpr int OWN = COST + HS_SUB * 2;                     // [HS_SUB] int16
-    static constexpr int WACC = OWN + HS_SUB * 2;                     // [NW][4][32] survivor masks of a row's steps
-    static constexpr int HQ = WACC + AUC_NW * 4 * 32 * 4;             // [NW][QCAP] survivor queue
+    static constexpr int HQ = OWN + HS_SUB * 2;                       // [NW][QCAP] survivor queue
     static constexpr int ABOVE = HQ + AUC_NW * AUC_QCAP * 2;          // [KP] u32 ...
     static constexpr int GAP = ABOVE + KP * 4;
     static constexpr int RBASE = GAP + KP * 4;
@@ -1067,7 +1066,6 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
     __shared__ int s_nact, s_any_cold, s_wcnt[AUC_NW];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned int lt = (1u << lane) - 1u;
-    unsigned int* const wacc = reinterpret_cast<unsigned int*>(smem_raw + L::WACC) + warp * (4 * 32);
     unsigned short* const wq = reinterpret_cast<unsigned short*>(smem_raw + L::HQ) + warp * AUC_QCAP;
     const int G = gridDim.x, b = blockIdx.x;
     const long long tiles_total = (N + J - 1) / J;
@@ -1173,96 +1171,113 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
             }
         };
         if (!any_cold) {
-            // Fast path (every active row has a fine window).  A warp streams its rows of the sub-range in steps of
-            // 1024 jobs (four 16-byte loads per lane), software-pipelined one step ahead across row boundaries
-            // (two register buffers, ping-pong).  The filter leaves one 32-bit survivor mask per lane and step;
-            // the masks of a row's (up to four) steps are parked in shared memory and handled once per row: one
-            // prefix sum over the lanes' counts, the survivors' positions pushed into the warp's queue, and the
-            // queue drained 32 entries at a time with all lanes busy.
-            // Loads are valid below `lim` (whole 16-byte groups): the sub-range's end, or - in the last sub-range
-            // of the matrix - the padded row end, whose columns >= N hold -inf and never survive.
-            const long long hard_end = (sub + sublen == N) ? ld : c_end;
-            const int lim = (int)((hard_end - sub) < HS_SUB ? (hard_end - sub) : HS_SUB);
-            const int nsteps = (lim + 1023) >> 10;
-            const bool last_full = (lim & 1023) == 0;
-            const int plane = lim - ((nsteps - 1) << 10) - lane * 8;         // last step: load q valid iff (q<<8) < plane
-            const uint4* cbase = reinterpret_cast<const uint4*>(cost_s) + lane;
-            // load cursor
-            int la = warp, lst = 0;
-            const uint4* lrp = nullptr;
-            if (la < nact) lrp = reinterpret_cast<const uint4*>(S + (size_t)act[la] * ld + sub) + lane;
-            auto issue = [&](uint4 (&sv)[4]) {
-                if (la >= nact) return;
-                if (last_full || lst + 1 < nsteps) {
+            // Fast path (every active row has a fine window).  Software-pipelined: the next step's four 16-byte loads
+            // are in flight while this step is filtered, across row boundaries too.  Survivors are not
+            // handled by the lane that found them (a divergent loop, ~5 of 32 lanes busy) but pushed as
+            // job offsets into a per-warp queue and handled 32 at a time when the queue fills / the row ends.
+            int qn = 0;
+            const int nfull = sublen >> 10, nsteps = (sublen + 1023) >> 10;
+            auto load_step = [&](int w, int st, uint4 (&sv)[4]) {
+                const uint4* rp = reinterpret_cast<const uint4*>(S + (size_t)w * ld + sub) + (st << 7) + lane;
+                if (st < nfull) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) sv[q] = ldg_stream128(lrp + q * 32);
-                } else {
+                    for (int q = 0; q < 4; ++q) sv[q] = ldg_stream128(rp + q * 32);
+                } else {   // tail step; columns >= N of S hold -inf and their staged cost is 0: they never survive
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         sv[q] = make_uint4(0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u);
-                        if ((q << 8) < plane) sv[q] = ldg_stream128(lrp + q * 32);
+                        if ((st << 10) + q * 256 + lane * 8 < sublen) sv[q] = ldg_stream128(rp + q * 32);
                     }
                 }
-                ++lst;
-                lrp += 128;
-                if (lst == nsteps) {
-                    lst = 0;
-                    la += AUC_NW;
-                    if (la < nact) lrp = reinterpret_cast<const uint4*>(S + (size_t)act[la] * ld + sub) + lane;
-                }
             };
-            // process cursor
-            int pa = warp, pst = 0;
-            auto row_end = [&](int w) {
+            auto flush = [&](int w) {
                 const __half* srow = S + (size_t)w * ld + sub;
                 const int wbase = sm.r_base[w], whb = sm.r_hbase[w], wnlo = sm.r_nlo[w], wshift = sm.r_shift[w];
-                unsigned int m[4];
-                int cnt = 0;
+                unsigned int* lw = seg_lists + (size_t)w * AUC_SEG_CAP;
+                __syncwarp();
+                for (int i0 = 0; i0 < qn; i0 += 32) {
+                    const int i = i0 + lane;
+                    bool live = i < qn;
+                    const int cc = live ? (int)wq[i] : 0;
+                    live = live && own_s[cc] != w;                               // owner entry: counted above
+                    int key = 0;
+                    if (live) key = (int)h2key(h2bits(__hsub(srow[cc], __ushort_as_half(cost_s[cc]))));
+                    const unsigned int m = __ballot_sync(0xffffffffu, live);
+                    if (m) {
+                        unsigned int slot0 = 0;
+                        if (lane == 0) slot0 = atomicAdd(&seg_cnt_s[w], (unsigned)__popc(m));
+                        slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+                        const unsigned int slot = slot0 + __popc(m & lt);
+                        if (live && slot < AUC_SEG_CAP) lw[slot] = ((unsigned)cc << 16) | (unsigned)key;
+                    }
+                    if (live) {
+                        if (wshift == 0) {
+                            if (key >= whb) {
+                                if (key - whb >= AUC_W - wnlo) atomicAdd(&sm.above[w], 1u);
+                                else hist_add(sm.hist, w, wnlo + key - whb);
+                            } else if (key >= wbase + wnlo) {
+                                atomicAdd(&sm.gap[w], 1u);
+                            } else {
+                                hist_add(sm.hist, w, key - wbase);
+                            }
+                        } else {
+                            const int bin = (key - wbase) >> wshift;
+                            if (bin >= AUC_W) atomicAdd(&sm.above[w], 1u);
+                            else hist_add(sm.hist, w, bin);
+                        }
+                    }
+                }
+                qn = 0;
+                __syncwarp();
+            };
+            uint4 cur[4], nxt[4];
+            int a = warp, st = 0;                                  // position in the active-row list, step in the row
+            int w = a < nact ? (int)act[a] : 0;
+            if (a < nact) load_step(w, 0, cur);
+            while (a < nact) {
+                int an = a, wn = w, sn = st + 1;
+                if (sn == nsteps) { an = a + AUC_NW; sn = 0; wn = an < nact ? (int)act[an] : 0; }
+                if (an < nact) load_step(wn, sn, nxt);
+                // ---- filter: v = S - cost against the window's low edge ----
+                const __half2 f2 = u2h2(sm.r_lo2[w]);
+                const uint4* cp = reinterpret_cast<const uint4*>(cost_s) + (st << 7) + lane;
+                unsigned int acc = 0;   // low half bit 4q+h: job 2h of load q survives; high half: job 2h+1
 #pragma unroll
-                for (int s = 0; s < 4; ++s) { m[s] = (s < nsteps) ? wacc[s * 32 + lane] : 0u; cnt += __popc(m[s]); }
-                int incl = cnt;
+                for (int q = 0; q < 4; ++q) {
+                    const uint4 cv = cp[q * 32];
+                    const unsigned int sw[4] = {cur[q].x, cur[q].y, cur[q].z, cur[q].w};
+                    const unsigned int cw[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        const __half2 v2 = __hsub2(u2h2(sw[h]), u2h2(cw[h]));
+                        acc |= __hge2_mask(v2, f2) & ((1u << (4 * q + h)) | (1u << (16 + 4 * q + h)));
+                    }
+                }
+                // ---- push the survivors' job offsets ----
+                const int mine = __popc(acc);
+                int incl = mine;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
                     const int o = __shfl_up_sync(0xffffffffu, incl, d);
                     if (lane >= d) incl += o;
                 }
                 const int total = __shfl_sync(0xffffffffu, incl, 31);
-                if (total == 0) return;
-                // queue entry = (step << 10) | (lane << 5) | bit position of the mask; decoded when drained
-                auto drain = [&](int qn) {
-                    __syncwarp();
-                    for (int i0 = 0; i0 < qn; i0 += 32) {
-                        const int i = i0 + lane;
-                        const bool live = i < qn;
-                        const int e = live ? (int)wq[i] : 0;
-                        const int bpos = e & 31;
-                        const int cc = (e & 0xc00) + ((bpos & 12) << 6) + ((e & 0x3e0) >> 2) + ((bpos & 3) << 1) + (bpos >> 4);
-                        emit(w, srow, live, cc, wbase, whb, wnlo, wshift);
-                    }
-                    __syncwarp();
-                };
-                const unsigned int code0 = (unsigned)lane << 5;
-                if (total <= AUC_QCAP) {
-                    int pos = incl - cnt;
-#pragma unroll
-                    for (int s = 0; s < 4; ++s) {
-                        unsigned int a = m[s];
-                        const unsigned int code = code0 | (s << 10);
-                        while (a) {
-                            const int bpos = __ffs(a) - 1;
-                            a &= a - 1;
-                            wq[pos++] = (unsigned short)(code | bpos);
+                if (total) {
+                    const int cbase = (st << 10) + lane * 8;
+                    if (qn + total > AUC_QCAP) flush(w);
+                    if (total <= AUC_QCAP) {
+                        int pos = qn + incl - mine;
+                        while (acc) {
+                            const int bpos = __ffs(acc) - 1;
+                            acc &= acc - 1;
+                            const int pq = bpos & 15;
+                            wq[pos++] = (unsigned short)(cbase + ((pq >> 2) << 8) + ((pq & 3) << 1) + (bpos >> 4));
                         }
-                    }
-                    drain(total);
-                } else {
-                    // more than a queue's worth in one row segment (very wide windows): up to 4 per lane per round
-#pragma unroll
-                    for (int s = 0; s < 4; ++s) {
-                        unsigned int a = m[s];
-                        const unsigned int code = code0 | (s << 10);
-                        while (__any_sync(0xffffffffu, a != 0)) {
-                            const int pc = __popc(a);
+                        qn += total;
+                    } else {
+                        // more than a queue's worth in one step (only with very wide windows): 4 per lane per round
+                        while (__any_sync(0xffffffffu, acc != 0)) {
+                            const int pc = __popc(acc);
                             const int take = pc < 4 ? pc : 4;
                             int in2 = take;
 #pragma unroll
@@ -1272,47 +1287,22 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
                             }
                             int pos = in2 - take;
                             for (int r = 0; r < take; ++r) {
-                                const int bpos = __ffs(a) - 1;
-                                a &= a - 1;
-                                wq[pos++] = (unsigned short)(code | bpos);
+                                const int bpos = __ffs(acc) - 1;
+                                acc &= acc - 1;
+                                const int pq = bpos & 15;
+                                wq[pos++] = (unsigned short)(cbase + ((pq >> 2) << 8) + ((pq & 3) << 1) + (bpos >> 4));
                             }
-                            drain(__shfl_sync(0xffffffffu, in2, 31));
+                            qn = __shfl_sync(0xffffffffu, in2, 31);
+                            flush(w);
                         }
                     }
                 }
-            };
-            auto filter = [&](const uint4 (&sv)[4]) {
-                const int w = act[pa];
-                const __half2 f2 = u2h2(sm.r_lo2[w]);
-                const uint4* cp = cbase + (pst << 7);
-                unsigned int acc = 0;   // low half bit 4q+h: job 2h of load q survives; high half: job 2h+1
+                if (sn == 0 && qn) flush(w);                                     // the queue is per row
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint4 cv = cp[q * 32];
-                    const unsigned int sw[4] = {sv[q].x, sv[q].y, sv[q].z, sv[q].w};
-                    const unsigned int cw[4] = {cv.x, cv.y, cv.z, cv.w};
-#pragma unroll
-                    for (int h = 0; h < 4; ++h) {
-                        const __half2 v2 = __hsub2(u2h2(sw[h]), u2h2(cw[h]));
-                        acc |= __hge2_mask(v2, f2) & ((1u << (4 * q + h)) | (1u << (16 + 4 * q + h)));
-                    }
-                }
-                wacc[pst * 32 + lane] = acc;
-                ++pst;
-                if (pst == nsteps) {
-                    row_end(w);
-                    pst = 0;
-                    pa += AUC_NW;
-                }
-            };
-            uint4 bufA[4], bufB[4];
-            issue(bufA);
-            while (pa < nact) {
-                issue(bufB);
-                filter(bufA);
-                if (pa >= nact) break;
-                issue(bufA);
-                filter(bufB);
+                for (int q = 0; q < 4; ++q) cur[q] = nxt[q];
+                a = an;
+                w = wn;
+                st = sn;
             }
         } else {
             for (int a = warp; a < nact; a += AUC_NW) {

@@ -85,6 +85,52 @@ __global__ void gather_rows_kernel(const float* __restrict__ x, int dim, const l
     for (int d = threadIdx.x; d < dim; d += blockDim.x) out[(long long)r * dim + d] = src[d];
 }
 
+// r = x - C[id] without normalisation (simplified_semantic_id_generator.py:78-96, :160-164): one warp per row.
+__global__ void __launch_bounds__(256)
+residual_plain_kernel(const float* __restrict__ x, long long n, int dim, const int* __restrict__ ids,
+                      const float* __restrict__ centers, float* __restrict__ out) {
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const float* xr = x + row * dim;
+    const float* cr = centers + (long long)ids[row] * dim;
+    float* orow = out + row * dim;
+    if (dim % 4 == 0) {
+        for (int d = lane * 4; d < dim; d += 128) {
+            const float4 a = *reinterpret_cast<const float4*>(xr + d), b = *reinterpret_cast<const float4*>(cr + d);
+            *reinterpret_cast<float4*>(orow + d) = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+        }
+    } else {
+        for (int d = lane; d < dim; d += 32) orow[d] = xr[d] - cr[d];
+    }
+}
+
+// ids[row] = argmin over the candidates c with allow[group[row]][c] != 0 of dist[row][c]; first index on ties, 0 if no
+// candidate is allowed (torch.argmin of an all-inf row).  simplified_semantic_id_generator.py:317-331:
+// `dist[batch_match_matrix == 0] = inf; argmin(dist, dim=1)`.  One warp per row.
+__global__ void __launch_bounds__(256)
+masked_argmin_kernel(const float* __restrict__ dist, long long n, int k, const int* __restrict__ group,
+                     const unsigned char* __restrict__ allow, int* __restrict__ out) {
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const float* dr = dist + row * k;
+    const unsigned char* ar = allow + (long long)group[row] * k;
+    float best = __int_as_float(0x7f800000);
+    int arg = 0x7fffffff;
+    for (int c = lane; c < k; c += 32) {
+        const float d = ar[c] ? dr[c] : __int_as_float(0x7f800000);
+        if (d < best) { best = d; arg = c; }                     // strict: the first index wins inside a lane
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (ob < best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+    }
+    if (lane == 0) out[row] = (arg == 0x7fffffff) ? 0 : arg;
+}
+
 int residual_launch(const float* x, long long n, int dim, const int* ids, const float* centers,
                     const int* group_end, int ngroups, float* out, cudaStream_t stream) {
     if (n == 0) return 0;
@@ -113,6 +159,30 @@ int rqk_residual_normalise(const float* x, int64_t n, int32_t dim, const int32_t
     if (dim < 1 || dim > 1024) return fail(RQK_ERR_UNSUPPORTED, "rqk_residual_normalise: dim=%s%lld outside [1,1024]", "", dim);
     if (ngroups < 1 || ngroups > 32) return fail(RQK_ERR_UNSUPPORTED, "rqk_residual_normalise: ngroups=%s%lld outside [1,32]", "", ngroups);
     return residual_launch(x, n, dim, ids, centers, group_end, ngroups, out, (cudaStream_t)stream_);
+}
+
+// out[n][dim] = x - centers[ids] (no normalisation: simplified_semantic_id_generator.py:78-96); out may alias x.
+int rqk_residual_plain(const float* x, int64_t n, int32_t dim, const int32_t* ids, const float* centers, float* out,
+                       void* stream_) {
+    using namespace rqk;
+    if (!x || !ids || !centers || !out) return fail(RQK_ERR_ARG, "rqk_residual_plain: null pointer%s");
+    if (dim < 1) return fail(RQK_ERR_ARG, "rqk_residual_plain: dim=%s%lld < 1", "", dim);
+    if (n == 0) return 0;
+    residual_plain_kernel<<<(unsigned)ceil_div<long long>(n * 32, 256), 256, 0, (cudaStream_t)stream_>>>(x, n, dim, ids, centers, out);
+    RQK_LAUNCH_OK();
+    return 0;
+}
+
+// ids[n] = first argmin of dist[n][k] over the candidates allowed for the row's group (allow: uint8 [ngroups][k]).
+int rqk_masked_argmin(const float* dist, int64_t n, int32_t k, const int32_t* group, const uint8_t* allow,
+                      int32_t ngroups, int32_t* ids, void* stream_) {
+    using namespace rqk;
+    if (!dist || !group || !allow || !ids) return fail(RQK_ERR_ARG, "rqk_masked_argmin: null pointer%s");
+    if (k < 1 || ngroups < 1) return fail(RQK_ERR_ARG, "rqk_masked_argmin: k=%s%lld, ngroups=%lld must be >= 1", "", k, ngroups);
+    if (n == 0) return 0;
+    masked_argmin_kernel<<<(unsigned)ceil_div<long long>(n * 32, 256), 256, 0, (cudaStream_t)stream_>>>(dist, n, k, group, allow, ids);
+    RQK_LAUNCH_OK();
+    return 0;
 }
 
 // out = x * w (per-dim weights, hierarchical_rq_kmeans.py:583-604); out may alias x.

@@ -542,6 +542,32 @@ def residual_normalise(x: torch.Tensor, ids: torch.Tensor, centers: torch.Tensor
     return out
 
 
+def residual_plain(x: torch.Tensor, ids: torch.Tensor, centers: torch.Tensor,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """r = x - centers[ids], not normalised (the Simplified generator's residual; csrc/residual.cu).  out may be x."""
+    _req_cuda(x, "x")
+    n, dim = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    ids32 = ids if ids.dtype == torch.int32 else ids.to(torch.int32)
+    _call(x.device, lib().rqk_residual_plain, _ptr(x), n, dim, _ptr(ids32.contiguous()), _ptr(centers.contiguous()),
+          _ptr(out), _stream(x.device))
+    return out
+
+
+def masked_argmin(dist: torch.Tensor, group: torch.Tensor, allow: torch.Tensor) -> torch.Tensor:
+    """First argmin of dist [n, k] (fp32) over the candidates allowed for each row's group (allow uint8 [groups, k])."""
+    _req_cuda(dist, "dist")
+    n, k = dist.shape
+    dev = dist.device
+    ids = torch.empty(n, dtype=torch.int32, device=dev)
+    g32 = group.to(device=dev, dtype=torch.int32).contiguous()
+    a8 = allow.to(device=dev, dtype=torch.uint8).contiguous()
+    _call(dev, lib().rqk_masked_argmin, _ptr(dist.contiguous()), n, k, _ptr(g32), _ptr(a8), a8.shape[0], _ptr(ids),
+          _stream(dev))
+    return ids
+
+
 def scale_dims(x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     n, dim = x.shape
     if out is None:

@@ -282,10 +282,64 @@ def gen_io():
     print("io:", n, "songs,", len(sem), "distinct ids written")
 
 
+def gen_simplified():
+    """A full run of the reference's second entry point, SimplifiedHierarchicalRQ.train (simplified_semantic_id_
+    generator.py:176-245), on CPU: un-normalised residuals (:78-96), recursive middle layer with `inf` masks
+    (:98-174), last layer = two balanced KMeans.fit + dynamic match matrix (:247-309) + masked prediction (:311-331).
+    Recorded: every stage's centres and ids, and the temporary sub-centres each (l1, l2) group's match-matrix row
+    was built from (KMeans.fit is chaotic: the tests teacher-force on these)."""
+    import tempfile
+    from src.semantic_id_generator import simplified_semantic_id_generator as ref_s
+    n, dim = 3000, 32
+    x = O.synth_mix(n, dim, seed=31, modes=48)
+    lc, nc = [4, 8, 16], [4, 4, 8]
+    cfg = ref_h.HierarchicalRQKMeansConfig(layer_clusters=lc, need_clusters=nc, embedding_dim=dim,
+                                           group_dims=[dim], hierarchical_weights=[[1.0]] * 3, iter_limit=12)
+    tmp = tempfile.mkdtemp()
+    path = os.path.join(tmp, "v.csv")
+    with open(path, "w") as f:
+        for i in range(n):
+            f.write(f"s{i}," + ",".join(repr(float(v)) for v in x[i]) + "\n")
+    fits = []
+    orig_fit = ref_bk.KMeans.fit
+
+    def recording_fit(self, *a, **k):
+        r = orig_fit(self, *a, **k)
+        fits.append(self.cluster_centers.detach().cpu().numpy().copy())
+        return r
+
+    ref_bk.KMeans.fit = recording_fit
+    try:
+        set_seed(42)
+        m = ref_s.SimplifiedHierarchicalRQ(cfg)
+        m.train(path)
+    finally:
+        ref_bk.KMeans.fit = orig_fit
+    ids = np.array([m.semantic_ids[f"s{i}"] for i in range(n)], dtype=np.int64)
+    # order of KMeans.fit calls: need[0] middle sub-fits, 2 candidate fits, then one per (l1, l2) group with > n_need rows
+    sub = fits[nc[0] + 2:]
+    groups = []
+    for i in range(nc[0]):
+        for j in range(nc[1]):
+            cnt = int(((ids[:, 0] == i) & (ids[:, 1] == j)).sum())
+            groups.append(cnt)
+    big = [g for g, c in enumerate(groups) if c > nc[2]]
+    assert len(sub) == len(big), (len(sub), len(big))
+    assert min(groups) > 0, "pick a seed without empty (l1, l2) groups: their rows are host-RNG draws"
+    xl = np.loadtxt(path, delimiter=",", usecols=range(1, dim + 1), dtype=np.float32)
+    np.savez_compressed(os.path.join(OUT, "simplified.npz"), x=xl, ids=ids,
+                        c0=m.trained_kmeans_models[0].cluster_centers.cpu().numpy(),
+                        c_mid=m.middle_layer_centers.cpu().numpy(), c_last=m.final_layer_centers.cpu().numpy(),
+                        match=m.dynamic_match_matrix.numpy().astype(np.uint8), group_sizes=np.array(groups),
+                        sub_groups=np.array(big), sub_centers=np.stack(sub),
+                        layer_clusters=np.array(lc), need_clusters=np.array(nc), iter_limit=12)
+    print("simplified:", n, "rows,", len(big), "groups with a temporary fit,", len({tuple(r) for r in ids.tolist()}), "distinct ids")
+
+
 if __name__ == "__main__":
     import contextlib
     import io
-    which = sys.argv[1:] or ["auction", "eps", "distance", "stage", "encode", "fit_stats", "iter_limit", "io", "middle"]
+    which = sys.argv[1:] or ["auction", "eps", "distance", "stage", "encode", "fit_stats", "iter_limit", "io", "middle", "simplified"]
     for w in which:
         buf = io.StringIO()
         with contextlib.redirect_stdout(buf):   # the reference prints every iteration
