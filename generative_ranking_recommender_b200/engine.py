@@ -172,6 +172,17 @@ class _Uploader:
             self.stage = [torch.empty(self.CHUNK_BYTES // 4, dtype=torch.float32, pin_memory=True) for _ in range(self.NBUF)]
             self.pool = ThreadPoolExecutor(max_workers=self.THREADS, thread_name_prefix="rqk-h2d")
 
+    def warm(self, dev: torch.device):
+        """One-time set-up off the critical path: page-locks the staging buffers, starts the copy threads and pushes
+        one small chunk through every buffer (the first pinned allocation and the first copies on a new stream cost
+        several hundred milliseconds on the B200 box; tools/h2d_probe.py).  HierarchicalRQKMeans' constructor calls
+        it, so the first train() of a process pays only for the bytes it moves."""
+        if self.stage or dev.type != "cuda":
+            return
+        self._setup()
+        probe = np.zeros((self.NBUF * 2, (self.CHUNK_BYTES // 8)), dtype=np.float32)    # 2 chunks per buffer
+        self.upload(probe, dev)
+
     def upload(self, X: np.ndarray, dev: torch.device) -> torch.Tensor:
         n, d = X.shape
         dst = torch.empty((n, d), dtype=torch.float32, device=dev)

@@ -236,6 +236,8 @@ class HierarchicalRQKMeans:
         # train()/predict() is then this rank's contiguous row block
         self._shard = shard
         self.fit_stats: List[List[dict]] = []
+        if torch.device(self.device).type == "cuda" and torch.cuda.is_available():
+            engine.UPLOADER.warm(torch.device(self.device))      # one-time host-side set-up, not part of any fit
 
     # ---- small static helpers kept for API compatibility ----
     @staticmethod

@@ -511,6 +511,58 @@ def predict_hierarchy(x: np.ndarray, centers_list: Sequence[np.ndarray], need_cl
 
 
 # --------------------------------------------------------------------------------------------
+# SimplifiedHierarchicalRQ: simplified_semantic_id_generator.py (second entry point, README.md:192-195)
+# --------------------------------------------------------------------------------------------
+
+def simplified_residual(x: np.ndarray, ids: np.ndarray, centers: np.ndarray) -> np.ndarray:
+    """:78-96 / :160-164: batch - centres[ids], NOT normalised."""
+    return np.asarray(x, np.float32) - np.asarray(centers, np.float32)[np.asarray(ids, np.int64)]
+
+
+def simplified_middle_predict(x: np.ndarray, centers: np.ndarray, prev_ids: np.ndarray, pre_need: int, n_need: int):
+    """:139-174: distances to ALL pre_need * n_need centres, +inf outside the parent's block, argmin; the id
+    reported is raw % n_need, the residual uses the raw id.  Returns (raw ids, residual)."""
+    d = pairwise_distance_full(x, centers)
+    mask = np.full_like(d, np.inf)
+    for j in range(pre_need):                                              # :150-154
+        rows = prev_ids == j
+        if rows.any():
+            mask[rows, j * n_need:(j + 1) * n_need] = 0
+    raw = np.argmin(d + mask, axis=1).astype(np.int64)                     # :156-157
+    return raw, simplified_residual(x, raw, centers)
+
+
+def simplified_match_row(sub_centers: np.ndarray, candidates: np.ndarray, n_need: int,
+                         randint: Callable[[int], int] = np.random.randint) -> np.ndarray:
+    """:284-305 for one (l1, l2) group: every sub-centre takes its nearest not-yet-taken candidate (greedy, in
+    sub-centre order); random fill up to n_need; uint8 [n_candidates] of 0 / 1."""
+    n_cand = candidates.shape[0]
+    dm = np.linalg.norm(sub_centers[:, np.newaxis, :] - candidates[np.newaxis, :, :], axis=2)
+    sel = set()
+    for k in range(len(sub_centers)):
+        for ci in np.argsort(dm[k]):
+            if ci not in sel:
+                sel.add(ci)
+                break
+    while len(sel) < n_need:
+        r = randint(n_cand)
+        if r not in sel:
+            sel.add(r)
+    row = np.zeros(n_cand, dtype=np.uint8)
+    row[list(sel)] = 1
+    return row
+
+
+def simplified_predict_with_matrix(x: np.ndarray, prev1: np.ndarray, prev2: np.ndarray, candidates: np.ndarray,
+                                   match: np.ndarray, n_prev2: int) -> np.ndarray:
+    """:311-331: dist[match[group] == 0] = inf; argmin (ids index the 2K candidates)."""
+    d = pairwise_distance_full(x, candidates)
+    g = np.asarray(prev1, np.int64) * n_prev2 + np.asarray(prev2, np.int64)
+    d[np.asarray(match)[g] == 0] = np.inf
+    return np.argmin(d, axis=1).astype(np.int64)
+
+
+# --------------------------------------------------------------------------------------------
 # collision statistics: debug_collisions.py:27-61, train_semantic_ids.py:300-303
 # --------------------------------------------------------------------------------------------
 

@@ -616,3 +616,80 @@ def test_chunked_upload_of_pageable_rows(dev, engine):
     assert torch.equal(engine.h2d_rows(xs, dev), torch.from_numpy(np.ascontiguousarray(xs)).to(dev))
     small = x[:100]
     assert torch.equal(engine.h2d_rows(small, dev), torch.from_numpy(small).to(dev))
+
+
+# ------------------------------------------------------------------------------------------------
+# SimplifiedHierarchicalRQ: the reference's second entry point on this engine
+# ------------------------------------------------------------------------------------------------
+def _simplified_model(g):
+    from generative_ranking_recommender_b200.hierarchical_rq_kmeans import HierarchicalRQKMeansConfig
+    from generative_ranking_recommender_b200.simplified_semantic_id_generator import SimplifiedHierarchicalRQ
+    cfg = HierarchicalRQKMeansConfig(layer_clusters=[int(v) for v in g["layer_clusters"]],
+                                     need_clusters=[int(v) for v in g["need_clusters"]], embedding_dim=g["x"].shape[1],
+                                     group_dims=[g["x"].shape[1]], hierarchical_weights=[[1.0]] * 3, iter_limit=int(g["iter_limit"]))
+    return SimplifiedHierarchicalRQ(cfg)
+
+
+def test_simplified_generator_teacher_forced_on_reference_run(dev, engine, golden_dir):
+    """Every stage of SimplifiedHierarchicalRQ.train on the centres of an unmodified reference run (CPU, fixture):
+    un-normalised residuals (:78-96), inf-masked recursive middle layer (:139-174), the greedy dynamic match matrix
+    (:284-305) and the masked last-layer prediction (:311-331) reproduce the reference's ids and matrix exactly."""
+    from generative_ranking_recommender_b200.balancekmeans import KMeans
+    g = np.load(os.path.join(golden_dir, "simplified.npz"))
+    m = _simplified_model(g)
+    x, ids, need = torch.from_numpy(g["x"]).to(dev), g["ids"], [int(v) for v in g["need_clusters"]]
+    km0 = KMeans(n_clusters=need[0], cluster_centers=torch.from_numpy(g["c0"]).to(dev), device=dev)
+    ids0 = km0.predict(x)
+    assert np.array_equal(ids0.numpy(), ids[:, 0])
+    res1 = m._get_residuals(x, km0)
+    assert np.abs(res1.cpu().numpy() - O.simplified_residual(g["x"], ids[:, 0], g["c0"])).max() <= 1e-6
+    c_mid = torch.from_numpy(g["c_mid"]).to(dev)
+    from generative_ranking_recommender_b200.hierarchical_rq_kmeans import HierarchicalRQKMeans
+    raw = HierarchicalRQKMeans._reassign_middle_layer(res1, c_mid, ids0.to(dev), need[0], need[1])
+    assert np.array_equal((raw % need[1]).cpu().numpy(), ids[:, 1]) and np.array_equal((raw // need[1]).cpu().numpy(), ids[:, 0])
+    res2 = engine.residual_plain(res1, raw, c_mid)
+    want_raw, want_res2 = O.simplified_middle_predict(O.simplified_residual(g["x"], ids[:, 0], g["c0"]), g["c_mid"],
+                                                      ids[:, 0], need[0], need[1])
+    assert np.array_equal(raw.cpu().numpy(), want_raw) and np.abs(res2.cpu().numpy() - want_res2).max() <= 1e-6
+    for grp, sub in zip(g["sub_groups"], g["sub_centers"]):
+        assert np.array_equal(np.array(m._match_row(sub, g["c_last"], need[2]), dtype=np.uint8), g["match"][grp])
+    last = m._predict_with_dynamic_matrix(res2, torch.from_numpy(ids[:, 0]), torch.from_numpy(ids[:, 1]),
+                                          torch.from_numpy(g["c_last"]), torch.from_numpy(g["match"]).float(), batch_size=1000)
+    assert np.array_equal(last.cpu().numpy(), ids[:, 2])
+
+
+def test_simplified_generator_trains_end_to_end(dev, engine, golden_dir, tmp_path):
+    """train() from a CSV file as the reference's __main__ drives it: ids in range, reproducible under the
+    reference's seeds, the jsonl it writes, save_model / load_model; as many distinct codes as the reference's
+    own run on the same data (108 of 128), within the spread a chaotic fit allows."""
+    import json
+    g = np.load(os.path.join(golden_dir, "simplified.npz"))
+    need = [int(v) for v in g["need_clusters"]]
+    path = str(tmp_path / "v.csv")
+    with open(path, "w") as f:
+        for i, row in enumerate(g["x"]):
+            f.write(f"s{i}," + ",".join(repr(float(v)) for v in row) + "\n")
+    runs = []
+    for _ in range(2):
+        np.random.seed(42)
+        torch.manual_seed(42)
+        m = _simplified_model(g)
+        m.train(path)
+        runs.append(np.array([m.semantic_ids[f"s{i}"] for i in range(len(g["x"]))]))
+    ids = runs[0]
+    assert np.array_equal(runs[0], runs[1])
+    assert ids[:, 0].max() < need[0] and ids[:, 1].max() < need[1] and ids[:, 2].max() < 2 * int(g["layer_clusters"][2])
+    assert tuple(m.middle_layer_centers.shape) == (need[0] * need[1], g["x"].shape[1])
+    assert tuple(m.dynamic_match_matrix.shape) == (need[0] * need[1], 2 * int(g["layer_clusters"][2]))
+    assert (m.dynamic_match_matrix.sum(1) == need[2]).all()
+    allowed = m.dynamic_match_matrix[torch.from_numpy(ids[:, 0] * need[1] + ids[:, 1])]
+    assert (allowed[torch.arange(len(ids)), torch.from_numpy(ids[:, 2])] == 1).all()       # every id is an allowed candidate
+    uniq, ref_uniq = len({tuple(r) for r in ids.tolist()}), len({tuple(r) for r in g["ids"].tolist()})
+    assert abs(uniq - ref_uniq) <= 0.15 * ref_uniq, (uniq, ref_uniq)
+    out = str(tmp_path / "ids.jsonl")
+    m.save_semantic_ids(out)
+    lines = open(out).read().splitlines()
+    assert len(lines) == len(ids) and json.loads(lines[5]) == {"song_id": "s5", "semantic_ids": ids[5].tolist()}
+    m.save_model(str(tmp_path / "model.pkl"))
+    m2 = type(m).load_model(str(tmp_path / "model.pkl"))
+    assert torch.equal(m2.final_layer_centers.cpu(), m.final_layer_centers.cpu()) and m2.trained_kmeans_models[1] is None

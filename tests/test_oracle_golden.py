@@ -211,3 +211,23 @@ def test_middle_layer_restatement_against_reference_run(golden_dir):
     # the reference's predict() differs from its own train() ids after a recursive layer (residual from the first
     # parent's block, :577 after :1231) - the restatement must reproduce that, not "fix" it
     assert (pred[:, 2] != tid[2]).mean() > 0.2
+
+
+def test_simplified_generator_restatement_against_reference_run(golden_dir):
+    """SimplifiedHierarchicalRQ (the reference's second entry point): given the centres of an unmodified
+    reference run, the restated stages - un-normalised residuals, inf-masked middle layer, greedy dynamic match
+    matrix, masked last-layer prediction - give the reference's ids and match matrix."""
+    g = _load(golden_dir, "simplified.npz")
+    x, ids, need = g["x"], g["ids"], [int(v) for v in g["need_clusters"]]
+    ids0 = O.predict(x, g["c0"])
+    assert np.array_equal(ids0, ids[:, 0])
+    res1 = O.simplified_residual(x, ids0, g["c0"])
+    raw, res2 = O.simplified_middle_predict(res1, g["c_mid"], ids0, need[0], need[1])
+    assert np.array_equal(raw // need[1], ids0) and np.array_equal(raw % need[1], ids[:, 1])
+    assert len(g["sub_groups"]) == need[0] * need[1]                  # every group went through a temporary fit
+    for row, (grp, sub) in enumerate(zip(g["sub_groups"], g["sub_centers"])):
+        assert np.array_equal(O.simplified_match_row(sub, g["c_last"], need[2]), g["match"][grp]), grp
+    assert (g["match"].sum(1) == need[2]).all()
+    last = O.simplified_predict_with_matrix(res2, ids[:, 0], ids[:, 1], g["c_last"], g["match"], need[1])
+    assert np.array_equal(last, ids[:, 2])
+    assert ids[:, 2].max() >= need[2]                                  # raw candidate indices, not remapped (:229)
