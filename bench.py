@@ -632,6 +632,7 @@ def main():
                     "d2h_bytes_per_step": ids_bytes * world / max(iters, 1), "seconds": dt, "iterations": iters,
                     "iterations_per_level": [len(s) for s in model.fit_stats]}
 
+        run_train(np.ascontiguousarray(x_np[:65536]))        # warm-up: a small fit through the same API (allocator, streams)
         e2e = run_train(x_np)
         e2e["host_memory"] = "pageable np.ndarray"
         e2e["api"] = "HierarchicalRQKMeans.train(np.ndarray) -> cluster_ids (int64, host), iter_limit=20"

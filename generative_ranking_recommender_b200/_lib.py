@@ -58,7 +58,7 @@ SIGNATURES = {
     "rqk_residual_normalise": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_p, c_p, c_i32, c_p, c_p]),
     "rqk_scale_dims": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_p, c_p]),
     "rqk_residual_plain": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_p, c_p, c_p]),
-    "rqk_masked_argmin": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_p, c_i32, c_p, c_p]),
+    "rqk_masked_argmin": (ctypes.c_int, [c_p, c_i64, c_i32, c_p, c_p, c_i32, c_i32, c_p, c_p]),
     "rqk_gather_rows": (ctypes.c_int, [c_p, c_i32, c_p, c_i32, c_p, c_p]),
     "rqk_encode_workspace_bytes": (c_sz, [c_i64, c_i32, c_i32]),
     "rqk_encode": (ctypes.c_int, [c_p, c_i64, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p, c_i32, c_p, c_i32, c_i32,

@@ -1064,7 +1064,6 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
     unsigned int* const seg_cnt_s = reinterpret_cast<unsigned int*>(smem_raw + L::SEGCNT);
     unsigned short* const act = reinterpret_cast<unsigned short*>(smem_raw + L::ACT);
     __shared__ int s_nact, s_any_cold, s_wcnt[AUC_NW];
-    __shared__ unsigned int s_qcnt[AUC_NW];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned int lt = (1u << lane) - 1u;
     unsigned short* const wq = reinterpret_cast<unsigned short*>(smem_raw + L::HQ) + warp * AUC_QCAP;
@@ -1172,70 +1171,81 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
             }
         };
         if (!any_cold) {
-            // Fast path (every active row has a fine window).  A warp streams its rows of the sub-range in steps of
-            // 1024 jobs (four 16-byte loads per lane), software-pipelined one step ahead across row boundaries: two
-            // register buffers used alternately (no register copies), a load cursor that runs one step ahead of the
-            // process cursor and advances its row pointer incrementally.  Survivors are not handled by the lane that
-            // found them (a divergent loop, ~5 of 32 lanes busy) but pushed as packed positions into a per-warp queue
-            // - slots handed out by one shared-memory atomic per lane with survivors, order irrelevant - and handled
-            // 32 at a time when the queue fills / the row ends.
+            // Fast path (every active row has a fine window).  Software-pipelined: the next step's four 16-byte loads
+            // are in flight while this step is filtered, across row boundaries too.  Survivors are not
+            // handled by the lane that found them (a divergent loop, ~5 of 32 lanes busy) but pushed as
+            // job offsets into a per-warp queue and handled 32 at a time when the queue fills / the row ends.
+            int qn = 0;
             const int nfull = sublen >> 10, nsteps = (sublen + 1023) >> 10;
-            const int ptail = sublen - (nfull << 10) - lane * 8;          // tail step: load q valid iff (q << 8) < ptail
-            const uint4* cbase = reinterpret_cast<const uint4*>(cost_s) + lane;
-            unsigned int* const qcnt = &s_qcnt[warp];
-            if (lane == 0) *qcnt = 0;
-            __syncwarp();
-            int la = warp, lst = 0;                                         // load cursor
-            const uint4* lrp = nullptr;
-            if (la < nact) lrp = reinterpret_cast<const uint4*>(S + (size_t)act[la] * ld + sub) + lane;
-            auto issue = [&](uint4 (&sv)[4]) {
-                if (la >= nact) return;
-                if (lst < nfull) {
+            auto load_step = [&](int w, int st, uint4 (&sv)[4]) {
+                const uint4* rp = reinterpret_cast<const uint4*>(S + (size_t)w * ld + sub) + (st << 7) + lane;
+                if (st < nfull) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) sv[q] = ldg_stream128(lrp + q * 32);
+                    for (int q = 0; q < 4; ++q) sv[q] = ldg_stream128(rp + q * 32);
                 } else {   // tail step; columns >= N of S hold -inf and their staged cost is 0: they never survive
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         sv[q] = make_uint4(0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u, 0xfc00fc00u);
-                        if ((q << 8) < ptail) sv[q] = ldg_stream128(lrp + q * 32);
+                        if ((st << 10) + q * 256 + lane * 8 < sublen) sv[q] = ldg_stream128(rp + q * 32);
                     }
                 }
-                ++lst;
-                lrp += 128;
-                if (lst == nsteps) {
-                    lst = 0;
-                    la += AUC_NW;
-                    if (la < nact) lrp = reinterpret_cast<const uint4*>(S + (size_t)act[la] * ld + sub) + lane;
-                }
             };
-            int pa = warp, pst = 0, qn = 0;                                 // process cursor, queue fill
-            int w = pa < nact ? (int)act[pa] : 0;
-            // queue entry = (step << 10) | (lane << 5) | bit position of the survivor mask; decoded when drained
-            auto flush = [&]() {
+            auto flush = [&](int w) {
                 const __half* srow = S + (size_t)w * ld + sub;
                 const int wbase = sm.r_base[w], whb = sm.r_hbase[w], wnlo = sm.r_nlo[w], wshift = sm.r_shift[w];
+                unsigned int* lw = seg_lists + (size_t)w * AUC_SEG_CAP;
                 __syncwarp();
                 for (int i0 = 0; i0 < qn; i0 += 32) {
                     const int i = i0 + lane;
-                    const bool live = i < qn;
-                    const int e = live ? (int)wq[i] : 0;
-                    const int bpos = e & 31;
-                    const int cc = (e & 0xc00) + ((bpos & 12) << 6) + ((e & 0x3e0) >> 2) + ((bpos & 3) << 1) + (bpos >> 4);
-                    emit(w, srow, live, cc, wbase, whb, wnlo, wshift);
+                    bool live = i < qn;
+                    const int cc = live ? (int)wq[i] : 0;
+                    live = live && own_s[cc] != w;                               // owner entry: counted above
+                    int key = 0;
+                    if (live) key = (int)h2key(h2bits(__hsub(srow[cc], __ushort_as_half(cost_s[cc]))));
+                    const unsigned int m = __ballot_sync(0xffffffffu, live);
+                    if (m) {
+                        unsigned int slot0 = 0;
+                        if (lane == 0) slot0 = atomicAdd(&seg_cnt_s[w], (unsigned)__popc(m));
+                        slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+                        const unsigned int slot = slot0 + __popc(m & lt);
+                        if (live && slot < AUC_SEG_CAP) lw[slot] = ((unsigned)cc << 16) | (unsigned)key;
+                    }
+                    if (live) {
+                        if (wshift == 0) {
+                            if (key >= whb) {
+                                if (key - whb >= AUC_W - wnlo) atomicAdd(&sm.above[w], 1u);
+                                else hist_add(sm.hist, w, wnlo + key - whb);
+                            } else if (key >= wbase + wnlo) {
+                                atomicAdd(&sm.gap[w], 1u);
+                            } else {
+                                hist_add(sm.hist, w, key - wbase);
+                            }
+                        } else {
+                            const int bin = (key - wbase) >> wshift;
+                            if (bin >= AUC_W) atomicAdd(&sm.above[w], 1u);
+                            else hist_add(sm.hist, w, bin);
+                        }
+                    }
                 }
                 qn = 0;
-                if (lane == 0) *qcnt = 0;
                 __syncwarp();
             };
-            auto step = [&](const uint4 (&sv)[4]) {
+            uint4 cur[4], nxt[4];
+            int a = warp, st = 0;                                  // position in the active-row list, step in the row
+            int w = a < nact ? (int)act[a] : 0;
+            if (a < nact) load_step(w, 0, cur);
+            while (a < nact) {
+                int an = a, wn = w, sn = st + 1;
+                if (sn == nsteps) { an = a + AUC_NW; sn = 0; wn = an < nact ? (int)act[an] : 0; }
+                if (an < nact) load_step(wn, sn, nxt);
                 // ---- filter: v = S - cost against the window's low edge ----
                 const __half2 f2 = u2h2(sm.r_lo2[w]);
-                const uint4* cp = cbase + (pst << 7);
+                const uint4* cp = reinterpret_cast<const uint4*>(cost_s) + (st << 7) + lane;
                 unsigned int acc = 0;   // low half bit 4q+h: job 2h of load q survives; high half: job 2h+1
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const uint4 cv = cp[q * 32];
-                    const unsigned int sw[4] = {sv[q].x, sv[q].y, sv[q].z, sv[q].w};
+                    const unsigned int sw[4] = {cur[q].x, cur[q].y, cur[q].z, cur[q].w};
                     const unsigned int cw[4] = {cv.x, cv.y, cv.z, cv.w};
 #pragma unroll
                     for (int h = 0; h < 4; ++h) {
@@ -1243,20 +1253,25 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
                         acc |= __hge2_mask(v2, f2) & ((1u << (4 * q + h)) | (1u << (16 + 4 * q + h)));
                     }
                 }
-                // ---- push the survivors' positions ----
-                if (__any_sync(0xffffffffu, acc != 0)) {
-                    const int mine = __popc(acc);
-                    const int total = __reduce_add_sync(0xffffffffu, mine);
-                    const unsigned int code = ((unsigned)pst << 10) | ((unsigned)lane << 5);
-                    if (qn + total > AUC_QCAP) flush();
+                // ---- push the survivors' job offsets ----
+                const int mine = __popc(acc);
+                int incl = mine;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += o;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                if (total) {
+                    const int cbase = (st << 10) + lane * 8;
+                    if (qn + total > AUC_QCAP) flush(w);
                     if (total <= AUC_QCAP) {
-                        if (mine) {
-                            unsigned int pos = atomicAdd(qcnt, (unsigned)mine);
-                            while (acc) {
-                                const int bpos = __ffs(acc) - 1;
-                                acc &= acc - 1;
-                                wq[pos++] = (unsigned short)(code | bpos);
-                            }
+                        int pos = qn + incl - mine;
+                        while (acc) {
+                            const int bpos = __ffs(acc) - 1;
+                            acc &= acc - 1;
+                            const int pq = bpos & 15;
+                            wq[pos++] = (unsigned short)(cbase + ((pq >> 2) << 8) + ((pq & 3) << 1) + (bpos >> 4));
                         }
                         qn += total;
                     } else {
@@ -1274,29 +1289,20 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
                             for (int r = 0; r < take; ++r) {
                                 const int bpos = __ffs(acc) - 1;
                                 acc &= acc - 1;
-                                wq[pos++] = (unsigned short)(code | bpos);
+                                const int pq = bpos & 15;
+                                wq[pos++] = (unsigned short)(cbase + ((pq >> 2) << 8) + ((pq & 3) << 1) + (bpos >> 4));
                             }
                             qn = __shfl_sync(0xffffffffu, in2, 31);
-                            flush();
+                            flush(w);
                         }
                     }
                 }
-                ++pst;
-                if (pst == nsteps) {                                         // the queue is per row
-                    if (qn) flush();
-                    pst = 0;
-                    pa += AUC_NW;
-                    if (pa < nact) w = act[pa];
-                }
-            };
-            uint4 bufA[4], bufB[4];
-            issue(bufA);
-            while (pa < nact) {
-                issue(bufB);
-                step(bufA);
-                if (pa >= nact) break;
-                issue(bufA);
-                step(bufB);
+                if (sn == 0 && qn) flush(w);                                     // the queue is per row
+#pragma unroll
+                for (int q = 0; q < 4; ++q) cur[q] = nxt[q];
+                a = an;
+                w = wn;
+                st = sn;
             }
         } else {
             for (int a = warp; a < nact; a += AUC_NW) {

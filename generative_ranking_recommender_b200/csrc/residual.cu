@@ -108,9 +108,11 @@ residual_plain_kernel(const float* __restrict__ x, long long n, int dim, const i
 // ids[row] = argmin over the candidates c with allow[group[row]][c] != 0 of dist[row][c]; first index on ties, 0 if no
 // candidate is allowed (torch.argmin of an all-inf row).  simplified_semantic_id_generator.py:317-331:
 // `dist[batch_match_matrix == 0] = inf; argmin(dist, dim=1)`.  One warp per row.
+// penalty == 0: a disallowed candidate counts as +inf (the Simplified generator); penalty != 0: as fl32(d + 10000),
+// the reference's `distance.add_(10000.0 * (1 - match))` (hierarchical_rq_kmeans.py:953, :1288), one fp32 rounding.
 __global__ void __launch_bounds__(256)
 masked_argmin_kernel(const float* __restrict__ dist, long long n, int k, const int* __restrict__ group,
-                     const unsigned char* __restrict__ allow, int* __restrict__ out) {
+                     const unsigned char* __restrict__ allow, int penalty, int* __restrict__ out) {
     const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= n) return;
@@ -119,7 +121,7 @@ masked_argmin_kernel(const float* __restrict__ dist, long long n, int k, const i
     float best = __int_as_float(0x7f800000);
     int arg = 0x7fffffff;
     for (int c = lane; c < k; c += 32) {
-        const float d = ar[c] ? dr[c] : __int_as_float(0x7f800000);
+        const float d = ar[c] ? dr[c] : (penalty ? __fadd_rn(dr[c], 10000.0f) : __int_as_float(0x7f800000));
         if (d < best) { best = d; arg = c; }                     // strict: the first index wins inside a lane
     }
 #pragma unroll
@@ -173,14 +175,15 @@ int rqk_residual_plain(const float* x, int64_t n, int32_t dim, const int32_t* id
     return 0;
 }
 
-// ids[n] = first argmin of dist[n][k] over the candidates allowed for the row's group (allow: uint8 [ngroups][k]).
+// ids[n] = first argmin of dist[n][k] over the candidates allowed for the row's group (allow: uint8 [ngroups][k]);
+// penalty 0: disallowed = +inf; 1: disallowed = fl32(d + 10000) (the reference's last-layer match-matrix mask).
 int rqk_masked_argmin(const float* dist, int64_t n, int32_t k, const int32_t* group, const uint8_t* allow,
-                      int32_t ngroups, int32_t* ids, void* stream_) {
+                      int32_t ngroups, int32_t penalty, int32_t* ids, void* stream_) {
     using namespace rqk;
     if (!dist || !group || !allow || !ids) return fail(RQK_ERR_ARG, "rqk_masked_argmin: null pointer%s");
     if (k < 1 || ngroups < 1) return fail(RQK_ERR_ARG, "rqk_masked_argmin: k=%s%lld, ngroups=%lld must be >= 1", "", k, ngroups);
     if (n == 0) return 0;
-    masked_argmin_kernel<<<(unsigned)ceil_div<long long>(n * 32, 256), 256, 0, (cudaStream_t)stream_>>>(dist, n, k, group, allow, ids);
+    masked_argmin_kernel<<<(unsigned)ceil_div<long long>(n * 32, 256), 256, 0, (cudaStream_t)stream_>>>(dist, n, k, group, allow, penalty, ids);
     RQK_LAUNCH_OK();
     return 0;
 }

@@ -566,15 +566,16 @@ def residual_plain(x: torch.Tensor, ids: torch.Tensor, centers: torch.Tensor,
     return out
 
 
-def masked_argmin(dist: torch.Tensor, group: torch.Tensor, allow: torch.Tensor) -> torch.Tensor:
-    """First argmin of dist [n, k] (fp32) over the candidates allowed for each row's group (allow uint8 [groups, k])."""
+def masked_argmin(dist: torch.Tensor, group: torch.Tensor, allow: torch.Tensor, penalty: bool = False) -> torch.Tensor:
+    """First argmin of dist [n, k] (fp32) over the candidates allowed for each row's group (allow uint8 [groups, k]).
+    penalty: disallowed candidates compete with fl32(d + 10000) (the reference's match-matrix mask) instead of inf."""
     _req_cuda(dist, "dist")
     n, k = dist.shape
     dev = dist.device
     ids = torch.empty(n, dtype=torch.int32, device=dev)
     g32 = group.to(device=dev, dtype=torch.int32).contiguous()
     a8 = allow.to(device=dev, dtype=torch.uint8).contiguous()
-    _call(dev, lib().rqk_masked_argmin, _ptr(dist.contiguous()), n, k, _ptr(g32), _ptr(a8), a8.shape[0], _ptr(ids),
+    _call(dev, lib().rqk_masked_argmin, _ptr(dist.contiguous()), n, k, _ptr(g32), _ptr(a8), a8.shape[0], 1 if penalty else 0, _ptr(ids),
           _stream(dev))
     return ids
 

@@ -10,9 +10,11 @@ that file): same classes, constructor arguments, return types, exceptions and on
 Underneath, the hot path (direct strategy, layer_clusters == need_clusters, :438-447 -> :606-669) runs
 on sm_100a kernels through `balancekmeans.KMeans` and `engine`; the data stays on the GPU across levels
 and the per-level residual overwrites the level's input in place (the reference keeps three N x D
-copies per level).  The recursive middle-layer and dual-KMeans last-layer strategies of the shipped
-PROD config (layer_clusters != need_clusters) are the next rows of the scope table and
-raise NotImplementedError here rather than running on some other path.
+copies per level).  The two strategies of the shipped PROD config's shape (layer_clusters != need_clusters) run on
+the same kernels: the recursive middle layer (:671-752, :839-904) and the last layer's two balanced fits + match
+matrix (:754-837, :906-1086).  What stays out: layers with 512 or more clusters (`half=True`, the fp16-cdist
+regime of `pairwise_distance_half`; the kernels take K <= 256), which raise NotImplementedError rather than running
+somewhere else.
 """
 from __future__ import annotations
 
@@ -385,9 +387,7 @@ class HierarchicalRQKMeans:
                 if n_clusters == need_clusters:                                         # :438-447
                     centers, ids = self._train_layer_0(layer_data, layer)
                 elif layer == L - 1:                                                    # :449-462
-                    raise NotImplementedError(
-                        "last-layer dual-KMeans + match-matrix strategy (layer_clusters != need_clusters) "
-                        "is the next scope row (SURVEY.md 8f), not built yet")
+                    centers, ids = self._train_last_layer(layer_data, layer)
                 else:                                                                   # :464-475
                     centers, ids, raw_ids = self._train_middle_layer(layer_data, layer)
                 if layer < L - 1:
@@ -401,7 +401,9 @@ class HierarchicalRQKMeans:
                 if self.checkpoint_manager:                                             # :482-498
                     # the residual leaves the device while the next layer trains (its first in-place write waits
                     # for the copy on the stream; the pickle is written by a thread)
-                    self.checkpoint_manager.save_layer_checkpoint(layer, ids_cpu, current_data, centers, None,
+                    layer_match = self.match_matrices[-1] if (layer == L - 1 and n_clusters != need_clusters and
+                                                              self.match_matrices) else None
+                    self.checkpoint_manager.save_layer_checkpoint(layer, ids_cpu, current_data, centers, layer_match,
                                                                   asynchronous=True)
                 logger.info(f"[LAYER {layer + 1}] Completed in {time.time() - layer_start_time:.2f}s")
             except Exception as e:
@@ -483,6 +485,126 @@ class HierarchicalRQKMeans:
         raw = self._reassign_middle_layer(X, centers, prev, pre_need, cur_need)
         return centers, raw % cur_need, raw
 
+    # ---- last layer: two balanced fits + match matrix (:754-837) ----
+    def _train_last_layer(self, X: torch.Tensor, layer: int):
+        """:754-837.  Candidates = the 2 * layer_clusters[-1] centres of two balanced `KMeans.fit` runs; every
+        (l1, l2) group may use need[-1] of them (`_assign_last_match_matrix`); ids are positions inside the
+        group's allowed set.  Returns (candidate centres, ids in [0, need))."""
+        if self._shard is not None and self._shard.active:
+            raise NotImplementedError("the last-layer match-matrix strategy with rows sharded over GPUs is not built yet")
+        n_clusters = self.config.layer_clusters[layer]
+        need_clusters = self.config.need_clusters[layer]
+        if len(self.result_cluster_ids) < 2:
+            raise RuntimeError(
+                f"Previous layers cluster IDs not found. "
+                f"Expected at least 2 layers but only have {len(self.result_cluster_ids)} layers.")
+        kmeans_centers_list, stats = [], []
+        for _part in range(2):                                                          # :792-806
+            kmeans = KMeans(n_clusters=n_clusters, device=self.device, balanced=True)
+            kmeans.fit(X=X, distance="euclidean", iter_limit=20, tqdm_flag=False, half=n_clusters >= 512, online=False)
+            kmeans_centers_list.append(kmeans.cluster_centers.detach())
+        self.fit_stats.append(stats)
+        cur_kmeans_centers = torch.cat(kmeans_centers_list, dim=0)                      # :809
+        prev_prev_cluster_ids = self.result_cluster_ids[-2].cpu().numpy()
+        prev_cluster_ids = self.result_cluster_ids[-1].cpu().numpy()
+        prev_prev_need_cluster = self.config.need_clusters[layer - 2]
+        match_matrix = self._assign_last_match_matrix(
+            cur_kmeans_centers, 2 * n_clusters, X, prev_prev_need_cluster, self.config.need_clusters[layer - 1],
+            prev_prev_cluster_ids, prev_cluster_ids, need_clusters, 2 * need_clusters, layer)
+        self.match_matrices.append(match_matrix)                                        # :821
+        # :824 - multiplies by need[layer - 2], not need[layer - 1] (SURVEY.md A13); kept
+        before_cluster_ids = prev_prev_cluster_ids * prev_prev_need_cluster + prev_cluster_ids
+        raw = self._reassign_last_layer(X, cur_kmeans_centers, before_cluster_ids, match_matrix)
+        ids = self._merge_match_matrix_cluster_ids(match_matrix, raw, before_cluster_ids)
+        return cur_kmeans_centers, ids.to(X.device)
+
+    def _assign_last_match_matrix(self, cur_kmeans_centers: torch.Tensor, cur_n_cluster: int, X: torch.Tensor,
+                                  prev_prev_need_cluster: int, prev_need_cluster: int, prev_prev_cluster_ids: np.ndarray,
+                                  prev_cluster_ids: np.ndarray, cur_need_cluster: int, cur_trunct_cluster: int,
+                                  layer: int) -> List[List[int]]:
+        """:968-1052.  Row (i, j): empty group -> all zeros; up to need rows -> the rows themselves; fewer than
+        2 * need -> a host-RNG subset of need rows; else the centres of a balanced sub-fit.  Each sub-centre then
+        takes its nearest unused candidate (`torch.cdist` there; the score-pass kernel here), random fill (host RNG)
+        if fewer than need were taken.  Host RNG calls happen in the reference's order."""
+        dev = X.device
+        group = torch.from_numpy(prev_prev_cluster_ids.astype(np.int64) * prev_need_cluster +
+                                 prev_cluster_ids.astype(np.int64)).to(dev)
+        order = torch.argsort(group, stable=True)                   # np.where(...)[0] order: ascending rows
+        counts = torch.bincount(group, minlength=prev_prev_need_cluster * prev_need_cluster).cpu().tolist()
+        cur_match_matrix, start = [], 0
+        for g in range(prev_prev_need_cluster * prev_need_cluster):
+            rows = order[start:start + counts[g]]
+            start += counts[g]
+            if counts[g] == 0:                                                          # :996-998
+                cur_match_matrix.append([0] * cur_n_cluster)
+                continue
+            if counts[g] <= cur_need_cluster:                                           # :1002-1003
+                sub_centers = engine.gather_rows(X, rows)
+            elif counts[g] < cur_trunct_cluster:                                        # :1004-1007
+                random_idx = np.random.choice(counts[g], cur_need_cluster, replace=False)
+                sub_centers = engine.gather_rows(X, rows[torch.from_numpy(random_idx).to(dev)])
+            else:                                                                       # :1008-1015
+                sub_kmeans = KMeans(n_clusters=cur_need_cluster, device=self.device, balanced=True)
+                adaptive_iter = self._calculate_adaptive_iter_limit(counts[g], cur_need_cluster, layer, base_iter_limit=20)
+                sub_kmeans.fit(X=engine.gather_rows(X, rows), distance="euclidean", iter_limit=adaptive_iter,
+                               tqdm_flag=False, half=False, online=False)
+                sub_centers = sub_kmeans.cluster_centers
+            cur_match_matrix.append(self._match_row_last_layer(sub_centers, cur_kmeans_centers, cur_need_cluster))
+        return cur_match_matrix
+
+    @staticmethod
+    def _match_row_last_layer(sub_centers: torch.Tensor, cur_kmeans_centers: torch.Tensor, cur_need_cluster: int) -> List[int]:
+        """:1017-1050 for one group: greedy nearest unused candidate per sub-centre, first index on ties, random fill."""
+        cur_n_cluster = len(cur_kmeans_centers)
+        distances = engine.score_pass(sub_centers.float().contiguous(), cur_kmeans_centers.float().contiguous(),
+                                      argmin=False, dist=True).dist.cpu().numpy()
+        match_matrix_row = [0] * cur_n_cluster
+        exist_idx_set = set()
+        for j_idx in range(min(len(sub_centers), cur_need_cluster)):
+            dist_row = distances[j_idx].copy()
+            dist_row[list(exist_idx_set)] = np.inf
+            min_idx = int(np.argmin(dist_row))
+            match_matrix_row[min_idx] = 1
+            exist_idx_set.add(min_idx)
+        if len(exist_idx_set) < cur_need_cluster:                                       # :1041-1048
+            for _ in range(cur_need_cluster - len(exist_idx_set)):
+                min_idx = np.random.randint(cur_n_cluster)
+                while min_idx in exist_idx_set:
+                    min_idx = np.random.randint(cur_n_cluster)
+                match_matrix_row[min_idx] = 1
+                exist_idx_set.add(min_idx)
+        return match_matrix_row
+
+    @staticmethod
+    def _reassign_last_layer(X: torch.Tensor, kmeans_centers: torch.Tensor, before_cluster_ids: np.ndarray,
+                             match_matrix: List[List[int]], batch_size: int = 1 << 20) -> torch.Tensor:
+        """:906-966 (ids; a last layer hands on no residual): argmin of fl32(d + 10000 * (1 - match[before])) over the
+        2K candidates, raw candidate index."""
+        dev = X.device
+        allow = torch.from_numpy(np.asarray(match_matrix, dtype=np.uint8)).to(dev)
+        group = torch.from_numpy(np.asarray(before_cluster_ids, dtype=np.int64)).to(dev)
+        if len(group) and (int(group.max()) >= allow.shape[0] or int(group.min()) < 0):
+            raise IndexError(f"index {int(group.max())} is out of bounds for axis 0 with size {allow.shape[0]}")
+        out = []
+        for i in range(0, len(X), batch_size):
+            dist = engine.score_pass(X[i:i + batch_size], kmeans_centers, argmin=False, dist=True).dist
+            out.append(engine.masked_argmin(dist, group[i:i + batch_size], allow, penalty=True))
+        return torch.cat(out) if out else torch.empty(0, dtype=torch.int32, device=dev)
+
+    @staticmethod
+    def _merge_match_matrix_cluster_ids(match_matrix: List[List[int]], cluster_ids: torch.Tensor,
+                                        before_cluster_ids: np.ndarray) -> torch.Tensor:
+        """:1054-1086: the id becomes its position among the ones of the group's row (KeyError if the row does not
+        allow it, as the reference's dict lookup)."""
+        mm = np.asarray(match_matrix, dtype=np.int64)
+        raw = cluster_ids.cpu().numpy().astype(np.int64)
+        before = np.asarray(before_cluster_ids, dtype=np.int64)
+        ok = mm[before, raw] == 1
+        if not ok.all():
+            raise KeyError(int(raw[np.argmin(ok)]))
+        pos = np.cumsum(mm == 1, axis=1) - 1
+        return torch.from_numpy(pos[before, raw].astype(np.int64))
+
     @staticmethod
     def _reassign_middle_layer(X: torch.Tensor, centers: torch.Tensor, prev: torch.Tensor, pre_need: int,
                                cur_need: int) -> torch.Tensor:                          # :839-904 (ids; the caller subtracts)
@@ -513,8 +635,18 @@ class HierarchicalRQKMeans:
             c = self.cluster_centers_list[layer].to(dev, torch.float32)
             w = self._weight_vector(layer, dev)
             xw = engine.scale_dims(cur, w) if w is not None else cur
-            if layer == 0 or layer == L - 1:                                            # :1146-1173, :1235-1305 (no match matrix)
+            if layer == 0:                                                              # :1146-1173
                 ids = engine.score_pass(xw, c, argmin=True).argmin
+            elif layer == L - 1:                                                        # :1235-1305
+                # :1248 looks the matrix up at index layer - 1; train() appends exactly one (:821), so for a 3-layer
+                # model the mask is skipped and the ids are raw candidate indices - reproduced
+                mm = self.match_matrices[layer - 1] if layer - 1 < len(self.match_matrices) else []
+                if mm:
+                    before = (all_ids[-2].long() * self.config.need_clusters[layer - 2] + all_ids[-1].long()).cpu().numpy()
+                    raw = self._reassign_last_layer(xw, c, before, mm)
+                    ids = self._merge_match_matrix_cluster_ids(mm, raw, before).to(dev)
+                else:
+                    ids = engine.score_pass(xw, c, argmin=True).argmin
             else:                                                                       # :1175-1233
                 pre_need, cur_need = self.config.need_clusters[layer - 1], self.config.need_clusters[layer]
                 prev = all_ids[layer - 1].long()
@@ -543,17 +675,13 @@ class HierarchicalRQKMeans:
         if X.shape[1] != self.config.embedding_dim:
             raise ValueError(
                 f"Input dimension {X.shape[1]} does not match config embedding_dim {self.config.embedding_dim}")
-        if self.match_matrices:
-            raise NotImplementedError("predict() with a match matrix (last-layer dual K-Means) is the next scope row")
         dev = torch.device(self.device)
         x = self._h2d(X, dev)
         L = len(self.cluster_centers_list)
         recursive = [l for l in range(1, L - 1)
                      if len(self.cluster_centers_list[l]) != self.config.need_clusters[l]]
-        if recursive or len(self.cluster_centers_list[-1]) != self.config.need_clusters[-1] or \
+        if recursive or self.match_matrices or len(self.cluster_centers_list[-1]) != self.config.need_clusters[-1] or \
                 len(self.cluster_centers_list[0]) != self.config.need_clusters[0]:
-            if len(self.cluster_centers_list[-1]) != self.config.need_clusters[-1]:
-                raise NotImplementedError("predict() for a last layer trained with the dual K-Means strategy")
             return self._predict_chain(x).t().contiguous().long().cpu().numpy()
         centers = [c.to(dev, torch.float32) for c in self.cluster_centers_list]
         weights = [self._weight_vector(l, dev) for l in range(len(centers))]

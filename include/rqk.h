@@ -143,11 +143,12 @@ int rqk_residual_normalise(const float* x, int64_t n, int32_t dim, const int32_t
 int rqk_scale_dims(const float* x, int64_t n, int32_t dim, const float* w, float* out, void* stream);
 /* simplified_semantic_id_generator.py:78-96, :160-164 (`batch - centers[cluster_ids]`, NOT normalised) and :317-331
  * (`dist[match == 0] = inf; argmin`): group int32 [n] selects the row's line of allow uint8 [ngroups][k]; first index
- * on ties, 0 if no candidate is allowed. */
+ * on ties, 0 if no candidate is allowed.  penalty = 1: a disallowed candidate competes with fl32(d + 10000) instead of
+ * +inf, hierarchical_rq_kmeans.py:953 / :1288 (`distance.add_(10000.0 * (1 - match_matrix_batch))`). */
 int rqk_residual_plain(const float* x, int64_t n, int32_t dim, const int32_t* ids, const float* centers, float* out,
                        void* stream);
 int rqk_masked_argmin(const float* dist, int64_t n, int32_t k, const int32_t* group, const uint8_t* allow,
-                      int32_t ngroups, int32_t* ids, void* stream);
+                      int32_t ngroups, int32_t penalty, int32_t* ids, void* stream);
 int rqk_gather_rows(const float* x, int32_t dim, const int64_t* rows, int32_t nrows, float* out, void* stream);
 
 /* ---- multi-level encode ----------------------------------------------------------------------

@@ -336,10 +336,63 @@ def gen_simplified():
     print("simplified:", n, "rows,", len(big), "groups with a temporary fit,", len({tuple(r) for r in ids.tolist()}), "distinct ids")
 
 
+def gen_last_layer():
+    """A full HierarchicalRQKMeans.train + predict of the unmodified reference with the PROD config's SHAPE
+    (direct first layer, recursive middle layer, last layer = two balanced KMeans.fit + match matrix,
+    hierarchical_rq_kmeans.py:754-837, :906-1086, :1235-1305) at a size the CPU finishes in minutes.  Recorded: every
+    layer's centres and ids, the match matrix, and the sub-centres (argument of the torch.cdist call, :1014) each
+    (l1, l2) group's matrix row was built from - the sub-fits and the random subsets are host-RNG / chaotic, so the
+    tests teacher-force on them."""
+    n, dim = 3000, 32
+    x = O.synth_mix(n, dim, seed=33, modes=48)
+    lc, nc = [4, 16, 16], [4, 4, 8]
+    cfg = ref_h.HierarchicalRQKMeansConfig(layer_clusters=lc, need_clusters=nc, embedding_dim=dim, group_dims=[dim],
+                                           hierarchical_weights=[[1.0]] * 3, iter_limit=20)
+    subs = []
+    orig_cdist = torch.cdist
+
+    def recording_cdist(a, b, *args, **kw):
+        if sys._getframe(1).f_code.co_name == "_assign_last_match_matrix":      # not the sub-fits' own distance calls
+            subs.append(a.detach().cpu().numpy().copy())
+        return orig_cdist(a, b, *args, **kw)
+
+    set_seed(42)
+    m = ref_h.HierarchicalRQKMeans(cfg, device=torch.device("cpu"))
+    orig_assign = m._assign_last_match_matrix
+
+    def wrapped(*a, **k):
+        torch.cdist = recording_cdist          # only the match-matrix builder's direct calls (KMeans uses F.cdist too)
+        try:
+            subs.clear()
+            out = orig_assign(*a, **k)
+            wrapped.subs = list(subs)
+            return out
+        finally:
+            torch.cdist = orig_cdist
+
+    m._assign_last_match_matrix = wrapped
+    out = m.train(x, resume=False)
+    ids = np.column_stack([t.cpu().numpy() for t in out["cluster_ids"]]).astype(np.int64)
+    match = np.array(m.match_matrices[0], dtype=np.uint8)
+    sizes = [int(((ids[:, 0] == i) & (ids[:, 1] == j)).sum()) for i in range(nc[0]) for j in range(nc[1])]
+    nonempty = [g_ for g_, c in enumerate(sizes) if c > 0]
+    sub = wrapped.subs
+    assert len(sub) == len(nonempty), (len(sub), len(nonempty))
+    assert all(s_.shape[0] == nc[2] for s_ in sub), "every group large enough for need[-1] sub-centres"
+    pred = m.predict(x)
+    np.savez_compressed(os.path.join(OUT, "last_layer.npz"), x=x, train_ids=ids, predict_ids=pred.astype(np.int64),
+                        c0=out["cluster_centers"][0].cpu().numpy(), c_mid=out["cluster_centers"][1].cpu().numpy(),
+                        c_last=out["cluster_centers"][2].cpu().numpy(), match=match, group_sizes=np.array(sizes),
+                        sub_groups=np.array(nonempty), sub_centers=np.stack(sub), layer_clusters=np.array(lc),
+                        need_clusters=np.array(nc), iter_limit=20)
+    print("last_layer:", n, "rows,", len(nonempty), "non-empty groups,", len({tuple(r) for r in ids.tolist()}), "distinct ids,",
+          "predict agrees with train on", float((pred == ids).all(1).mean()))
+
+
 if __name__ == "__main__":
     import contextlib
     import io
-    which = sys.argv[1:] or ["auction", "eps", "distance", "stage", "encode", "fit_stats", "iter_limit", "io", "middle", "simplified"]
+    which = sys.argv[1:] or ["auction", "eps", "distance", "stage", "encode", "fit_stats", "iter_limit", "io", "middle", "simplified", "last_layer"]
     for w in which:
         buf = io.StringIO()
         with contextlib.redirect_stdout(buf):   # the reference prints every iteration

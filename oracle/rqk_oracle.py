@@ -511,6 +511,50 @@ def predict_hierarchy(x: np.ndarray, centers_list: Sequence[np.ndarray], need_cl
 
 
 # --------------------------------------------------------------------------------------------
+# last layer of the PROD-shaped config: two balanced fits + match matrix (hierarchical_rq_kmeans.py:754-1086)
+# --------------------------------------------------------------------------------------------
+
+def last_layer_match_row(sub_centers: np.ndarray, centers: np.ndarray, need: int,
+                         randint: Callable[[int], int] = np.random.randint) -> np.ndarray:
+    """_assign_last_match_matrix, :1017-1050, for one (l1, l2) group: `torch.cdist(sub_centers, centres)` (the mm
+    path: the candidates are more than 25), every sub-centre takes its nearest unused candidate (first index on
+    ties), random fill up to `need`.  uint8 [2K]."""
+    k2 = centers.shape[0]
+    d = pairwise_distance_full(sub_centers, centers, batch_size=1 << 30)
+    row = np.zeros(k2, dtype=np.uint8)
+    used: List[int] = []
+    for j in range(min(len(sub_centers), need)):
+        dr = d[j].copy()
+        dr[used] = np.inf
+        m = int(np.argmin(dr))
+        row[m] = 1
+        used.append(m)
+    while len(set(used)) < need:
+        m = randint(k2)
+        while m in used:
+            m = randint(k2)
+        row[m] = 1
+        used.append(m)
+    return row
+
+
+def last_layer_reassign(xw: np.ndarray, centers: np.ndarray, before: np.ndarray, match: np.ndarray) -> np.ndarray:
+    """_reassign_clusters_last_layer_with_residuals, :906-966: argmin of d + 10000 * (1 - match[before]) in fp32;
+    raw candidate index."""
+    d = pairwise_distance_full(xw, centers)
+    m = np.asarray(match, dtype=np.float32)[np.asarray(before, np.int64)]
+    return np.argmin(d + np.float32(10000.0) * (np.float32(1.0) - m), axis=1).astype(np.int64)
+
+
+def merge_match_ids(match: np.ndarray, raw: np.ndarray, before: np.ndarray) -> np.ndarray:
+    """_merge_match_matrix_cluster_ids, :1054-1086: position of the raw id among the ones of the group's row."""
+    mm = np.asarray(match, dtype=np.int64)
+    pos = np.cumsum(mm == 1, axis=1) - 1
+    assert (mm[before, raw] == 1).all(), "KeyError in the reference"
+    return pos[before, raw]
+
+
+# --------------------------------------------------------------------------------------------
 # SimplifiedHierarchicalRQ: simplified_semantic_id_generator.py (second entry point, README.md:192-195)
 # --------------------------------------------------------------------------------------------
 

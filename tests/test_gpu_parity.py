@@ -693,3 +693,74 @@ def test_simplified_generator_trains_end_to_end(dev, engine, golden_dir, tmp_pat
     m.save_model(str(tmp_path / "model.pkl"))
     m2 = type(m).load_model(str(tmp_path / "model.pkl"))
     assert torch.equal(m2.final_layer_centers.cpu(), m.final_layer_centers.cpu()) and m2.trained_kmeans_models[1] is None
+
+
+# ------------------------------------------------------------------------------------------------
+# last layer of the PROD-shaped config: two balanced fits + match matrix
+# ------------------------------------------------------------------------------------------------
+def _last_layer_model(g, dev):
+    from generative_ranking_recommender_b200.hierarchical_rq_kmeans import HierarchicalRQKMeans, HierarchicalRQKMeansConfig
+    dim = g["x"].shape[1]
+    cfg = HierarchicalRQKMeansConfig(layer_clusters=[int(v) for v in g["layer_clusters"]],
+                                     need_clusters=[int(v) for v in g["need_clusters"]], embedding_dim=dim,
+                                     group_dims=[dim], hierarchical_weights=[[1.0]] * 3, iter_limit=int(g["iter_limit"]))
+    return HierarchicalRQKMeans(cfg, device=dev)
+
+
+def test_last_layer_teacher_forced_on_reference_run(dev, engine, golden_dir):
+    """hierarchical_rq_kmeans.py:754-837, :906-1086, :1235-1305 on the centres / sub-centres of an unmodified reference
+    run: the match matrix (greedy nearest unused candidate), the masked reassignment (+10000 in fp32), the id
+    remapping, and predict() with its lookup-index quirk (raw candidate ids for a 3-layer model)."""
+    g = np.load(os.path.join(golden_dir, "last_layer.npz"))
+    m = _last_layer_model(g, dev)
+    x = torch.from_numpy(g["x"]).to(dev)
+    tid, need, dim = g["train_ids"], [int(v) for v in g["need_clusters"]], g["x"].shape[1]
+    c0, c_mid, c_last = (torch.from_numpy(g[k]).to(dev) for k in ("c0", "c_mid", "c_last"))
+    ids0 = engine.score_pass(x, c0, argmin=True).argmin
+    assert np.array_equal(ids0.cpu().numpy(), tid[:, 0])
+    res0 = engine.residual_normalise(x, ids0, c0, [dim])
+    raw = m._reassign_middle_layer(res0, c_mid, ids0, need[0], need[1])
+    assert np.array_equal((raw % need[1]).cpu().numpy(), tid[:, 1])
+    res1 = engine.residual_normalise(res0, raw, c_mid, [dim])
+    for grp, sub in zip(g["sub_groups"], g["sub_centers"]):
+        row = m._match_row_last_layer(torch.from_numpy(sub).to(dev), c_last, need[2])
+        assert np.array_equal(np.array(row, dtype=np.uint8), g["match"][grp]), grp
+    before = tid[:, 0] * need[0] + tid[:, 1]
+    mm = g["match"].tolist()
+    raw_last = m._reassign_last_layer(res1, c_last, before, mm, batch_size=1000)
+    want_raw = O.last_layer_reassign(res1.cpu().numpy(), g["c_last"], before, g["match"])
+    assert np.array_equal(raw_last.cpu().numpy(), want_raw)
+    assert np.array_equal(m._merge_match_matrix_cluster_ids(mm, raw_last, before).numpy(), tid[:, 2])
+    m.cluster_centers_list, m.match_matrices, m.is_trained = [c0, c_mid, c_last], [mm], True
+    assert np.array_equal(m.predict(g["x"]), g["predict_ids"])
+
+
+def test_last_layer_training_structure(dev, engine, golden_dir, tmp_path):
+    """train() on the PROD config's shape end to end: ids in [0, need) at every layer, need[-1] allowed candidates
+    per (l1, l2) group, reproducible, checkpoint / save_model carry the match matrix, about as many distinct codes
+    as the reference's own run on this data."""
+    import pickle
+    g = np.load(os.path.join(golden_dir, "last_layer.npz"))
+    need = [int(v) for v in g["need_clusters"]]
+    runs = []
+    for _ in range(2):
+        np.random.seed(42)
+        torch.manual_seed(42)
+        m = _last_layer_model(g, dev)
+        out = m.train(g["x"], resume=False)
+        runs.append(np.stack([t.numpy() for t in out["cluster_ids"]]))
+    ids = runs[0]
+    assert np.array_equal(runs[0], runs[1])
+    assert [int(ids[l].max()) < need[l] for l in range(3)] == [True] * 3 and ids.min() == 0
+    assert tuple(out["cluster_centers"][2].shape) == (2 * int(g["layer_clusters"][2]), g["x"].shape[1])
+    mm = np.array(m.match_matrices[0])
+    assert mm.shape == (need[0] * need[1], 2 * int(g["layer_clusters"][2])) and (mm.sum(1) == need[2]).all()
+    uniq, ref_uniq = len({tuple(r) for r in ids.T.tolist()}), len({tuple(r) for r in g["train_ids"].tolist()})
+    assert abs(uniq - ref_uniq) <= 0.15 * ref_uniq, (uniq, ref_uniq)
+    pred = m.predict(g["x"])
+    assert pred.shape == (len(g["x"]), 3) and np.array_equal(pred[:, 0], ids[0]) and pred[:, 2].max() < mm.shape[1]
+    m.save_model(str(tmp_path / "model"))
+    assert pickle.load(open(tmp_path / "model" / "match_matrices.pkl", "rb")) == m.match_matrices
+    m2 = _last_layer_model(g, dev)
+    m2.load_model(str(tmp_path / "model"))
+    assert np.array_equal(m2.predict(g["x"]), pred)

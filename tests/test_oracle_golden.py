@@ -231,3 +231,25 @@ def test_simplified_generator_restatement_against_reference_run(golden_dir):
     last = O.simplified_predict_with_matrix(res2, ids[:, 0], ids[:, 1], g["c_last"], g["match"], need[1])
     assert np.array_equal(last, ids[:, 2])
     assert ids[:, 2].max() >= need[2]                                  # raw candidate indices, not remapped (:229)
+
+
+def test_last_layer_match_matrix_restatement_against_reference_run(golden_dir):
+    """The PROD config's shape (direct first layer, recursive middle layer, last layer = two balanced fits + match
+    matrix) on the centres and sub-centres of an unmodified reference run: match matrix, train ids (positions inside
+    the group's allowed set) and predict() ids (raw candidate indices: the lookup-index bug of :1248)."""
+    g = _load(golden_dir, "last_layer.npz")
+    x, tid, need, dim = g["x"], g["train_ids"], [int(v) for v in g["need_clusters"]], g["x"].shape[1]
+    ids0 = O.predict(x, g["c0"])
+    assert np.array_equal(ids0, tid[:, 0])
+    res0 = O.residual_normalised(x, ids0, g["c0"], [dim])
+    raw, res1 = O.reassign_middle_layer(res0, g["c_mid"], ids0, need[0], need[1], [dim])
+    assert np.array_equal(raw % need[1], tid[:, 1])
+    for grp, sub in zip(g["sub_groups"], g["sub_centers"]):
+        assert np.array_equal(O.last_layer_match_row(sub, g["c_last"], need[2]), g["match"][grp]), grp
+    before = tid[:, 0] * need[0] + tid[:, 1]                                   # :824
+    raw_last = O.last_layer_reassign(res1, g["c_last"], before, g["match"])
+    assert np.array_equal(O.merge_match_ids(g["match"], raw_last, before), tid[:, 2])
+    pred = O.predict_hierarchy(x, [g["c0"], g["c_mid"], g["c_last"]], need, [dim], [[1.0]] * 3,
+                               match_matrices=[g["match"].tolist()])
+    assert np.array_equal(pred, g["predict_ids"])
+    assert g["predict_ids"][:, 2].max() >= need[2]                            # raw candidate ids at predict time

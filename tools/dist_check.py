@@ -20,14 +20,22 @@ dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 shard = engine.ShardGroup()
 
-def make(nloc, r):
+def make(nloc, r, kind="iso"):
     g = torch.Generator(device=dev)
     g.manual_seed(100 + r)
-    return torch.randn((nloc, 512), device=dev, generator=g)
+    if kind == "iso":
+        return torch.randn((nloc, 512), device=dev, generator=g)
+    # clustered, unit-norm rows (the shape of a level-2 residual): dense fp16 score values, wide windows, window
+    # misses - the partial HIST passes and their rank-major tie offsets get exercised
+    gc = torch.Generator(device=dev)
+    gc.manual_seed(99)
+    c = torch.randn((96, 512), device=dev, generator=gc)
+    x = c[torch.randint(0, 96, (nloc,), device=dev, generator=g)] + 0.35 * torch.randn((nloc, 512), device=dev, generator=g)
+    return x / x.norm(dim=1, keepdim=True)
 
 ok = True
-for nloc, k in ((30011, 64), (100000, 128)):
-    x = make(nloc, rank)
+for nloc, k, kind in ((30011, 64, "iso"), (100000, 128, "iso"), (150001, 256, "mix"), (60000, 128, "mix")):
+    x = make(nloc, rank, kind)
     np.random.seed(7)
     km = KMeans(n_clusters=k, device=dev, balanced=True, shard=shard)
     km.cluster_centers = km.initialize(x)
@@ -36,7 +44,7 @@ for nloc, k in ((30011, 64), (100000, 128)):
     score, assign, stats, shift = km._iterate(x, n_global)
     gathered = shard.all_gather(assign)                       # [world, nloc]
     if rank == 0:
-        xa = torch.cat([make(nloc, r) for r in range(world)])
+        xa = torch.cat([make(nloc, r, kind) for r in range(world)])
         np.random.seed(7)
         k1 = KMeans(n_clusters=k, device=dev, balanced=True)
         k1.cluster_centers = k1.initialize(xa)
@@ -44,7 +52,7 @@ for nloc, k in ((30011, 64), (100000, 128)):
         s1, a1, st1, sh1 = k1._iterate(xa, n_global)
         same_assign = torch.equal(a1, gathered.reshape(-1))
         cerr = (k1.cluster_centers - km.cluster_centers).abs().max().item() / k1.cluster_centers.abs().max().item()
-        print(f"n={n_global} k={k}: init identical {same_init}; assignment identical {same_assign}; rounds {stats.rounds}/{st1.rounds} "
+        print(f"n={n_global} k={k} {kind}: misses {stats.window_misses}/{st1.window_misses}; init identical {same_init}; assignment identical {same_assign}; rounds {stats.rounds}/{st1.rounds} "
               f"passes {stats.passes}/{st1.passes}; centroid max rel diff {cerr:.2e}; shift {shift:.4f}/{sh1:.4f}", flush=True)
         ok &= same_init and same_assign and cerr < 1e-5
     dist.barrier()
