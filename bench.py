@@ -501,7 +501,7 @@ def main():
     # launches of our kernels inside the timed region: per step score pass (pad, minmax, split, tc) = 4,
     # auction init (memset + init) 2 + ROUND_LAUNCHES per enqueued round (rounds are enqueued two at a time, one
     # batch ahead of the host's look at the state) + finalize 1, centroid update 8
-    ROUND_LAUNCHES = 5 if world == 1 else 9
+    ROUND_LAUNCHES = 5 if world == 1 else 7
 
     def auction_launches(st):
         rounds_ = st.passes - st.cold_passes

@@ -292,7 +292,8 @@ __device__ __forceinline__ const unsigned short* peer_sample(const PeerCtx& c, i
 }
 // All threads of the CTA call this after their stores to the local exchange block.  Returns false on a timeout
 // (a peer that never arrives: 4 s), which the caller turns into an error state instead of a hang.
-__device__ bool peer_barrier(const PeerCtx& c, int kind, int seq) {
+// `signal` = false: wait only (another CTA of the grid publishes this rank's arrival).
+__device__ bool peer_barrier(const PeerCtx& c, int kind, int seq, bool signal = true) {
     __shared__ int s_ok;
     __threadfence_system();
     __syncthreads();
@@ -300,8 +301,10 @@ __device__ bool peer_barrier(const PeerCtx& c, int kind, int seq) {
     if (t == 0) s_ok = 1;
     __syncthreads();
     if (t < c.world && t != c.rank) {
-        int* dst = peer_flags(c, t) + kind * PEER_MAX + c.rank;
-        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(dst), "r"(seq) : "memory");
+        if (signal) {
+            int* dst = peer_flags(c, t) + kind * PEER_MAX + c.rank;
+            asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(dst), "r"(seq) : "memory");
+        }
         const int* src = peer_flags(c, c.rank) + kind * PEER_MAX + t;
         unsigned long long t0, t1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -321,6 +324,20 @@ __device__ bool peer_barrier(const PeerCtx& c, int kind, int seq) {
 // ------------------------------------------------------------------------------------------
 // resolve: merged histograms -> thresholds / next windows / state machine.  One CTA.
 // ------------------------------------------------------------------------------------------
+// Outcome of a bidding round from its two global counters: all jobs have a bidder (:113-114), or the state is
+// frozen (file header) - at counter 100..1000 the run is decided, below 99 the retain phase is fast-forwarded.
+struct BidOutcome { bool finished, jump; };
+__device__ __forceinline__ BidOutcome bid_outcome(int counter, unsigned long long n_with, unsigned long long n_viol, long long N) {
+    BidOutcome o{false, false};
+    if (n_with == (unsigned long long)N) {
+        o.finished = true;
+    } else if (n_viol == 0 && counter >= 1) {
+        if (counter >= 100 && counter <= 1000) o.finished = true;
+        else if (counter < 99) o.jump = true;
+    }
+    return o;
+}
+
 // `expect`: -1, or the mode whose pass must have just run (MODE_HIST / MODE_BID) for the call to act.
 __device__ __noinline__ void auction_resolve_body(AuctionPtrs p, long long N, int K, long long jpw, int expect) {
     __shared__ int s_unresolved, s_miss;
@@ -336,12 +353,9 @@ __device__ __noinline__ void auction_resolve_body(AuctionPtrs p, long long N, in
     // ---- 1. outcome of the bidding round that just ran ----
     bool finished = false, jump = false;
     if (was_bid) {
-        if (s_nwith_g == (unsigned long long)N) {
-            finished = true;                                  // :113-114
-        } else if (s_nviol_g == 0 && s.counter >= 1) {
-            if (s.counter >= 100 && s.counter <= 1000) finished = true;   // frozen: ends at counter 1001
-            else if (s.counter < 99) jump = true;                        // frozen in the retain phase
-        }
+        const BidOutcome o = bid_outcome(s.counter, s_nwith_g, s_nviol_g, N);
+        finished = o.finished;
+        jump = o.jump;
     }
     if (finished) {
         __syncthreads();
@@ -1657,13 +1671,22 @@ __device__ __forceinline__ void sample_select_bin(const unsigned int* hist, int 
 __global__ void __launch_bounds__(1024, 1)
 auction_sample_kernel(const __half* __restrict__ S, long long ld, long long N, int K, long long jpw, AuctionPtrs p,
                       unsigned short* __restrict__ collect_out, int collect_n,
-                      const unsigned short* __restrict__ ext_keys, int ext_n, int ext_cnt, PeerCtx peers, int peer_par) {
+                      const unsigned short* __restrict__ ext_keys, int ext_n, int ext_cnt, PeerCtx peers, int peer_par,
+                      int barrier_seq) {
     pdl_launch_dependents();
     pdl_wait();
     const AuctionState st = *p.st;
     if (st.mode != MODE_HIST || !st.need_sample) return;
     __shared__ unsigned short keys[AUC_SAMPLE];
     const int w = blockIdx.x, tid = threadIdx.x;
+    if (peers.world > 0 && barrier_seq >= 0) {
+        // every rank's samples are in its exchange block once the kernel before this one has completed (which the
+        // wait above guarantees): CTA 0 publishes this rank's arrival, every CTA waits for all ranks
+        if (!peer_barrier(peers, 0, barrier_seq, blockIdx.x == 0)) {
+            if (tid == 0) { p.st->error = 1; p.st->mode = MODE_DONE; p.st->done = 1; }
+            return;
+        }
+    }
     long long ns = N < AUC_SAMPLE ? N : AUC_SAMPLE;
     if (collect_out) ns = collect_n < ns ? collect_n : ns;
     if (ext_keys || peers.world > 0) ns = ext_n;
@@ -1845,6 +1868,148 @@ auction_sample_kernel(const __half* __restrict__ S, long long ld, long long N, i
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Sharded jobs, whole-round protocol (rqk_auction_peer_round): seven launches per round, chained with programmatic
+// dependent launch, three flag barriers that sit INSIDE kernels which have work of their own:
+//   1. auction_peer_bid_collect_kernel  (K CTAs)   counters of the previous round's bids exchanged and resolved
+//                                                  (every CTA derives the next state from the summed counters, the
+//                                                  LAST CTA applies it), then the local window samples
+//   2. auction_sample_kernel            (K CTAs)   sample barrier, windows from the union of all ranks' samples
+//   3. auction_hist_kernel              (G CTAs)   merges straight into this rank's exchange block
+//   4. auction_peer_exchange_kernel     (16 CTAs)  histogram barrier, every CTA sums a slice over the ranks (one NVLink
+//                                                  round trip), last CTA resolves + rank-major tie offsets
+//   5. tie prefix, 6. bid-list replay, 7. S-scanning fallback (returns at once unless a list overflowed)
+// ------------------------------------------------------------------------------------------
+constexpr int PEER_XCH_CTAS = 16;
+
+__global__ void __launch_bounds__(1024, 1)
+auction_peer_bid_collect_kernel(const __half* __restrict__ S, long long ld, long long N, int K, long long n_global,
+                                AuctionPtrs p, int count, PeerCtx peers, int seq_bid, int seq_sample) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ AuctionState st;
+    __shared__ unsigned int s_sum[2];
+    const int tid = threadIdx.x, w = blockIdx.x;
+    if (tid == 0) st = *p.st;          // nobody writes the state before the LAST CTA of this grid has read it
+    __syncthreads();
+    if (st.mode == MODE_DONE) return;
+    const bool was_bid = st.mode == MODE_BID;
+    bool do_sample = st.mode == MODE_HIST && st.need_sample != 0;
+    if (was_bid) {
+        const int par = seq_bid & 1;
+        if (w == 0 && tid == 0) {
+            int* mine = peer_tail(peers, peers.rank, par);
+            mine[0] = (int)*p.n_with;
+            mine[1] = (int)*p.n_viol;
+        }
+        if (!peer_barrier(peers, 2, seq_bid, w == 0)) {
+            if (tid == 0) { p.st->error = 1; p.st->mode = MODE_DONE; p.st->done = 1; }
+            return;
+        }
+        if (tid < 32) {                                        // one lane per rank: the peer loads overlap
+            unsigned int a = 0, b = 0;
+            if (tid < peers.world) {
+                const int* t = peer_tail(peers, tid, par);
+                a = (unsigned int)__ldcv(t);
+                b = (unsigned int)__ldcv(t + 1);
+            }
+#pragma unroll
+            for (int d = 16; d; d >>= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, d);
+                b += __shfl_xor_sync(0xffffffffu, b, d);
+            }
+            if (tid == 0) { s_sum[0] = a; s_sum[1] = b; }
+        }
+        __syncthreads();
+        const BidOutcome o = bid_outcome(st.counter, s_sum[0], s_sum[1], n_global);
+        __syncthreads();
+        if (tid == 0 && !o.finished) {                         // the state auction_resolve_body will write
+            st.counter += 1;
+            st.ff_pending = 0;
+            if (o.jump) { st.ff_pending = 100 - st.counter; st.counter = 100; }
+            st.mode = MODE_HIST;
+            st.need_sample = 1;
+        }
+        __syncthreads();
+        do_sample = !o.finished;
+    }
+    if (do_sample) {
+        // `count` evenly strided local jobs of worker w -> own exchange block (16 consecutive jobs = one sector)
+        unsigned short* out = reinterpret_cast<unsigned short*>(peers.buf[peers.rank] + peer_sample_off(K)) +
+                              (size_t)(seq_sample & 1) * K * AUC_SAMPLE_MAX + (size_t)w * count;
+        long long ns = N < count ? N : count;
+        const __half eps = bits2h(st.eps_bits);
+        const long long nchunks = (ns + 15) / 16, cstride = N / (nchunks > 0 ? nchunks : 1);
+        for (int i = tid; i < count; i += 1024) {
+            unsigned short key = 0;                            // padding sorts last
+            if (i < ns) {
+                long long col = cstride * (i >> 4) + (i & 15);
+                if (col >= N) col = N - 1;
+                __half c = p.cost[col];
+                const short o = p.owner[col];
+                const __half sv = S[(size_t)w * ld + col];
+                if (st.ff_pending > 0 && o >= 0)
+                    for (int r = 0; r < st.ff_pending; ++r) c = __hadd(c, eps);
+                key = (unsigned short)h2key(h2bits((o == w) ? sv : __hsub(sv, c)));
+            }
+            out[i] = key;
+        }
+    }
+    if (was_bid && auction_last_cta(p.ticket)) {
+        // every CTA has taken its snapshot of the state and CTA 0 has published the local counters: apply the round
+        if (tid == 0) { *p.n_with = s_sum[0]; *p.n_viol = s_sum[1]; }
+        __syncthreads();
+        auction_resolve_body(p, n_global, K, n_global / K, MODE_BID);
+    }
+}
+
+// HIST exchange of the whole-round protocol: the HIST kernel has merged this rank's histograms into its exchange
+// block (parity of seq).  Barrier, then every CTA sums its slice of the reduce block over all ranks into the
+// workspace copy the resolve step reads, and clears the slice of the OTHER parity block (every peer has finished
+// reading it: it has arrived at this barrier); the last CTA resolves and takes the rank-major tie offsets.
+__global__ void __launch_bounds__(1024, 1)
+auction_peer_exchange_kernel(AuctionPtrs p, long long N, int K, long long jpw, PeerCtx peers, int seq) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ int s_mode, s_pass;
+    const int tid = threadIdx.x, NT = blockDim.x, par = seq & 1;
+    if (tid == 0) { s_mode = p.st->mode; s_pass = p.st->passes; }
+    __syncthreads();
+    if (s_mode != MODE_HIST) return;
+    const int RB = K * AUC_W + 2 * K;                          // histograms + above + gap (the bid counters travel apart)
+    if (!peer_barrier(peers, 1, seq, blockIdx.x == 0)) {
+        if (tid == 0) { p.st->error = 1; p.st->mode = MODE_DONE; p.st->done = 1; }
+        return;
+    }
+    const unsigned int* mine = peer_hist(peers, peers.rank, K, par);
+    unsigned int* other = peer_hist(peers, peers.rank, K, par ^ 1);
+    for (int i = blockIdx.x * NT + tid; i < RB; i += gridDim.x * NT) {
+        unsigned int acc = __ldcg(mine + i);
+#pragma unroll
+        for (int r = 0; r < PEER_MAX; ++r)                     // all peers' loads in flight together
+            if (r < peers.world && r != peers.rank) acc += __ldcv(peer_hist(peers, r, K, par) + i);
+        p.hist_g[i] = acc;
+        other[i] = 0u;
+    }
+    if (!auction_last_cta(p.ticket)) return;
+    const int this_pass = s_pass;
+    auction_resolve_body(p, N, K, jpw, MODE_HIST);
+    __syncthreads();
+    for (int w = tid; w < K; w += NT) {                        // workers THIS pass resolved (see auction_resolve_peer_kernel)
+        if (p.res_pass[w] != this_pass || p.tkey[w] < 0) continue;
+        const int base = p.win_base[w], hbase = p.win_hbase[w], nlo = p.win_nlo[w], tk = p.tkey[w];
+        const int bin = tk >= hbase ? nlo + tk - hbase : tk - base;
+        unsigned int part[PEER_MAX];
+#pragma unroll
+        for (int r = 0; r < PEER_MAX; ++r)
+            part[r] = (r < peers.rank) ? __ldcv(peer_hist(peers, r, K, par) + (size_t)w * AUC_W + bin) : 0u;
+        unsigned int off = 0;
+#pragma unroll
+        for (int r = 0; r < PEER_MAX; ++r) off += part[r];
+        p.rank_off[w] = off;
+    }
+}
+
 // After a resolve that leaves every worker resolved: per-CTA exclusive prefix of the number of
 // values equal to the threshold (bin tkey-base of the per-CTA dumps), and the window predicted for
 // the values after this round's cost update.  Grid = K CTAs.
@@ -1937,11 +2102,16 @@ static cudaError_t launch_round_kernel(void (*kernel)(KArgs...), unsigned grid, 
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+static bool auction_pdl_ok() {
+    static const bool ok = [] { const char* e = getenv("RQK_NO_PDL"); return !(e && e[0] == '1'); }();
+    return ok;
+}
+
 static int auction_launch(const AuctionArgs& a, const void* scores_t, int64_t ld, int64_t n, int32_t k, int64_t n_global,
-                          int which, int fused, cudaStream_t stream) {
-    // the single-GPU driver (fused resolve) chains its round kernels with programmatic dependent launch
-    static const bool pdl_ok = [] { const char* e = getenv("RQK_NO_PDL"); return !(e && e[0] == '1'); }();
-    const bool pdl = fused != 0 && pdl_ok;
+                          int which, int fused, cudaStream_t stream, bool chain = false) {
+    // the single-GPU driver (fused resolve) and the whole-round sharded protocol (`chain`) chain their round kernels
+    // with programmatic dependent launch
+    const bool pdl = (fused != 0 || chain) && auction_pdl_ok();
     auto kern = (a.J == 128) ? auction_pass_kernel<128> : auction_pass_kernel<64>;
     // the attribute is per device (and this process may drive several): cache what has been set per device ordinal
     int devi = 0;
@@ -1957,7 +2127,7 @@ static int auction_launch(const AuctionArgs& a, const void* scores_t, int64_t ld
     if (which & 1)
         RQK_CUDA_OK(launch_round_kernel(auction_sample_kernel, (unsigned)k, 1024u, 0, stream, pdl, (const __half*)scores_t,
                                         (long long)ld, (long long)n, (int)k, (long long)(n_global / k), a.p,
-                                        (unsigned short*)nullptr, 0, (const unsigned short*)nullptr, 0, 1, PeerCtx{}, 0));
+                                        (unsigned short*)nullptr, 0, (const unsigned short*)nullptr, 0, 1, PeerCtx{}, 0, -1));
     if (which & 2) {
         static bool hs_set[RQK_MAX_DEVICES][2] = {};
         const size_t hs = auction_hist_smem(k);
@@ -2068,7 +2238,7 @@ int rqk_auction_sample_collect(const void* scores_t, int64_t ld, int64_t n, int3
     if (rc) return rc;
     if (!scores_t || !out || count < 1 || count > AUC_SAMPLE) return fail(RQK_ERR_ARG, "rqk_auction_sample_collect: bad argument%s");
     auction_sample_kernel<<<k, 1024, 0, (cudaStream_t)stream_>>>((const __half*)scores_t, ld, n, k, n_global / k, a.p,
-                                                                  (unsigned short*)out, count, nullptr, 0, 1, PeerCtx{}, 0);
+                                                                  (unsigned short*)out, count, nullptr, 0, 1, PeerCtx{}, 0, -1);
     RQK_LAUNCH_OK();
     return 0;
 }
@@ -2084,7 +2254,7 @@ int rqk_auction_sample_window(int64_t n, int64_t ld, int32_t k, int64_t n_global
     if (!keys || count < 1 || parts < 1 || (int64_t)count * parts > AUC_SAMPLE)
         return fail(RQK_ERR_ARG, "rqk_auction_sample_window: bad argument%s");
     auction_sample_kernel<<<k, 1024, 0, (cudaStream_t)stream_>>>(nullptr, ld, n_global, k, n_global / k, a.p, nullptr, 0,
-                                                                  (const unsigned short*)keys, count * parts, count, PeerCtx{}, 0);
+                                                                  (const unsigned short*)keys, count * parts, count, PeerCtx{}, 0, -1);
     RQK_LAUNCH_OK();
     return 0;
 }
@@ -2138,10 +2308,10 @@ int rqk_auction_peer_sample(const void* scores_t, int64_t ld, int64_t n, int32_t
     cudaStream_t stream = (cudaStream_t)stream_;
     unsigned short* mine = reinterpret_cast<unsigned short*>(c.buf[rank] + peer_sample_off(k)) + (size_t)(seq & 1) * k * AUC_SAMPLE_MAX;
     auction_sample_kernel<<<k, 1024, 0, stream>>>((const __half*)scores_t, ld, n, k, n_global / k, a.p, mine, count, nullptr, 0, 1,
-                                                  PeerCtx{}, 0);
+                                                  PeerCtx{}, 0, -1);
     auction_peer_barrier_kernel<<<1, 32, 0, stream>>>(a.p, c, 0, seq);
     auction_sample_kernel<<<k, 1024, 0, stream>>>(nullptr, ld, n_global, k, n_global / k, a.p, nullptr, 0, nullptr, count * world, count,
-                                                  c, seq & 1);
+                                                  c, seq & 1, -1);
     RQK_LAUNCH_OK();
     return 0;
 }
@@ -2149,27 +2319,49 @@ int rqk_auction_peer_sample(const void* scores_t, int64_t ld, int64_t n, int32_t
 int rqk_auction_peer_resolve(int64_t n, int64_t ld, int32_t k, int64_t n_global, int32_t expect, const void* const* peers,
                              int32_t world, int32_t rank, int32_t seq, void* workspace, size_t workspace_bytes, void* stream_);
 
-// One whole ROUND of a sharded job in one call (nine launches): local samples -> flag barrier -> windows from the
-// union; HIST pass; 1-CTA kernel that sums the peers' histograms, resolves and derives the rank-major tie offsets;
-// tie prefix; bidding round; 1-CTA kernel that sums the peers' counters and advances the state.  Uses sequence
-// numbers seq0+1 .. seq0+3 (the caller advances its counter by 3).  (Running the exchange in the last CTA of the
-// pass kernels instead, as the single-GPU driver does with its resolve step, measured SLOWER on 2 x B200: the
-// exchange is a chain of NVLink round trips, and a 1024-thread kernel of its own keeps more of them in flight.)
+// One whole ROUND of a sharded job in one call: seven launches chained with programmatic dependent launch (see
+// "whole-round protocol" above).  Sequence numbers: seq0 = the bid-counter exchange of the PREVIOUS round (its
+// resolve runs at the head of this call), seq0+1 the window samples, seq0+2 the threshold histograms; this round's
+// bid counters are exchanged under seq0+3 by the next call (the caller advances its counter by 3 per call and
+// keeps calling until the state reports done).  The hist area of the own exchange block must be zero when an
+// auction starts (rqk_auction_peer_hist_bytes).
 int rqk_auction_peer_round(const void* scores_t, int64_t ld, int64_t n, int32_t k, int64_t n_global, int32_t count,
                            const void* const* peers, int32_t world, int32_t rank, int32_t seq0, void* workspace,
                            size_t workspace_bytes, void* stream_) {
     using namespace rqk;
-    int rc = rqk_auction_peer_sample(scores_t, ld, n, k, n_global, count, peers, world, rank, seq0 + 1, workspace,
-                                     workspace_bytes, stream_);
-    if (rc) return rc;
     AuctionArgs a;
-    if ((rc = auction_prepare(n, ld, k, workspace, workspace_bytes, &a, "rqk_auction_peer_round"))) return rc;
+    int rc = auction_prepare(n, ld, k, workspace, workspace_bytes, &a, "rqk_auction_peer_round");
+    if (rc) return rc;
+    PeerCtx c;
+    if ((rc = peer_ctx(peers, world, rank, &c, "rqk_auction_peer_round"))) return rc;
+    if (!scores_t || count < 1 || (int64_t)count * world > AUC_SAMPLE) return fail(RQK_ERR_ARG, "rqk_auction_peer_round: bad argument%s");
+    if (n_global < k) return fail(RQK_ERR_ARG, "rqk_auction_peer_round: n_global=%s%lld < k=%lld", "", n_global, k);
     cudaStream_t stream = (cudaStream_t)stream_;
-    if ((rc = auction_launch(a, scores_t, ld, n, k, n_global, 2, 0, stream))) return rc;
-    if ((rc = rqk_auction_peer_resolve(n, ld, k, n_global, 0, peers, world, rank, seq0 + 2, workspace, workspace_bytes, stream_))) return rc;
-    if ((rc = auction_launch(a, scores_t, ld, n, k, n_global, 4, 0, stream))) return rc;
-    return rqk_auction_peer_resolve(n, ld, k, n_global, 1, peers, world, rank, seq0 + 3, workspace, workspace_bytes, stream_);
+    const bool pdl = auction_pdl_ok();
+    RQK_CUDA_OK(launch_round_kernel(auction_peer_bid_collect_kernel, (unsigned)k, 1024u, 0, stream, pdl, (const __half*)scores_t,
+                                    (long long)ld, (long long)n, (int)k, (long long)n_global, a.p, (int)count, c, (int)seq0,
+                                    (int)(seq0 + 1)));
+    RQK_CUDA_OK(launch_round_kernel(auction_sample_kernel, (unsigned)k, 1024u, 0, stream, pdl, (const __half*)nullptr, (long long)ld,
+                                    (long long)n_global, (int)k, (long long)(n_global / k), a.p, (unsigned short*)nullptr, 0,
+                                    (const unsigned short*)nullptr, (int)(count * world), (int)count, c, (int)((seq0 + 1) & 1),
+                                    (int)(seq0 + 1)));
+    // the HIST kernel merges this rank's histograms straight into its exchange block (parity of seq0 + 2)
+    AuctionArgs ah = a;
+    ah.p.hist_g = reinterpret_cast<unsigned int*>(c.buf[rank] + PEER_FLAGS_BYTES + PEER_TAIL_BYTES) +
+                  (size_t)((seq0 + 2) & 1) * peer_rb_words(k);
+    ah.p.above_g = ah.p.hist_g + (size_t)k * AUC_W;
+    ah.p.gap_g = ah.p.above_g + k;
+    if ((rc = auction_launch(ah, scores_t, ld, n, k, n_global, 2, 0, stream, true))) return rc;
+    RQK_CUDA_OK(launch_round_kernel(auction_peer_exchange_kernel, (unsigned)PEER_XCH_CTAS, 1024u, 0, stream, pdl, a.p,
+                                    (long long)n_global, (int)k, (long long)(n_global / k), c, (int)(seq0 + 2)));
+    if ((rc = auction_launch(a, scores_t, ld, n, k, n_global, 8 | 4, 0, stream, true))) return rc;
+    RQK_LAUNCH_OK();
+    return 0;
 }
+
+// Bytes of the histogram area of an exchange block (it starts at byte 512, after the flag and counter words) that
+// must be zero when an auction starts; the kernels keep it zero from then on.
+size_t rqk_auction_peer_hist_bytes(int32_t k) { return 2 * rqk::peer_rb_words(k) * 4; }
 
 // Resolve step of a sharded job with the rank exchange inside (expect: 0 after a HIST pass, 1 after a BID pass).
 int rqk_auction_peer_resolve(int64_t n, int64_t ld, int32_t k, int64_t n_global, int32_t expect, const void* const* peers,

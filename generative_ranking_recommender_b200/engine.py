@@ -374,6 +374,10 @@ def auction(scores_t: torch.Tensor, n: int, minmax: torch.Tensor,
         # Exchange through peer memory: the sums over ranks happen inside the sampling / resolve kernels
         # (flag barrier + direct reads of the peers' exchange blocks over NVLink); no collective call per round.
         ptrs = peer[2]
+        if not _PEER_STEPS:
+            # the whole-round protocol lets the HIST kernel merge straight into the exchange block: its histogram
+            # area starts every auction zeroed (every rank is past the previous auction: an all-reduce lies between)
+            peer[0][512:512 + int(L.rqk_auction_peer_hist_bytes(k))].zero_()
         count = max(4096 // shard.world, 1)
         for _ in range(0, 5000, batch):
             for _q in range(batch):

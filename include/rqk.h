@@ -106,12 +106,14 @@ int rqk_auction_tie_offset(int64_t n, int64_t ld, int32_t k, const int32_t* tota
  * of `world` (<= 8) device pointers, peers[r] = rank r's exchange block of rqk_auction_peer_bytes(k_max) bytes of
  * symmetric memory (zeroed once) as mapped into this process; seq: increased by one per call by every rank. */
 size_t rqk_auction_peer_bytes(int32_t k);
+/* bytes [512, 512 + this) of an exchange block must be zero when an auction that uses rqk_auction_peer_round starts */
+size_t rqk_auction_peer_hist_bytes(int32_t k);
 int rqk_auction_peer_sample(const void* scores_t, int64_t ld, int64_t n, int32_t k, int64_t n_global, int32_t count,
                             const void* const* peers, int32_t world, int32_t rank, int32_t seq, void* workspace,
                             size_t workspace_bytes, void* stream);
 int rqk_auction_peer_round(const void* scores_t, int64_t ld, int64_t n, int32_t k, int64_t n_global, int32_t count,
                            const void* const* peers, int32_t world, int32_t rank, int32_t seq0, void* workspace,
-                           size_t workspace_bytes, void* stream);   /* a whole round (9 launches); uses seq0+1 .. seq0+3 */
+                           size_t workspace_bytes, void* stream);   /* a whole round (7 launches): seq0 = the previous round's bid counters, seq0+1 samples, seq0+2 histograms */
 int rqk_auction_peer_resolve(int64_t n, int64_t ld, int32_t k, int64_t n_global, int32_t expect,
                              const void* const* peers, int32_t world, int32_t rank, int32_t seq, void* workspace,
                              size_t workspace_bytes, void* stream);

@@ -308,7 +308,7 @@ def test_peer_exchange_protocol_single_rank(dev, engine, n, k, bid_path, whole_r
     sess.init(_mm(st, n))
     seq, info = 0, None
     for _ in range(1500):
-        if whole_round:                 # one call: exchange + resolve run in the last CTA of the pass kernels
+        if whole_round:                 # one call per round: seven chained launches, exchanges inside the kernels
             sess.peer_round(4096, ptrs, 1, 0, seq)
         else:                           # step functions: exchange + resolve as their own 1-CTA kernels
             sess.peer_sample(4096, ptrs, 1, 0, seq + 1)
