@@ -253,6 +253,7 @@ class _Scratch:
 
 SCRATCH = _Scratch()
 
+SAMPLE_JOBS = 8192       # window-sampling jobs per worker over all ranks (csrc/auction.cu AUC_SAMPLE)
 FLAG_FARTHEST = 1
 FLAG_SIMT = 2
 
@@ -378,7 +379,7 @@ def auction(scores_t: torch.Tensor, n: int, minmax: torch.Tensor,
             # the whole-round protocol lets the HIST kernel merge straight into the exchange block: its histogram
             # area starts every auction zeroed (every rank is past the previous auction: an all-reduce lies between)
             peer[0][512:512 + int(L.rqk_auction_peer_hist_bytes(k))].zero_()
-        count = max(4096 // shard.world, 1)
+        count = max(SAMPLE_JOBS // shard.world, 1)
         for _ in range(0, 5000, batch):
             for _q in range(batch):
                 if _PEER_STEPS:          # the exchange + resolve as their own 1-CTA kernels (debugging / timing)
@@ -400,8 +401,8 @@ def auction(scores_t: torch.Tensor, n: int, minmax: torch.Tensor,
     for _ in range(0, 5000, batch):
         for _q in range(batch):
             # One ROUND, enqueued without knowing its outcome (kernels whose turn it is not return at once):
-            # identical sampled windows on every rank (4096 / world local jobs per worker, all-gathered) ...
-            local = sess.sample_collect(max(4096 // shard.world, 1))
+            # identical sampled windows on every rank (SAMPLE_JOBS / world local jobs per worker, all-gathered) ...
+            local = sess.sample_collect(max(SAMPLE_JOBS // shard.world, 1))
             sess.sample_window(shard.all_gather(local))
             # ... thresholds from the rank-summed histograms, ties ranked across ranks in rank order ...
             sess.do_pass(2)
