@@ -1023,8 +1023,13 @@ auction_pass_kernel(const __half* __restrict__ S, long long ld, long long N, int
 constexpr int HS_SUB = AUC_SUB;   // jobs staged (cost, owner) per sub-range
 __device__ __forceinline__ uint4 ldg_stream128(const void* ptr) {
     uint4 r;
+#if defined(RQK_HIST_NOALLOC)
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(ptr));
+#else
     asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(ptr));
+#endif
     return r;
 }
 
@@ -1244,11 +1249,11 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
                 qn = 0;
                 __syncwarp();
             };
-            uint4 cur[4], nxt[4];
+            uint4 bufA[4], bufB[4];
             int a = warp, st = 0;                                  // position in the active-row list, step in the row
             int w = a < nact ? (int)act[a] : 0;
-            if (a < nact) load_step(w, 0, cur);
-            while (a < nact) {
+            if (a < nact) load_step(w, 0, bufA);
+            auto body = [&](uint4 (&cur)[4], uint4 (&nxt)[4]) {
                 int an = a, wn = w, sn = st + 1;
                 if (sn == nsteps) { an = a + AUC_NW; sn = 0; wn = an < nact ? (int)act[an] : 0; }
                 if (an < nact) load_step(wn, sn, nxt);
@@ -1312,12 +1317,23 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
                     }
                 }
                 if (sn == 0 && qn) flush(w);                                     // the queue is per row
-#pragma unroll
-                for (int q = 0; q < 4; ++q) cur[q] = nxt[q];
                 a = an;
                 w = wn;
                 st = sn;
+            };
+#if defined(RQK_HIST_PINGPONG)
+            while (a < nact) {                                                   // the two buffers used alternately
+                body(bufA, bufB);
+                if (a >= nact) break;
+                body(bufB, bufA);
             }
+#else
+            while (a < nact) {
+                body(bufA, bufB);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) bufA[q] = bufB[q];
+            }
+#endif
         } else {
             for (int a = warp; a < nact; a += AUC_NW) {
                 const int w = act[a];
