@@ -581,22 +581,36 @@ def main():
                 roofline["tensor"] = {"error": repr(e)}
         del sess, sc
 
-    # ---- encode (the KMeans.predict + residual chain train() emits its ids with), rows resident in HBM ----
+    # ---- encode (the ids train() emits / predict() returns), rows resident in HBM ----
+    # fused = the single tcgen05 kernel over all levels (csrc/encode_fused.cu); chain = score pass + residual per level
     encode = None
     if rank == 0 and not args.no_extras:
         try:
             cs = [km.cluster_centers for km, _ in wl.levels]
-            for _ in range(2):
-                engine.encode(wl.x0, cs, CLUSTERS, [DIM], mode=0)
-            ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ee0.record()
-            for _ in range(3):
-                engine.encode(wl.x0, cs, CLUSTERS, [DIM], mode=0)
-            ee1.record()
-            torch.cuda.synchronize()
-            t_enc = ee0.elapsed_time(ee1) / 3
+
+            def time_encode(fused):
+                for _ in range(2):
+                    engine.encode(wl.x0, cs, CLUSTERS, [DIM], mode=0, fused=fused)
+                ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ee0.record()
+                for _ in range(3):
+                    engine.encode(wl.x0, cs, CLUSTERS, [DIM], mode=0, fused=fused)
+                ee1.record()
+                torch.cuda.synchronize()
+                return ee0.elapsed_time(ee1) / 3
+            t_enc = time_encode(True)
+            redo = engine.encode_reevaluated_rows(dev)
+            t_chain = time_encode(False)
+            tf = (roofline or {}).get("tensor", {}).get("tf32_tflops_measured")
+            flops = 3.0 * 2.0 * sum(CLUSTERS) * DIM * n          # three TF32 MMAs per product
             encode = {"value": n / (t_enc / 1e3), "unit": "vectors/s", "rows": n, "ms": t_enc, "gpus": 1,
-                      "what": "3-level ids of resident fp32 rows (rqk_encode, mode 0)"}
+                      "what": "3-level ids of resident fp32 rows, one tcgen05 kernel over all levels "
+                              "(rqk_encode_fused, mode 0): X read once, no residual in memory",
+                      "rows_reevaluated_exactly": redo,
+                      "level_chain_ms": t_chain, "level_chain_vectors_per_s": n / (t_chain / 1e3),
+                      "tensor_bound": ({"tflops_3xtf32_issued": flops / (t_enc / 1e3) / 1e12, "peak_tf32_tflops": tf,
+                                        "frac": flops / (t_enc / 1e3) / 1e12 / tf} if tf else None),
+                      "hbm_bytes_per_vector": 4 * DIM + 4 * len(CLUSTERS)}
         except Exception as e:      # never lose the bench line over the side metric
             encode = {"error": repr(e)}
 

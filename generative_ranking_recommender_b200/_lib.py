@@ -64,6 +64,9 @@ SIGNATURES = {
     "rqk_encode_workspace_bytes": (c_sz, [c_i64, c_i32, c_i32]),
     "rqk_encode": (ctypes.c_int, [c_p, c_i64, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p, c_i32, c_p, c_i32, c_i32,
                                   c_p, c_sz, c_p]),
+    "rqk_encode_fused_supported": (ctypes.c_int, [c_i32, c_i32, c_p, c_p, c_i32]),
+    "rqk_encode_fused_workspace_bytes": (c_sz, [c_i64, c_i32, c_i32, c_p]),
+    "rqk_encode_fused": (ctypes.c_int, [c_p, c_i64, c_i32, c_i32, c_p, c_p, c_p, c_p, c_i32, c_p, c_sz, c_p]),
 }
 
 

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librqk_sm100a.so")
-SOURCES = ["rqk_api.cu", "score_simt.cu", "score_tc.cu", "auction.cu", "centroid.cu", "residual.cu", "encode.cu", "seed_draw.cu"]
+SOURCES = ["rqk_api.cu", "score_simt.cu", "score_tc.cu", "auction.cu", "centroid.cu", "residual.cu", "encode.cu", "encode_fused.cu", "seed_draw.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-rdc=false",

@@ -12,6 +12,7 @@ contiguous row block.  The only data exchanged per iteration are
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -19,7 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib, sharding
-from ._lib import AuctionInfo, AuctionLayout, check, lib
+from ._lib import AuctionInfo, AuctionLayout, RqkError, check, lib
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -246,6 +247,9 @@ class _Scratch:
             b = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
             self.bufs[k] = b
         return b
+
+    def peek(self, key: str, dev: torch.device) -> Optional[torch.Tensor]:
+        return self.bufs.get((key, dev.index or 0))
 
     def clear(self):
         self.bufs.clear()
@@ -602,8 +606,13 @@ def gather_rows(x: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
 
 
 def encode(x: torch.Tensor, centers: List[torch.Tensor], needs: Sequence[int], group_dims: Sequence[int],
-           weights: Optional[List[Optional[torch.Tensor]]] = None, mode: int = 0, simt: bool = False) -> torch.Tensor:
-    """Multi-level ids int32 [levels, n] (csrc/encode.cu).  mode 0 = the chain train() emits, mode 1 = predict()."""
+           weights: Optional[List[Optional[torch.Tensor]]] = None, mode: int = 0, simt: bool = False,
+           fused: Optional[bool] = None) -> torch.Tensor:
+    """Multi-level ids int32 [levels, n].  mode 0 = the chain train() emits, mode 1 = predict().
+    Unit weights and one dim-group (what train_semantic_ids.py runs) go through the single tensor-core kernel of
+    csrc/encode_fused.cu - X read once, no residual in memory; everything else (per-group weights, dim-groups, cluster
+    counts that are not multiples of 32, the CUDA-core cross-check) through the level chain of csrc/encode.cu.
+    `fused` = True / False forces one or the other (tests, timing); RQK_ENC_CHAIN=1 forces the chain."""
     _req_cuda(x, "x")
     x = x.contiguous()
     n, dim = x.shape
@@ -612,15 +621,32 @@ def encode(x: torch.Tensor, centers: List[torch.Tensor], needs: Sequence[int], g
     centers = [c.contiguous() for c in centers]
     PtrArr = ctypes.c_void_p * levels
     cptr = PtrArr(*[c.data_ptr() for c in centers])
-    wptr = PtrArr(*[(w.data_ptr() if w is not None else None) for w in (weights or [None] * levels)])
     IntArr = ctypes.c_int32 * levels
     ks = IntArr(*[int(c.shape[0]) for c in centers])
     nd = IntArr(*[int(v) for v in needs])
     ids = torch.empty((levels, n), dtype=torch.int32, device=dev)
-    ge = _group_end(group_dims, dev)
     L = lib()
+    unit = all(w is None for w in (weights or [None] * levels)) and len(group_dims) == 1 and not simt
+    can = bool(unit and L.rqk_encode_fused_supported(dim, levels, ks, nd, mode))
+    if fused is None:
+        fused = can and os.environ.get("RQK_ENC_CHAIN", "0") != "1"
+    elif fused and not can:
+        raise RqkError("encode(fused=True): shape, weights or dim-groups outside what rqk_encode_fused takes")
+    if fused:
+        ws = SCRATCH.get("encode_fused", L.rqk_encode_fused_workspace_bytes(n, dim, levels, ks), dev)
+        _call(dev, L.rqk_encode_fused, _ptr(x), n, dim, levels, cptr, ks, nd, _ptr(ids), mode, _ptr(ws), ws.numel(),
+              _stream(dev))
+        return ids
+    wptr = PtrArr(*[(w.data_ptr() if w is not None else None) for w in (weights or [None] * levels)])
+    ge = _group_end(group_dims, dev)
     kmax = max(int(c.shape[0]) for c in centers)
     ws = SCRATCH.get("encode", L.rqk_encode_workspace_bytes(n, dim, kmax), dev)
     _call(dev, L.rqk_encode, _ptr(x), n, dim, levels, cptr, wptr, ks, nd, _ptr(ge), ge.numel(), _ptr(ids), mode,
                        FLAG_SIMT if simt else 0, _ptr(ws), ws.numel(), _stream(dev))
     return ids
+
+
+def encode_reevaluated_rows(dev: torch.device) -> int:
+    """Rows the last fused encode() on `dev` handed to the exact re-evaluation kernel (host sync)."""
+    ws = SCRATCH.peek("encode_fused", dev)
+    return 0 if ws is None else int(ws[:4].view(torch.int32).item())

@@ -165,6 +165,23 @@ int rqk_encode(const float* x, int64_t n, int32_t dim, int32_t levels, const voi
                const int32_t* group_end, int32_t ngroups, int32_t* ids, int32_t mode, int32_t flags, void* workspace,
                size_t workspace_bytes, void* stream);
 
+/* ---- multi-level encode in one tensor-core kernel (csrc/encode_fused.cu) ----------------------
+ * Same ids as rqk_encode for unit weights and one dim-group (the shape train_semantic_ids.py runs:
+ * hierarchical_rq_kmeans.py:539-581, :1111-1122), but X is read from HBM once and the per-level
+ * residual is never materialised: level l's scores are x . C_l^T corrected by gathered rows of the
+ * Gram tables C_m C_l^T (m < l) and the running scales.  Rows whose top-2 gap is inside the error
+ * budget of that algebra are re-evaluated through the literal chain by a second small kernel.
+ * rqk_encode_fused_supported: 1 if the shape is taken (1..4 levels, cluster counts multiples of 32
+ * in [32,256], dim a multiple of 32; mode 1 needs needs[l] == ks[l] at the masked levels), else 0 -
+ * callers then use rqk_encode.  workspace[0] (int32) = number of re-evaluated rows of the call.
+ */
+int rqk_encode_fused_supported(int32_t dim, int32_t levels, const int32_t* ks /*HOST*/, const int32_t* needs /*HOST*/,
+                               int32_t mode);
+size_t rqk_encode_fused_workspace_bytes(int64_t n, int32_t dim, int32_t levels, const int32_t* ks /*HOST*/);
+int rqk_encode_fused(const float* x, int64_t n, int32_t dim, int32_t levels, const void* const* centers /*HOST*/,
+                     const int32_t* ks /*HOST*/, const int32_t* needs /*HOST*/, int32_t* ids, int32_t mode,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

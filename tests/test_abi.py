@@ -48,6 +48,11 @@ def test_sizes_only_entry_points_work_on_cpu():
     assert L.rqk_auction_workspace_bytes(100000, 128) > 100000 * 4
     assert L.rqk_centroid_workspace_bytes(100000, 128, 512) > 0
     assert L.rqk_encode_workspace_bytes(100000, 512, 256) > 0
+    ks = (ctypes.c_int32 * 3)(128, 128, 256)
+    assert L.rqk_encode_fused_supported(512, 3, ks, ks, 0) == 1 and L.rqk_encode_fused_supported(512, 3, ks, ks, 1) == 1
+    assert 0 < L.rqk_encode_fused_workspace_bytes(1000000, 512, 3, ks) < 16 << 20      # no N x D scratch
+    odd = (ctypes.c_int32 * 3)(8, 8, 16)
+    assert L.rqk_encode_fused_supported(64, 3, odd, odd, 0) == 0 and L.rqk_encode_fused_workspace_bytes(10, 64, 3, odd) == 0
     lay = _lib.AuctionLayout()
     assert L.rqk_auction_layout_query(100000, 128, ctypes.byref(lay)) == 0
     assert lay.reduce_count == 128 * 256 + 2 * 128 + 2

@@ -764,3 +764,105 @@ def test_last_layer_training_structure(dev, engine, golden_dir, tmp_path):
     m2 = _last_layer_model(g, dev)
     m2.load_model(str(tmp_path / "model"))
     assert np.array_equal(m2.predict(g["x"]), pred)
+
+
+# ------------------------------------------------------------------------------------------------
+# single-kernel multi-level encode (csrc/encode_fused.cu) against the oracle's literal chain
+# ------------------------------------------------------------------------------------------------
+def _chain_centres(x, clusters, seed):
+    """Centres that look like a trained model's: means of three rows of the level's input (x, then the oracle's
+    normalised residual).  At level 0 a quarter of them ARE data rows, so some rows sit exactly on their centre: the
+    d = 0 corner of the residual's 1e-8 guard, where x - c is exactly zero in every implementation.  (Deeper levels get
+    no such centres: a centre copied from the oracle's residual differs from any other implementation's residual of
+    that row by an ulp, and an ulp-sized difference normalised to unit length is a direction made of rounding noise -
+    the reference itself is chaotic there.)"""
+    rng = np.random.default_rng(seed)
+    cur, centres = x, []
+    for l, k in enumerate(clusters):
+        pick = rng.integers(0, len(x), (k, 3))
+        c = cur[pick].mean(axis=1).astype(np.float32)
+        if l == 0:
+            c[: k // 4] = cur[pick[: k // 4, 0]]
+        centres.append(np.ascontiguousarray(c))
+        if l < len(clusters) - 1:
+            cur = O.residual_normalised(cur, O.predict(cur, c), c, [x.shape[1]])
+    return centres
+
+
+@pytest.mark.parametrize("n,dim,clusters", [
+    (100000, 512, [128, 128, 256]),          # the north-star codebook at BASELINE config 1's size: phases {0,1} | {2}
+    (30011, 512, [256, 256, 256, 256]),      # BASELINE config 5's codebook: four phases
+    (5000, 128, [32, 64, 96, 256]),          # three levels share one phase (accumulator columns 0 / 32 / 96)
+    (1000, 64, [64, 64]),                    # one narrow phase (third pipeline stage)
+    (777, 256, [128]),                       # a single level
+    (129, 512, [256, 32]),                   # second phase narrower than the first
+])
+def test_fused_encode_matches_oracle_chain(dev, engine, record_property, n, dim, clusters, monkeypatch):
+    """ids of the single-kernel encoder == the oracle's chain (mode 0: KMeans.predict + normalised residual per
+    level; mode 1: predict() with its +10000 quirk) outside counted fp64 near-ties, and == the GPU level chain wherever
+    that one is itself right.  Reports how many rows the kernel re-evaluated and what the algebra alone would do."""
+    import _parity_util as P
+    x = O.synth_mix(n, dim, seed=21, modes=min(1024, max(8, n // 50)))
+    centres = _chain_centres(x, clusters, seed=5)
+    xd = torch.from_numpy(x).to(dev)
+    cd = [torch.from_numpy(c).to(dev) for c in centres]
+    L = len(clusters)
+    w = [[1.0]] * L
+    want = {0: np.column_stack(O.encode_train_chain(x, centres, [dim], w))}
+    if L >= 3:                                   # the reference's predict() indexes two levels back (:1256)
+        want[1] = O.predict_hierarchy(x, centres, clusters, [dim], w)
+    for mode in sorted(want):
+        got = engine.encode(xd, cd, clusters, [dim], None, mode=mode, fused=True).t().cpu().numpy()
+        redo = engine.encode_reevaluated_rows(dev)
+        res = P.chain_mismatches(x, centres, got, want[mode], [dim], w, predict_mode=(mode == 1), needs=clusters)
+        P.report(record_property, f"fused_encode_{'x'.join(map(str, clusters))}_mode{mode}", res)
+        chain = engine.encode(xd, cd, clusters, [dim], None, mode=mode, fused=False).t().cpu().numpy()
+        differ = int((got != chain).any(axis=1).sum())
+        line = f"   n={n} mode {mode}: {redo} rows re-evaluated exactly, {differ} rows differ from the GPU level chain"
+        print(line)
+        record_property(f"fused_encode_redo_{'x'.join(map(str, clusters))}_mode{mode}", line)
+        assert sum(res["bad"]) == 0, res
+        assert sum(res["excluded"]) <= max(2, 0.002 * n), res
+        assert redo <= max(16, 0.02 * n), "the error budget flags far too many rows"
+        assert got.min() >= 0 and all(got[:, l].max() < clusters[l] for l in range(L))
+    # what the algebra does on its own (no re-evaluation): informational, plus a sanity bound
+    monkeypatch.setenv("RQK_ENC_FLAG_TOL", "0")
+    raw = engine.encode(xd, cd, clusters, [dim], None, mode=0, fused=True).t().cpu().numpy()
+    assert engine.encode_reevaluated_rows(dev) == 0
+    res0 = P.chain_mismatches(x, centres, raw, want[0], [dim], w)
+    P.report(record_property, f"fused_encode_{'x'.join(map(str, clusters))}_no_reevaluation", res0)
+    assert sum(res0["bad"]) + sum(res0["excluded"]) <= max(4, 0.005 * n), res0
+
+
+def test_fused_encode_is_what_predict_and_train_ids_use(dev, engine):
+    """predict() / encode_like_train() of a directly trained [32,32,64] model run through the fused kernel (unit
+    weights, one dim-group) and agree with the level chain outside near-ties; shapes the kernel does not take
+    (cluster counts that are not multiples of 32, dim-groups) silently keep the chain and fused=True refuses them."""
+    from generative_ranking_recommender_b200 import HierarchicalRQKMeans, HierarchicalRQKMeansConfig
+    from generative_ranking_recommender_b200._lib import RqkError
+    import _parity_util as P
+    n, dim, cl = 20000, 128, [32, 32, 64]
+    x = O.synth_mix(n, dim, seed=3, modes=200)
+    cfg = HierarchicalRQKMeansConfig(layer_clusters=cl, need_clusters=cl, embedding_dim=dim, iter_limit=10)
+    np.random.seed(11)
+    torch.manual_seed(11)
+    m = HierarchicalRQKMeans(cfg, device=dev)
+    out = m.train(x, resume=False)
+    centres = [c.cpu().numpy() for c in out["cluster_centers"]]
+    w = [[1.0]] * 3
+    pred = m.predict(x)
+    assert engine.SCRATCH.peek("encode_fused", dev) is not None, "predict() did not take the fused encoder"
+    want = O.predict_hierarchy(x, centres, cl, [dim], w)
+    resp = P.chain_mismatches(x, centres, pred, want, [dim], w, predict_mode=True, needs=cl)
+    P.report(None, "predict_ids_fused", resp)
+    assert sum(resp["bad"]) == 0 and sum(resp["excluded"]) <= 0.01 * n, resp
+    ids = np.column_stack([t.numpy() for t in out["cluster_ids"]])
+    res = P.chain_mismatches(x, centres, m.encode_like_train(x), ids, [dim], w)
+    assert sum(res["bad"]) == 0 and sum(res["excluded"]) <= 0.002 * n, res
+    xd = torch.from_numpy(x).to(dev)
+    c8 = [torch.from_numpy(c[:8]).to(dev).contiguous() for c in centres]
+    with pytest.raises(RqkError):
+        engine.encode(xd, c8, [8, 8, 8], [dim], None, fused=True)
+    assert engine.encode(xd, c8, [8, 8, 8], [dim], None).shape == (3, n)          # chain
+    with pytest.raises(RqkError):
+        engine.encode(xd, [torch.from_numpy(c).to(dev) for c in centres], cl, [64, 64], None, fused=True)

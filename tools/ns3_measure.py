@@ -55,7 +55,7 @@ if what == "encode":
     del x, cur
     torch.cuda.empty_cache()
     chunk_rows = 8 << 20                                   # 16 GiB of fp32 rows per chunk
-    out = {"what": "encode-only throughput (rqk_encode mode 0), [128,128,256], S-mix rows generated on the device",
+    out = {"what": "encode-only throughput (engine.encode mode 0 = rqk_encode_fused: one tcgen05 kernel over the three levels), [128,128,256], S-mix rows generated on the device",
            "n_gpus": world, "sizes": []}
     for total in (1000000, 10000000, 50000000, 100000000):
         mine = total // world + (1 if rank < total % world else 0)
