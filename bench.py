@@ -531,25 +531,32 @@ def main():
         sc = engine.score_pass(xl, km.cluster_centers, scores=True, argmin=False)
         sess = engine.AuctionSession(sc.scores_t, n, n)
         sess.init(sc.minmax)
-        t_hist, t_bid = [], []
+        # The kernels are launched one by one through the C-ABI step entry point in the flow rqk_auction chains
+        # (which | 16): HIST dumps per CTA, the merge kernel (one CTA per worker) sums the dumps, resolves the thresholds
+        # and takes the tie prefix, the bidding kernel's last CTA resolves the round.  A cycle runs whichever of them
+        # the device-side state machine lets act; the others return at once.
+        FLOW = 16
+        t_hist, t_bid, t_merge = [], [], []
         prev = sess.poll()
-        for cyc in range(40):
-            sess.do_pass(1)                                  # window sampling (early-exits unless needed), untimed
-            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        for cyc in range(60):
+            sess.do_pass(1 | FLOW)                           # window sampling (early-exits unless needed), untimed
+            e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
             e0.record()
-            sess.do_pass(2)                                  # streaming HIST kernel (returns at once in a BID cycle)
+            sess.do_pass(2 | FLOW)                           # streaming HIST kernel
             e1.record()
-            sess.do_pass(4)                                  # bid-list replay (+ the S-scanning fallback, which returns at once)
+            sess.do_pass(8 | FLOW)                           # merge + resolve + tie prefix
             e2.record()
-            sess.resolve()
+            sess.do_pass(4 | FLOW)                           # bid-list replay (+ the S-scanning fallback, which returns at once)
+            e3.record()
             cur = sess.poll()
             if cur.done:
                 break
             if cyc >= 4:                                     # past the cold start
                 if cur.cold_passes > prev.cold_passes:
                     t_hist.append(e0.elapsed_time(e1))
-                else:
-                    t_bid.append(e1.elapsed_time(e2))
+                    t_merge.append(e1.elapsed_time(e2))
+                if cur.passes - cur.cold_passes > prev.passes - prev.cold_passes:
+                    t_bid.append(e2.elapsed_time(e3))
             prev = cur
         k0 = CLUSTERS[0]
         alg_bytes = 2.0 * k0 * n
@@ -571,6 +578,10 @@ def main():
                     "ms_per_launch": sum(t_bid) / len(t_bid), "launches_timed": len(t_bid),
                     "note": "not a stream over S: reads ~2 % of it as L2-resident lists plus cost/owner of every job; "
                             "timed together with the early-exiting S-scanning fallback kernel"}
+            if t_merge:
+                roofline["merge_resolve_kernel"] = {
+                    "kernel": "auction_merge_resolve_kernel (per-worker sum of the CTA histograms, threshold, tie prefix)",
+                    "ms_per_launch": sum(t_merge) / len(t_merge), "launches_timed": len(t_merge)}
             roofline["composite"] = composite                # the per-ITERATION figure of SURVEY.md 8(d)
             try:
                 tf = tf32_peak(dev)

@@ -125,6 +125,10 @@ struct AuctionPtrs {
     unsigned int* rank_off;   // [K] ties at the threshold held by lower ranks (peer-memory sharding; else 0)
     unsigned int* ticket;     // [1] CTAs finished in the running pass kernel (fused resolve)
     int* res_pass;            // [K] value of AuctionState.passes when the worker's threshold was resolved
+    // single-GPU driver: the HIST pass only dumps per CTA; auction_merge_resolve_kernel (one CTA per worker) sums them
+    unsigned int* above_cta;  // [G][K]
+    unsigned int* gap_cta;    // [G][K]
+    int* unres_g;             // [2] workers the running merge-resolve pass left unresolved / window misses among them
 };
 
 static inline int auction_tile_cols(int K) { return K <= 128 ? 128 : 64; }
@@ -178,6 +182,9 @@ static inline size_t auction_ws_layout(long long N, long long ld, int K, Auction
     size_t o_ro = take_((size_t)K * 4);
     size_t o_tk2 = take_(4);
     size_t o_rp = take_((size_t)K * 4);
+    size_t o_ac = take_((size_t)G * K * 4);
+    size_t o_gc = take_((size_t)G * K * 4);
+    size_t o_ug = take_(8);
     if (reduce_off) *reduce_off = o_hist;
     if (tie_total_off) *tie_total_off = o_tt;
     if (p) {
@@ -207,6 +214,9 @@ static inline size_t auction_ws_layout(long long N, long long ld, int K, Auction
         p->rank_off = (unsigned int*)(base + o_ro);
         p->ticket = (unsigned int*)(base + o_tk2);
         p->res_pass = (int*)(base + o_rp);
+        p->above_cta = (unsigned int*)(base + o_ac);
+        p->gap_cta = (unsigned int*)(base + o_gc);
+        p->unres_g = (int*)(base + o_ug);
     }
     return off;
 }
@@ -242,6 +252,8 @@ __global__ void auction_init_kernel(AuctionPtrs p, long long ld, int K, const un
         s.force_scan = force_scan;
         *p.list_ok = 1;
         *p.ticket = 0;
+        p.unres_g[0] = 0;
+        p.unres_g[1] = 0;
         unsigned int smax = key2h(minmax_keys[0]), smin = key2h(minmax_keys[1]);
         // eps = (max - min) / 50 in fp16 (two roundings), floored at half(1e-4)  (:33-34)
         __half range = __hsub(bits2h(smax), bits2h(smin));
@@ -338,6 +350,108 @@ __device__ __forceinline__ BidOutcome bid_outcome(int counter, unsigned long lon
     return o;
 }
 
+// Threshold of ONE worker from its merged window histogram (one warp; lane l holds bins [8l, 8l+8) in h, lsum = their
+// sum).  Either resolves the worker (tkey / take / res_pass), or re-aims its window (refine inside a coarse bin, the
+// gap of a split window, a slide after a miss) and counts it in *unresolved (and *miss).
+__device__ __forceinline__ void resolve_one_worker(const AuctionPtrs& p, int w, const unsigned int (&h)[AUC_BPL],
+                                                   unsigned int lsum, unsigned long long ab, unsigned long long gap,
+                                                   int base, int shift, int hbase, int nlo, long long need, long long jpw,
+                                                   int passes, int* sink, int* unresolved, int* miss) {
+    const int lane = threadIdx.x & 31;
+    // suffix sums over lanes (bins above mine)
+    unsigned int suf = lsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned int o = __shfl_down_sync(0xffffffffu, suf, d);
+        if (lane + d < 32) suf += o;
+    }
+                // strictly above my bins (the gap of a split window sits between bins nlo-1 and nlo)
+    unsigned long long cum_excl = ab + (suf - lsum) + ((AUC_BPL * lane + AUC_BPL - 1) < nlo ? gap : 0ull);
+    const unsigned long long total = ab + __shfl_sync(0xffffffffu, suf, 0) + gap;
+    unsigned int hsum = 0;                                    // my bins of the upper run
+#pragma unroll
+    for (int i = 0; i < AUC_BPL; ++i) hsum += (AUC_BPL * lane + i >= nlo) ? h[i] : 0u;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) hsum += __shfl_xor_sync(0xffffffffu, hsum, d);
+    const unsigned long long c_hi = ab + hsum;               // everything >= hbase
+    const bool in_gap = gap > 0 && c_hi < (unsigned long long)need && c_hi + gap >= (unsigned long long)need;
+    int found_bin = -1;
+    unsigned long long g_above = 0;
+    if (!in_gap && ab < (unsigned long long)need && total >= (unsigned long long)need) {
+        unsigned long long c = cum_excl;
+#pragma unroll
+        for (int i = AUC_BPL - 1; i >= 0; --i) {
+            if (i != AUC_BPL - 1 && AUC_BPL * lane + i == nlo - 1) c += gap;   // stepping over the gap inside my bins
+            if (found_bin < 0 && c < (unsigned long long)need && c + h[i] >= (unsigned long long)need) {
+                found_bin = lane * AUC_BPL + i;
+                g_above = c;
+            }
+            c += h[i];
+        }
+    }
+    unsigned int who = __ballot_sync(0xffffffffu, found_bin >= 0);
+    if (who) {
+        int src = __ffs(who) - 1;
+        found_bin = __shfl_sync(0xffffffffu, found_bin, src);
+        g_above = __shfl_sync(0xffffffffu, g_above, src);
+        if (lane == 0) {
+            p.miss_run[w] = 0;
+            if (shift == 0) {
+                const int tk_new = found_bin >= nlo ? hbase + found_bin - nlo : base + found_bin;
+                const int tp = p.tprev[w];
+                if (tp >= 0) {
+                    const int d = tp - tk_new;
+                    atomicAdd(&sink[d < 64 ? 0 : d < 128 ? 1 : d < 250 ? 2 : 3], 1);
+                }
+                p.tkey[w] = found_bin >= nlo ? hbase + found_bin - nlo : base + found_bin;
+                p.take[w] = (int)(jpw - (long long)g_above);
+                p.res_pass[w] = passes;
+            } else {   // refine inside the bin that holds the threshold
+                int nshift = shift >= 8 ? shift - 8 : 0;
+                const int nb2 = base + (found_bin << shift);
+                p.win_base[w] = nb2;
+                p.win_hbase[w] = nb2 + AUC_HALF;
+                p.win_nlo[w] = AUC_HALF;
+                p.win_shift[w] = nshift;
+                p.tkey[w] = -1;
+                atomicAdd(unresolved, 1);
+            }
+        }
+    } else if (lane == 0 && in_gap) {
+        // the threshold lies between the two halves of a split window: histogram just that range
+        int nb2 = base + nlo, span = hbase - nb2, nshift = 0;
+        while ((span >> nshift) > AUC_W) ++nshift;
+        p.win_base[w] = nb2;
+        p.win_hbase[w] = nb2 + AUC_HALF;
+        p.win_nlo[w] = AUC_HALF;
+        p.win_shift[w] = nshift;
+        p.tkey[w] = -1;
+        atomicAdd(unresolved, 1);
+        atomicAdd(miss, 1);
+    } else if (lane == 0) {
+        // the window missed the threshold: slide one window up / down, restart coarse if that
+        // keeps failing (or if the window was a refinement, which cannot miss by construction)
+        const int run = p.miss_run[w];
+        const bool is_above = ab >= (unsigned long long)need;
+        int nb = is_above ? (shift == 0 ? hbase + (AUC_W - nlo) : base + (AUC_W << shift)) : base - (AUC_W << shift);
+        if (shift != 0 || run >= 2 || nb < AUC_MIN_KEY || nb > 65536 - AUC_W) {
+            p.win_base[w] = 0;
+            p.win_hbase[w] = AUC_HALF;
+            p.win_nlo[w] = AUC_HALF;
+            p.win_shift[w] = AUC_COLD_SHIFT;
+            p.miss_run[w] = 0;
+        } else {
+            p.win_base[w] = nb;
+            p.win_hbase[w] = nb + AUC_HALF;
+            p.win_nlo[w] = AUC_HALF;
+            p.miss_run[w] = run + 1;
+        }
+        p.tkey[w] = -1;
+        atomicAdd(unresolved, 1);
+        if (shift == 0) atomicAdd(miss, 1);
+    }
+}
+
 // `expect`: -1, or the mode whose pass must have just run (MODE_HIST / MODE_BID) for the call to act.
 __device__ __noinline__ void auction_resolve_body(AuctionPtrs p, long long N, int K, long long jpw, int expect) {
     __shared__ int s_unresolved, s_miss;
@@ -406,104 +520,15 @@ __device__ __noinline__ void auction_resolve_body(AuctionPtrs p, long long N, in
                 for (int i = 0; i < AUC_BPL; ++i) hn[i] = __ldcg(p.hist_g + (w + NWARPS) * AUC_W + lane * AUC_BPL + i);
             }
             if (settled) continue;
-            // suffix sums over lanes (bins above mine)
-            unsigned int suf = lsum;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                unsigned int o = __shfl_down_sync(0xffffffffu, suf, d);
-                if (lane + d < 32) suf += o;
-            }
-            const unsigned long long ab = p.above_g[w];
-            // strictly above my bins (the gap of a split window sits between bins nlo-1 and nlo)
-            unsigned long long cum_excl = ab + (suf - lsum) + ((AUC_BPL * lane + AUC_BPL - 1) < nlo ? gap : 0ull);
-            const unsigned long long total = ab + __shfl_sync(0xffffffffu, suf, 0) + gap;
-            unsigned int hsum = 0;                                    // my bins of the upper run
-#pragma unroll
-            for (int i = 0; i < AUC_BPL; ++i) hsum += (AUC_BPL * lane + i >= nlo) ? h[i] : 0u;
-#pragma unroll
-            for (int d = 16; d; d >>= 1) hsum += __shfl_xor_sync(0xffffffffu, hsum, d);
-            const unsigned long long c_hi = ab + hsum;               // everything >= hbase
-            const bool in_gap = gap > 0 && c_hi < (unsigned long long)need && c_hi + gap >= (unsigned long long)need;
-            int found_bin = -1;
-            unsigned long long g_above = 0;
-            if (!in_gap && ab < (unsigned long long)need && total >= (unsigned long long)need) {
-                unsigned long long c = cum_excl;
-#pragma unroll
-                for (int i = AUC_BPL - 1; i >= 0; --i) {
-                    if (i != AUC_BPL - 1 && AUC_BPL * lane + i == nlo - 1) c += gap;   // stepping over the gap inside my bins
-                    if (found_bin < 0 && c < (unsigned long long)need && c + h[i] >= (unsigned long long)need) {
-                        found_bin = lane * AUC_BPL + i;
-                        g_above = c;
-                    }
-                    c += h[i];
-                }
-            }
-            unsigned int who = __ballot_sync(0xffffffffu, found_bin >= 0);
-            if (who) {
-                int src = __ffs(who) - 1;
-                found_bin = __shfl_sync(0xffffffffu, found_bin, src);
-                g_above = __shfl_sync(0xffffffffu, g_above, src);
-                if (lane == 0) {
-                    p.miss_run[w] = 0;
-                    if (shift == 0) {
-                        const int tk_new = found_bin >= nlo ? hbase + found_bin - nlo : base + found_bin;
-                        const int tp = p.tprev[w];
-                        if (tp >= 0) {
-                            const int d = tp - tk_new;
-                            atomicAdd(&s.sink[d < 64 ? 0 : d < 128 ? 1 : d < 250 ? 2 : 3], 1);
-                        }
-                        p.tkey[w] = found_bin >= nlo ? hbase + found_bin - nlo : base + found_bin;
-                        p.take[w] = (int)(jpw - (long long)g_above);
-                        p.res_pass[w] = s.passes;
-                    } else {   // refine inside the bin that holds the threshold
-                        int nshift = shift >= 8 ? shift - 8 : 0;
-                        const int nb2 = base + (found_bin << shift);
-                        p.win_base[w] = nb2;
-                        p.win_hbase[w] = nb2 + AUC_HALF;
-                        p.win_nlo[w] = AUC_HALF;
-                        p.win_shift[w] = nshift;
-                        p.tkey[w] = -1;
-                        atomicAdd(&s_unresolved, 1);
-                    }
-                }
-            } else if (lane == 0 && in_gap) {
-                // the threshold lies between the two halves of a split window: histogram just that range
-                int nb2 = base + nlo, span = hbase - nb2, nshift = 0;
-                while ((span >> nshift) > AUC_W) ++nshift;
-                p.win_base[w] = nb2;
-                p.win_hbase[w] = nb2 + AUC_HALF;
-                p.win_nlo[w] = AUC_HALF;
-                p.win_shift[w] = nshift;
-                p.tkey[w] = -1;
-                atomicAdd(&s_unresolved, 1);
-                atomicAdd(&s_miss, 1);
-            } else if (lane == 0) {
-                // the window missed the threshold: slide one window up / down, restart coarse if that
-                // keeps failing (or if the window was a refinement, which cannot miss by construction)
-                const int run = p.miss_run[w];
-                const bool is_above = ab >= (unsigned long long)need;
-                int nb = is_above ? (shift == 0 ? hbase + (AUC_W - nlo) : base + (AUC_W << shift)) : base - (AUC_W << shift);
-                if (shift != 0 || run >= 2 || nb < AUC_MIN_KEY || nb > 65536 - AUC_W) {
-                    p.win_base[w] = 0;
-                    p.win_hbase[w] = AUC_HALF;
-                    p.win_nlo[w] = AUC_HALF;
-                    p.win_shift[w] = AUC_COLD_SHIFT;
-                    p.miss_run[w] = 0;
-                } else {
-                    p.win_base[w] = nb;
-                    p.win_hbase[w] = nb + AUC_HALF;
-                    p.win_nlo[w] = AUC_HALF;
-                    p.miss_run[w] = run + 1;
-                }
-                p.tkey[w] = -1;
-                atomicAdd(&s_unresolved, 1);
-                if (shift == 0) atomicAdd(&s_miss, 1);
-            }
+            resolve_one_worker(p, w, h, lsum, p.above_g[w], gap, base, shift, hbase, nlo, need, jpw, s.passes, s.sink,
+                               &s_unresolved, &s_miss);
         }
     }
     __syncthreads();
-    // ---- 3. zero the merged histograms for the next pass ----
-    for (int i = tid; i < K * AUC_W + 2 * K + 2; i += NT) p.hist_g[i] = 0;
+    // ---- 3. zero the reduce block for the next pass ----
+    // (after a BID pass only its counters: the histogram part was zeroed by the HIST resolve before it, or never
+    // written at all when the HIST passes dump per CTA for auction_merge_resolve_kernel)
+    for (int i = tid + (was_bid ? K * AUC_W : 0); i < K * AUC_W + 2 * K + 2; i += NT) p.hist_g[i] = 0;
     __syncthreads();
     if (tid == 0) {
         s.passes += 1;
@@ -1387,8 +1412,24 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
         }
     }
 
-    // ---- publish (active rows only): per-CTA dump (for the tie prefix) + merge of non-empty bins ----
+    // ---- publish (active rows only) ----
     unsigned int* dump = reinterpret_cast<unsigned int*>(p.hist_cta + (size_t)b * K * AUC_W);
+    if (fused) {
+        // single-GPU driver: plain stores of the CTA's histogram / above / gap counts.  auction_merge_resolve_kernel
+        // (one CTA per worker, next in the chain) sums them over the CTAs, resolves the worker's threshold and takes
+        // the tie prefix - no global atomics here, no serial resolve in a last CTA.
+        for (int a = tid >> 7; a < nact; a += AUC_THREADS >> 7) {
+            const int i = (int)act[a] * (AUC_W / 2) + (tid & 127);
+            dump[i] = sm.hist[i];
+        }
+        for (int a = tid; a < nact; a += AUC_THREADS) {
+            const int i = act[a];
+            p.above_cta[(size_t)b * K + i] = sm.above[i];
+            p.gap_cta[(size_t)b * K + i] = sm.gap[i];
+        }
+        return;
+    }
+    // step-by-step / sharded flows: per-CTA dump (for the tie prefix) + merge of non-empty bins into the reduce block
     for (int a = tid >> 7; a < nact; a += AUC_THREADS >> 7) {                // AUC_W / 2 = 128 words per row
         const int i = (int)act[a] * (AUC_W / 2) + (tid & 127);
         const unsigned int h = sm.hist[i];
@@ -1401,7 +1442,6 @@ auction_hist_kernel(const __half* __restrict__ S, long long ld, long long N, int
         if (sm.above[i]) atomicAdd(&p.above_g[i], sm.above[i]);
         if (sm.gap[i]) atomicAdd(&p.gap_g[i], sm.gap[i]);
     }
-    if (fused && auction_last_cta(p.ticket)) auction_resolve_body(p, n_global, K, n_global / K, MODE_HIST);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -2054,6 +2094,105 @@ auction_tieprefix_kernel(AuctionPtrs p, int K, int G) {
     if (tid == AUC_MAX_CTAS - 1) p.tie_total[w] = cnt[AUC_MAX_CTAS - 1];
 }
 
+// Single-GPU driver, after a HIST pass that only dumped per CTA: CTA w sums worker w's window histogram over the G
+// dumps (16-bit pairs -> 32-bit bins), resolves the worker's threshold (resolve_one_worker - what the last CTA of the
+// HIST kernel used to do for all K workers one after the other), takes the tie prefix if the worker was resolved, and
+// the CTA that finishes last makes the state transition of the resolve step (part 4 of auction_resolve_body).
+// Workers settled by an earlier pass of the round keep what that pass left (threshold, dump, tie prefix).
+__global__ void __launch_bounds__(AUC_MAX_CTAS, 1)
+auction_merge_resolve_kernel(AuctionPtrs p, int K, int G, long long jpw) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ unsigned int part[8][AUC_W];
+    __shared__ unsigned int hist_s[AUC_W];
+    __shared__ unsigned int cnt[AUC_MAX_CTAS];
+    __shared__ unsigned int s_ab[AUC_MAX_CTAS / 32], s_gp[AUC_MAX_CTAS / 32];
+    __shared__ int s_flag[2], s_mode, s_passes;
+    const int w = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { s_mode = p.st->mode; s_passes = p.st->passes; s_flag[0] = 0; s_flag[1] = 0; }
+    __syncthreads();
+    if (s_mode != MODE_HIST) return;                         // no HIST pass has just run (done, or a no-op round)
+    const bool settled = p.tkey[w] >= 0;
+    if (!settled) {
+        // ---- 1. merge ----
+        const unsigned int* d32 = reinterpret_cast<const unsigned int*>(p.hist_cta);
+        const int word = tid & 127, grp = tid >> 7;          // 8 groups of 128 threads, group q takes CTAs q, q+8, ..
+        unsigned int lo = 0, hi = 0;
+        for (int g = grp; g < G; g += 8) {
+            const unsigned int h = __ldcg(d32 + ((size_t)g * K + w) * (AUC_W / 2) + word);
+            lo += h & 0xffffu;
+            hi += h >> 16;
+        }
+        part[grp][2 * word] = lo;
+        part[grp][2 * word + 1] = hi;
+        unsigned int ab = 0, gp = 0;
+        if (tid < G) { ab = __ldcg(p.above_cta + (size_t)tid * K + w); gp = __ldcg(p.gap_cta + (size_t)tid * K + w); }
+        ab = __reduce_add_sync(0xffffffffu, ab);
+        gp = __reduce_add_sync(0xffffffffu, gp);
+        if (lane == 0) { s_ab[warp] = ab; s_gp[warp] = gp; }
+        __syncthreads();
+        if (tid < AUC_W) {
+            unsigned int t = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) t += part[q][tid];
+            hist_s[tid] = t;
+        }
+        __syncthreads();
+        // ---- 2. resolve (one warp) ----
+        if (warp == 0) {
+            unsigned long long abt = 0, gpt = 0;
+            for (int q = 0; q < AUC_MAX_CTAS / 32; ++q) { abt += s_ab[q]; gpt += s_gp[q]; }
+            const int base = p.win_base[w], shift = p.win_shift[w];
+            const int hbase = p.win_hbase[w], nlo = (shift == 0) ? p.win_nlo[w] : 0;
+            const unsigned long long gap = (shift == 0) ? gpt : 0ull;
+            unsigned int h[AUC_BPL];
+            unsigned int lsum = 0;
+#pragma unroll
+            for (int i = 0; i < AUC_BPL; ++i) { h[i] = hist_s[lane * AUC_BPL + i]; lsum += h[i]; }
+            resolve_one_worker(p, w, h, lsum, abt, gap, base, shift, hbase, nlo, jpw + 1, jpw, s_passes, p.st->sink,
+                               &s_flag[0], &s_flag[1]);
+        }
+        __syncthreads();
+        // ---- 3. tie prefix over the CTAs, if this pass resolved the worker (as auction_tieprefix_kernel) ----
+        const int tk = p.tkey[w];
+        if (tk >= 0) {
+            const int base = p.win_base[w], hbase = p.win_hbase[w], nlo = p.win_nlo[w];
+            const int bin = tk >= hbase ? nlo + tk - hbase : tk - base;   // shift is 0 when resolved
+            unsigned int c = 0;
+            if (tid < G) c = p.hist_cta[((size_t)tid * K + w) * AUC_W + bin];
+            cnt[tid] = c;
+            __syncthreads();
+            for (int d = 1; d < AUC_MAX_CTAS; d <<= 1) {
+                unsigned int v = (tid >= d) ? cnt[tid - d] : 0;
+                __syncthreads();
+                cnt[tid] += v;
+                __syncthreads();
+            }
+            if (tid < G) p.tieprefix[(size_t)tid * K + w] = cnt[tid] - c + p.rank_off[w];
+            if (tid == AUC_MAX_CTAS - 1) p.tie_total[w] = cnt[AUC_MAX_CTAS - 1];
+        }
+        if (tid == 0) {
+            if (s_flag[0]) atomicAdd(&p.unres_g[0], 1);
+            if (s_flag[1]) atomicAdd(&p.unres_g[1], 1);
+        }
+    }
+    // ---- 4. the CTA that finishes last: state transition of a resolved HIST pass ----
+    if (auction_last_cta(p.ticket) && tid == 0) {
+        AuctionState s = *p.st;
+        const int unresolved = __ldcg(&p.unres_g[0]), miss = __ldcg(&p.unres_g[1]);
+        p.unres_g[0] = 0;
+        p.unres_g[1] = 0;
+        s.passes += 1;
+        s.cold_passes += 1;
+        s.window_misses += miss;
+        s.ff_pending = 0;
+        s.need_sample = 0;
+        s.use_list = (*p.list_ok != 0 && !s.force_scan) ? 1 : 0;
+        s.mode = (unresolved == 0) ? MODE_BID : MODE_HIST;
+        *p.st = s;
+    }
+}
+
 // sharded jobs: ranks are ordered, so a rank's CTAs come after all ties of lower ranks
 __global__ void auction_tie_offset_kernel(AuctionPtrs p, int K, int G, const int* __restrict__ totals, int rank) {
     if (p.st->mode != MODE_BID) return;
@@ -2156,8 +2295,13 @@ static int auction_launch(const AuctionArgs& a, const void* scores_t, int64_t ld
                                         (const __half*)scores_t, (long long)ld, (long long)n, (int)k, a.J, spc, a.p,
                                         (long long)n_global, fused));
     }
-    if (which & 8)
-        RQK_CUDA_OK(launch_round_kernel(auction_tieprefix_kernel, (unsigned)k, (unsigned)AUC_MAX_CTAS, 0, stream, pdl, a.p, (int)k, a.G));
+    if (which & 8) {
+        if (fused)      // HIST only dumped: merge + resolve + tie prefix, one CTA per worker
+            RQK_CUDA_OK(launch_round_kernel(auction_merge_resolve_kernel, (unsigned)k, (unsigned)AUC_MAX_CTAS, 0, stream, pdl,
+                                            a.p, (int)k, a.G, (long long)(n_global / k)));
+        else
+            RQK_CUDA_OK(launch_round_kernel(auction_tieprefix_kernel, (unsigned)k, (unsigned)AUC_MAX_CTAS, 0, stream, pdl, a.p, (int)k, a.G));
+    }
     if (which & 4) {
         RQK_CUDA_OK(launch_round_kernel(auction_bidlist_kernel, (unsigned)a.G, (unsigned)AUC_THREADS, 0, stream, pdl,
                                         (const __half*)scores_t, (long long)ld, (long long)n, (int)k, a.J, spc, a.p,
@@ -2240,7 +2384,10 @@ int rqk_auction_pass(const void* scores_t, int64_t ld, int64_t n, int32_t k, int
     if (n_global < k) return fail(RQK_ERR_ARG, "rqk_auction_pass: n_global=%s%lld < k=%lld (argmin path, reference :24-26)", "", n_global, k);
     if (which == 0) which = 7;
     if (n_global != n) which &= ~1;   // sharded jobs: rqk_auction_sample_collect / _window (ranks must agree on the windows)
-    return auction_launch(a, scores_t, ld, n, k, n_global, which, 0, (cudaStream_t)stream_);
+    // bit 4: the kernels of the single-GPU driver's flow (HIST dumps per CTA, bit 3 = merge + resolve + tie prefix, the
+    // bidding kernel's last CTA resolves) - timing and tests of exactly what rqk_auction chains; unsharded jobs only
+    const int fused = (which & 16) && n_global == n ? 1 : 0;
+    return auction_launch(a, scores_t, ld, n, k, n_global, which & 15, fused, (cudaStream_t)stream_);
 }
 
 // Sharded window sampling, step 1: keys of `count` (<= 4096) evenly strided local jobs per worker -> out [k][count]

@@ -91,7 +91,12 @@ int rqk_auction(const void* scores_t, int64_t ld, int64_t n, int32_t k, const vo
 int rqk_auction_init(int64_t n, int64_t ld, int32_t k, const void* minmax_keys, void* workspace,
                      size_t workspace_bytes, void* stream);
 int rqk_auction_pass(const void* scores_t, int64_t ld, int64_t n, int32_t k, int64_t n_global, int32_t which,
-                     void* workspace, size_t workspace_bytes, void* stream);   /* which: 0 = all; bit0 sample, bit1 HIST, bit2 BID */
+                     void* workspace, size_t workspace_bytes, void* stream);
+/* which: 0 = sample + HIST + BID; else bit0 window sampling, bit1 HIST, bit2 BID, bit3 tie prefix.  Followed by
+ * rqk_auction_resolve this is the step-by-step flow (the HIST pass merges its histograms into the reduce block).
+ * bit4 (unsharded jobs): the kernels exactly as rqk_auction chains them - the HIST pass dumps its histograms per CTA,
+ * bit3 is then the merge kernel (one CTA per worker: sum of the dumps, threshold, tie prefix, state transition) and
+ * the bidding kernel's last CTA resolves the round; no rqk_auction_resolve calls in that flow. */
 /* sharded jobs: every rank samples `count` of its jobs per worker (uint16 fp16 keys, [k][count]); the host
  * all-gathers them into [k][world*count] (<= 4096) and every rank places identical windows from the union */
 int rqk_auction_sample_collect(const void* scores_t, int64_t ld, int64_t n, int32_t k, int64_t n_global, void* out,

@@ -823,7 +823,8 @@ def test_fused_encode_matches_oracle_chain(dev, engine, record_property, n, dim,
         record_property(f"fused_encode_redo_{'x'.join(map(str, clusters))}_mode{mode}", line)
         assert sum(res["bad"]) == 0, res
         assert sum(res["excluded"]) <= max(2, 0.002 * n), res
-        assert redo <= max(16, 0.02 * n), "the error budget flags far too many rows"
+        # (every row that IS a level-0 centre sits at d = 0 and is re-evaluated by design: clusters[0] // 4 of them)
+        assert redo <= max(16, 0.02 * n) + clusters[0] // 4, "the error budget flags far too many rows"
         assert got.min() >= 0 and all(got[:, l].max() < clusters[l] for l in range(L))
     # what the algebra does on its own (no re-evaluation): informational, plus a sanity bound
     monkeypatch.setenv("RQK_ENC_FLAG_TOL", "0")
