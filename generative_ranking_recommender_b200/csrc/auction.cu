@@ -128,7 +128,8 @@ struct AuctionPtrs {
     // single-GPU driver: the HIST pass only dumps per CTA; auction_merge_resolve_kernel (one CTA per worker) sums them
     unsigned int* above_cta;  // [G][K]
     unsigned int* gap_cta;    // [G][K]
-    int* unres_g;             // [2] workers the running merge-resolve pass left unresolved / window misses among them
+    int* unres_g;             // [4] workers the running merge-resolve pass left unresolved / window misses among them /
+                              //     arrival ticket of auction_peer_publish_kernel
 };
 
 static inline int auction_tile_cols(int K) { return K <= 128 ? 128 : 64; }
@@ -184,7 +185,7 @@ static inline size_t auction_ws_layout(long long N, long long ld, int K, Auction
     size_t o_rp = take_((size_t)K * 4);
     size_t o_ac = take_((size_t)G * K * 4);
     size_t o_gc = take_((size_t)G * K * 4);
-    size_t o_ug = take_(8);
+    size_t o_ug = take_(16);
     if (reduce_off) *reduce_off = o_hist;
     if (tie_total_off) *tie_total_off = o_tt;
     if (p) {
@@ -254,6 +255,7 @@ __global__ void auction_init_kernel(AuctionPtrs p, long long ld, int K, const un
         *p.ticket = 0;
         p.unres_g[0] = 0;
         p.unres_g[1] = 0;
+        p.unres_g[2] = 0;
         unsigned int smax = key2h(minmax_keys[0]), smin = key2h(minmax_keys[1]);
         // eps = (max - min) / 50 in fp16 (two roundings), floored at half(1e-4)  (:33-34)
         __half range = __hsub(bits2h(smax), bits2h(smin));
@@ -2094,103 +2096,237 @@ auction_tieprefix_kernel(AuctionPtrs p, int K, int G) {
     if (tid == AUC_MAX_CTAS - 1) p.tie_total[w] = cnt[AUC_MAX_CTAS - 1];
 }
 
+// ---- pieces shared by the per-worker merge kernels (one CTA of AUC_MAX_CTAS threads per worker) ----
+struct MergeSmem {
+    unsigned int part[8][AUC_W];
+    unsigned int hist[AUC_W];
+    unsigned int cnt[AUC_MAX_CTAS];
+    unsigned int ab[AUC_MAX_CTAS / 32], gp[AUC_MAX_CTAS / 32];
+};
+
+// hist[0..255] = worker w's window histogram summed over the G per-CTA dumps of the HIST pass (16-bit pairs -> 32-bit
+// bins); returns the summed above / gap counts to every thread.  Ends with a __syncthreads.
+__device__ __forceinline__ void merge_worker_dumps(const AuctionPtrs& p, int K, int G, int w, MergeSmem& m,
+                                                   unsigned int* above, unsigned int* gap) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned int* d32 = reinterpret_cast<const unsigned int*>(p.hist_cta);
+    const int word = tid & 127, grp = tid >> 7;              // 8 groups of 128 threads, group q takes CTAs q, q+8, ..
+    unsigned int lo = 0, hi = 0;
+    for (int g = grp; g < G; g += 8) {
+        const unsigned int h = __ldcg(d32 + ((size_t)g * K + w) * (AUC_W / 2) + word);
+        lo += h & 0xffffu;
+        hi += h >> 16;
+    }
+    m.part[grp][2 * word] = lo;
+    m.part[grp][2 * word + 1] = hi;
+    unsigned int ab = 0, gp = 0;
+    if (tid < G) { ab = __ldcg(p.above_cta + (size_t)tid * K + w); gp = __ldcg(p.gap_cta + (size_t)tid * K + w); }
+    ab = __reduce_add_sync(0xffffffffu, ab);
+    gp = __reduce_add_sync(0xffffffffu, gp);
+    if (lane == 0) { m.ab[warp] = ab; m.gp[warp] = gp; }
+    __syncthreads();
+    if (tid < AUC_W) {
+        unsigned int t = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t += m.part[q][tid];
+        m.hist[tid] = t;
+    }
+    unsigned int abt = 0, gpt = 0;
+    for (int q = 0; q < AUC_MAX_CTAS / 32; ++q) { abt += m.ab[q]; gpt += m.gp[q]; }
+    *above = abt;
+    *gap = gpt;
+    __syncthreads();
+}
+
+// Exclusive prefix over this rank's CTAs of the number of values equal to worker w's resolved threshold (bin of the
+// per-CTA dumps), offset by the ties lower ranks hold.  All threads of the CTA; contains __syncthreads.
+__device__ __forceinline__ void tie_prefix_worker(const AuctionPtrs& p, int K, int G, int w, MergeSmem& m, unsigned int rank_off) {
+    const int tid = threadIdx.x;
+    const int tk = p.tkey[w];
+    const int base = p.win_base[w], hbase = p.win_hbase[w], nlo = p.win_nlo[w];
+    const int bin = tk >= hbase ? nlo + tk - hbase : tk - base;   // shift is 0 when resolved
+    unsigned int c = 0;
+    if (tid < G) c = p.hist_cta[((size_t)tid * K + w) * AUC_W + bin];
+    m.cnt[tid] = c;
+    __syncthreads();
+    for (int d = 1; d < AUC_MAX_CTAS; d <<= 1) {                  // Hillis-Steele inclusive scan
+        unsigned int v = (tid >= d) ? m.cnt[tid - d] : 0;
+        __syncthreads();
+        m.cnt[tid] += v;
+        __syncthreads();
+    }
+    if (tid < G) p.tieprefix[(size_t)tid * K + w] = m.cnt[tid] - c + rank_off;
+    if (tid == AUC_MAX_CTAS - 1) p.tie_total[w] = m.cnt[AUC_MAX_CTAS - 1];
+}
+
+// State transition after a HIST pass whose workers were resolved one per CTA (part 4 of auction_resolve_body); run
+// by thread 0 of the CTA that finished last.
+__device__ __forceinline__ void merge_state_transition(const AuctionPtrs& p) {
+    AuctionState s = *p.st;
+    const int unresolved = __ldcg(&p.unres_g[0]), miss = __ldcg(&p.unres_g[1]);
+    p.unres_g[0] = 0;
+    p.unres_g[1] = 0;
+    s.passes += 1;
+    s.cold_passes += 1;
+    s.window_misses += miss;
+    s.ff_pending = 0;
+    s.need_sample = 0;
+    s.use_list = (*p.list_ok != 0 && !s.force_scan) ? 1 : 0;
+    s.mode = (unresolved == 0) ? MODE_BID : MODE_HIST;
+    *p.st = s;
+}
+
+// One warp: worker w's threshold from the histogram in m.hist (see resolve_one_worker).
+__device__ __forceinline__ void resolve_worker_from_smem(const AuctionPtrs& p, int w, const MergeSmem& m, unsigned long long abt,
+                                                         unsigned long long gpt, long long jpw, int passes, int* flags) {
+    const int lane = threadIdx.x & 31;
+    const int base = p.win_base[w], shift = p.win_shift[w];
+    const int hbase = p.win_hbase[w], nlo = (shift == 0) ? p.win_nlo[w] : 0;
+    const unsigned long long gap = (shift == 0) ? gpt : 0ull;
+    unsigned int h[AUC_BPL];
+    unsigned int lsum = 0;
+#pragma unroll
+    for (int i = 0; i < AUC_BPL; ++i) { h[i] = m.hist[lane * AUC_BPL + i]; lsum += h[i]; }
+    resolve_one_worker(p, w, h, lsum, abt, gap, base, shift, hbase, nlo, jpw + 1, jpw, passes, p.st->sink, &flags[0], &flags[1]);
+}
+
 // Single-GPU driver, after a HIST pass that only dumped per CTA: CTA w sums worker w's window histogram over the G
-// dumps (16-bit pairs -> 32-bit bins), resolves the worker's threshold (resolve_one_worker - what the last CTA of the
-// HIST kernel used to do for all K workers one after the other), takes the tie prefix if the worker was resolved, and
-// the CTA that finishes last makes the state transition of the resolve step (part 4 of auction_resolve_body).
-// Workers settled by an earlier pass of the round keep what that pass left (threshold, dump, tie prefix).
+// dumps, resolves the worker's threshold (what the last CTA of the HIST kernel used to do for all K workers one after
+// the other), takes the tie prefix if the worker was resolved, and the CTA that finishes last makes the state
+// transition of the resolve step.  Workers settled by an earlier pass of the round keep what that pass left
+// (threshold, dump, tie prefix).
 __global__ void __launch_bounds__(AUC_MAX_CTAS, 1)
 auction_merge_resolve_kernel(AuctionPtrs p, int K, int G, long long jpw) {
     pdl_launch_dependents();
     pdl_wait();
-    __shared__ unsigned int part[8][AUC_W];
-    __shared__ unsigned int hist_s[AUC_W];
-    __shared__ unsigned int cnt[AUC_MAX_CTAS];
-    __shared__ unsigned int s_ab[AUC_MAX_CTAS / 32], s_gp[AUC_MAX_CTAS / 32];
+    __shared__ MergeSmem m;
     __shared__ int s_flag[2], s_mode, s_passes;
-    const int w = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int w = blockIdx.x, tid = threadIdx.x, warp = tid >> 5;
     if (tid == 0) { s_mode = p.st->mode; s_passes = p.st->passes; s_flag[0] = 0; s_flag[1] = 0; }
     __syncthreads();
     if (s_mode != MODE_HIST) return;                         // no HIST pass has just run (done, or a no-op round)
     const bool settled = p.tkey[w] >= 0;
     if (!settled) {
-        // ---- 1. merge ----
-        const unsigned int* d32 = reinterpret_cast<const unsigned int*>(p.hist_cta);
-        const int word = tid & 127, grp = tid >> 7;          // 8 groups of 128 threads, group q takes CTAs q, q+8, ..
-        unsigned int lo = 0, hi = 0;
-        for (int g = grp; g < G; g += 8) {
-            const unsigned int h = __ldcg(d32 + ((size_t)g * K + w) * (AUC_W / 2) + word);
-            lo += h & 0xffffu;
-            hi += h >> 16;
+        unsigned int abt, gpt;
+        merge_worker_dumps(p, K, G, w, m, &abt, &gpt);
+        if (warp == 0) resolve_worker_from_smem(p, w, m, abt, gpt, jpw, s_passes, s_flag);
+        __syncthreads();
+        if (p.tkey[w] >= 0) tie_prefix_worker(p, K, G, w, m, p.rank_off[w]);
+        if (tid == 0) {
+            if (s_flag[0]) atomicAdd(&p.unres_g[0], 1);
+            if (s_flag[1]) atomicAdd(&p.unres_g[1], 1);
         }
-        part[grp][2 * word] = lo;
-        part[grp][2 * word + 1] = hi;
-        unsigned int ab = 0, gp = 0;
-        if (tid < G) { ab = __ldcg(p.above_cta + (size_t)tid * K + w); gp = __ldcg(p.gap_cta + (size_t)tid * K + w); }
-        ab = __reduce_add_sync(0xffffffffu, ab);
-        gp = __reduce_add_sync(0xffffffffu, gp);
-        if (lane == 0) { s_ab[warp] = ab; s_gp[warp] = gp; }
+    }
+    if (auction_last_cta(p.ticket) && tid == 0) merge_state_transition(p);
+}
+
+// Sharded jobs, whole-round protocol, after a HIST pass that only dumped per CTA.  Two kernels of K CTAs:
+//  publish   CTA w sums worker w's dumps and writes the LOCAL histogram row (+ above / gap) into this rank's exchange
+//            block with plain stores; the CTA that finishes last signals every peer (flag kind 1).  Never waits.
+//  resolve   CTA w waits for the peers' signals, sums worker w's row over the ranks (all peers' loads in flight
+//            together: one NVLink round trip of 1 KB per peer), resolves the threshold - every rank computes the same -
+//            and takes the tie prefix over its own CTAs, offset by the ties lower ranks hold at the resolved bin (their
+//            local rows are in shared memory already).  Last CTA: state transition.
+// Rows of settled workers are neither written nor read; rows are rewritten in full every pass, so nothing is cleared.
+__global__ void __launch_bounds__(AUC_MAX_CTAS, 1)
+auction_peer_publish_kernel(AuctionPtrs p, int K, int G, PeerCtx peers, int seq) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ MergeSmem m;
+    __shared__ int s_mode;
+    const int w = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) s_mode = p.st->mode;
+    __syncthreads();
+    if (s_mode != MODE_HIST) return;
+    if (p.tkey[w] < 0) {
+        unsigned int abt, gpt;
+        merge_worker_dumps(p, K, G, w, m, &abt, &gpt);
+        unsigned int* mine = peer_hist(peers, peers.rank, K, seq & 1);
+        if (tid < AUC_W) mine[(size_t)w * AUC_W + tid] = m.hist[tid];
+        if (tid == 0) { mine[(size_t)K * AUC_W + w] = abt; mine[(size_t)K * AUC_W + K + w] = gpt; }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        const int t = atomicAdd(&p.unres_g[2], 1);
+        s_mode = (t == (int)gridDim.x - 1) ? 1 : 0;
+        if (s_mode) p.unres_g[2] = 0;
+    }
+    __syncthreads();
+    if (s_mode && tid < peers.world && tid != peers.rank) {     // every local row is in place: tell the peers
+        __threadfence_system();
+        int* dst = peer_flags(peers, tid) + 1 * PEER_MAX + peers.rank;
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(dst), "r"(seq) : "memory");
+    }
+}
+
+__global__ void __launch_bounds__(AUC_MAX_CTAS, 1)
+auction_peer_resolve_workers_kernel(AuctionPtrs p, int K, int G, long long jpw, PeerCtx peers, int seq) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ MergeSmem m;
+    __shared__ unsigned int s_rows[PEER_MAX][AUC_W];          // the ranks' local rows of worker w
+    __shared__ unsigned int s_abgp[2][PEER_MAX];
+    __shared__ int s_flag[2], s_mode, s_passes;
+    const int w = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, par = seq & 1;
+    if (tid == 0) { s_mode = p.st->mode; s_passes = p.st->passes; s_flag[0] = 0; s_flag[1] = 0; }
+    __syncthreads();
+    if (s_mode != MODE_HIST) return;
+    const bool settled = p.tkey[w] >= 0;
+    if (!settled) {
+        if (!peer_barrier(peers, 1, seq, false)) {              // wait only: auction_peer_publish_kernel has signalled
+            if (tid == 0) { p.st->error = 1; p.st->mode = MODE_DONE; p.st->done = 1; }
+            return;
+        }
+        // the ranks' rows: thread (r, i) loads bin i of rank r - 8 x 256 loads, all in flight together
+        for (int i = tid; i < PEER_MAX * AUC_W; i += AUC_MAX_CTAS) {
+            const int r = i / AUC_W, b = i % AUC_W;
+            unsigned int v = 0;
+            if (r < peers.world) {
+                const unsigned int* src = peer_hist(peers, r, K, par) + (size_t)w * AUC_W + b;
+                v = (r == peers.rank) ? __ldcg(src) : __ldcv(src);
+            }
+            s_rows[r][b] = v;
+        }
+        if (tid < 2 * PEER_MAX) {
+            const int r = tid % PEER_MAX, which = tid / PEER_MAX;
+            unsigned int v = 0;
+            if (r < peers.world) {
+                const unsigned int* src = peer_hist(peers, r, K, par) + (size_t)K * AUC_W + (size_t)which * K + w;
+                v = (r == peers.rank) ? __ldcg(src) : __ldcv(src);
+            }
+            s_abgp[which][r] = v;
+        }
         __syncthreads();
         if (tid < AUC_W) {
             unsigned int t = 0;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) t += part[q][tid];
-            hist_s[tid] = t;
+            for (int r = 0; r < PEER_MAX; ++r) t += s_rows[r][tid];
+            m.hist[tid] = t;
         }
         __syncthreads();
-        // ---- 2. resolve (one warp) ----
         if (warp == 0) {
             unsigned long long abt = 0, gpt = 0;
-            for (int q = 0; q < AUC_MAX_CTAS / 32; ++q) { abt += s_ab[q]; gpt += s_gp[q]; }
-            const int base = p.win_base[w], shift = p.win_shift[w];
-            const int hbase = p.win_hbase[w], nlo = (shift == 0) ? p.win_nlo[w] : 0;
-            const unsigned long long gap = (shift == 0) ? gpt : 0ull;
-            unsigned int h[AUC_BPL];
-            unsigned int lsum = 0;
 #pragma unroll
-            for (int i = 0; i < AUC_BPL; ++i) { h[i] = hist_s[lane * AUC_BPL + i]; lsum += h[i]; }
-            resolve_one_worker(p, w, h, lsum, abt, gap, base, shift, hbase, nlo, jpw + 1, jpw, s_passes, p.st->sink,
-                               &s_flag[0], &s_flag[1]);
+            for (int r = 0; r < PEER_MAX; ++r) { abt += s_abgp[0][r]; gpt += s_abgp[1][r]; }
+            resolve_worker_from_smem(p, w, m, abt, gpt, jpw, s_passes, s_flag);
         }
         __syncthreads();
-        // ---- 3. tie prefix over the CTAs, if this pass resolved the worker (as auction_tieprefix_kernel) ----
         const int tk = p.tkey[w];
         if (tk >= 0) {
             const int base = p.win_base[w], hbase = p.win_hbase[w], nlo = p.win_nlo[w];
-            const int bin = tk >= hbase ? nlo + tk - hbase : tk - base;   // shift is 0 when resolved
-            unsigned int c = 0;
-            if (tid < G) c = p.hist_cta[((size_t)tid * K + w) * AUC_W + bin];
-            cnt[tid] = c;
-            __syncthreads();
-            for (int d = 1; d < AUC_MAX_CTAS; d <<= 1) {
-                unsigned int v = (tid >= d) ? cnt[tid - d] : 0;
-                __syncthreads();
-                cnt[tid] += v;
-                __syncthreads();
-            }
-            if (tid < G) p.tieprefix[(size_t)tid * K + w] = cnt[tid] - c + p.rank_off[w];
-            if (tid == AUC_MAX_CTAS - 1) p.tie_total[w] = cnt[AUC_MAX_CTAS - 1];
+            const int bin = tk >= hbase ? nlo + tk - hbase : tk - base;
+            unsigned int off = 0;
+            for (int r = 0; r < peers.rank; ++r) off += s_rows[r][bin];   // rank-major: lower ranks' ties come first
+            if (tid == 0) p.rank_off[w] = off;
+            tie_prefix_worker(p, K, G, w, m, off);
         }
         if (tid == 0) {
             if (s_flag[0]) atomicAdd(&p.unres_g[0], 1);
             if (s_flag[1]) atomicAdd(&p.unres_g[1], 1);
         }
     }
-    // ---- 4. the CTA that finishes last: state transition of a resolved HIST pass ----
-    if (auction_last_cta(p.ticket) && tid == 0) {
-        AuctionState s = *p.st;
-        const int unresolved = __ldcg(&p.unres_g[0]), miss = __ldcg(&p.unres_g[1]);
-        p.unres_g[0] = 0;
-        p.unres_g[1] = 0;
-        s.passes += 1;
-        s.cold_passes += 1;
-        s.window_misses += miss;
-        s.ff_pending = 0;
-        s.need_sample = 0;
-        s.use_list = (*p.list_ok != 0 && !s.force_scan) ? 1 : 0;
-        s.mode = (unresolved == 0) ? MODE_BID : MODE_HIST;
-        *p.st = s;
-    }
+    if (auction_last_cta(p.ticket) && tid == 0) merge_state_transition(p);
 }
 
 // sharded jobs: ranks are ordered, so a rank's CTAs come after all ties of lower ranks
@@ -2508,7 +2644,20 @@ int rqk_auction_peer_round(const void* scores_t, int64_t ld, int64_t n, int32_t 
                                     (long long)n_global, (int)k, (long long)(n_global / k), a.p, (unsigned short*)nullptr, 0,
                                     (const unsigned short*)nullptr, (int)(count * world), (int)count, c, (int)((seq0 + 1) & 1),
                                     (int)(seq0 + 1)));
-    // the HIST kernel merges this rank's histograms straight into its exchange block (parity of seq0 + 2)
+    // HIST dumps per CTA (as in the single-GPU driver); the per-worker publish / resolve kernels exchange the rows
+    static const bool old_xch = [] { const char* e = getenv("RQK_PEER_XCH16"); return e && e[0] == '1'; }();
+    if (!old_xch) {
+        if ((rc = auction_launch(a, scores_t, ld, n, k, n_global, 2, 1, stream, true))) return rc;
+        RQK_CUDA_OK(launch_round_kernel(auction_peer_publish_kernel, (unsigned)k, (unsigned)AUC_MAX_CTAS, 0, stream, pdl, a.p, (int)k,
+                                        a.G, c, (int)(seq0 + 2)));
+        RQK_CUDA_OK(launch_round_kernel(auction_peer_resolve_workers_kernel, (unsigned)k, (unsigned)AUC_MAX_CTAS, 0, stream, pdl, a.p,
+                                        (int)k, a.G, (long long)(n_global / k), c, (int)(seq0 + 2)));
+        if ((rc = auction_launch(a, scores_t, ld, n, k, n_global, 4, 0, stream, true))) return rc;
+        RQK_LAUNCH_OK();
+        return 0;
+    }
+    // RQK_PEER_XCH16=1 (timing comparisons): the HIST kernel merges this rank's histograms with atomics straight into
+    // its exchange block (parity of seq0 + 2), a 16-CTA kernel sums slices over the ranks and its last CTA resolves
     AuctionArgs ah = a;
     ah.p.hist_g = reinterpret_cast<unsigned int*>(c.buf[rank] + PEER_FLAGS_BYTES + PEER_TAIL_BYTES) +
                   (size_t)((seq0 + 2) & 1) * peer_rb_words(k);

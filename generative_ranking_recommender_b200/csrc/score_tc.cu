@@ -35,11 +35,19 @@ struct ScoreTcParams {
     int tmem_cols;           // columns per accumulator stage (power of two >= 32, >= KC)
     int stages;
     int raw;                 // depth of the raw X ring
+    int tmem_alloc;          // TMEM columns allocated (power of two)
+    int a_col0;              // ATMEM kernel: first TMEM column of the A-operand stages (64 columns each: hi | lo)
     const float* c2;         // [K] |c|^2
     ScoreOut o;
     int debug;               // timing attribution only (RQK_SCORE_DEBUG): 1 = skip epilogue math, 2 = hi.hi MMA only, 4 = no transform
 };
 
+// ATMEM (K <= 128, where two accumulators leave TMEM columns free): the transform warps write the hi / lo split of an
+// X block straight into TENSOR MEMORY (tcgen05.st, thread = row = TMEM lane) and the MMAs take their A operand from
+// there (tcgen05.mma [d], [a_tmem], b_desc).  The A operand then costs no shared-memory bandwidth at all - neither the
+// 32 KB written per k-block nor the 48 KB the three MMAs read back - which is what bounds the smem-operand kernel at
+// K = 128; the operand stages in shared memory hold the centroid blocks only.
+template <bool ATMEM>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_chi,
                 const __grid_constant__ CUtensorMap map_clo, const ScoreTcParams P) {
@@ -54,7 +62,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     // ---- smem carve-up: per stage {A hi 16K, A lo 16K, B hi KC*128, B lo KC*128}, all 1024-aligned ----
     const uint32_t a_bytes = TC_BM * TC_BK * 4;           // 16384
     const uint32_t b_bytes = (uint32_t)KC * TC_BK * 4;    // KC*128, multiple of 2048
-    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    const uint32_t b_off = ATMEM ? 0u : 2 * a_bytes;     // centroid blocks inside an operand stage
+    const uint32_t stage_bytes = b_off + 2 * b_bytes;
     // raw X ring: the X stream from HBM runs up to `nraw` k-blocks ahead of the operand stages, so that the HBM
     // latency is covered by bytes in flight instead of by stage occupancy (a stage is held from its centroid
     // load until its MMAs retire)
@@ -98,7 +107,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         fence_barrier_init();
     }
     if (warp == TC_MMA_WARP) {
-        uint32_t ncols = 2u * (uint32_t)P.tmem_cols;
+        uint32_t ncols = (uint32_t)P.tmem_alloc;
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(ncols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -130,8 +139,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     unsigned char* st = smem + (size_t)s * stage_bytes;
                     mbar_expect_tx(&full_bar[s], 2 * b_bytes);
-                    tma_load_2d(st + 2 * a_bytes, &map_chi, &full_bar[s], kb * TC_BK, 0);
-                    tma_load_2d(st + 2 * a_bytes + b_bytes, &map_clo, &full_bar[s], kb * TC_BK, 0);
+                    tma_load_2d(st + b_off, &map_chi, &full_bar[s], kb * TC_BK, 0);
+                    tma_load_2d(st + b_off + b_bytes, &map_clo, &full_bar[s], kb * TC_BK, 0);
                     if (++s == stages) { s = 0; ph ^= 1; }
                 }
             }
@@ -153,12 +162,17 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
                     const uint64_t a_hi = make_sw128_desc(st);
                     const uint64_t a_lo = make_sw128_desc(st + a_bytes);
-                    const uint64_t b_hi = make_sw128_desc(st + 2 * a_bytes);
-                    const uint64_t b_lo = make_sw128_desc(st + 2 * a_bytes + b_bytes);
+                    const uint64_t b_hi = make_sw128_desc(st + b_off);
+                    const uint64_t b_lo = make_sw128_desc(st + b_off + b_bytes);
+                    const uint32_t at_hi = tmem_base + (uint32_t)(P.a_col0 + s * 2 * TC_BK);   // ATMEM: A stage in TMEM
 #pragma unroll
                     for (int k = 0; k < TC_BK / 8; ++k) {
                         const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);   // +32 B along K inside the swizzle row
-                        if (!(P.debug & 2)) {
+                        if (ATMEM) {                                         // 8 tf32 = 8 TMEM columns per k-step
+                            umma_tf32_ts(d_tmem, at_hi + TC_BK + k * 8, b_hi + adv, idesc, (kb | k) != 0);
+                            umma_tf32_ts(d_tmem, at_hi + k * 8, b_lo + adv, idesc, 1);
+                            umma_tf32_ts(d_tmem, at_hi + k * 8, b_hi + adv, idesc, 1);
+                        } else if (!(P.debug & 2)) {
                             umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
                             umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
                             umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
@@ -194,6 +208,32 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 }
                 unsigned char* st = smem + (size_t)s * stage_bytes;
                 const float4* raw = reinterpret_cast<const float4*>(raw0 + (size_t)rs * a_bytes + (size_t)r * 128);
+                if (ATMEM) {
+                    // the row's 32 floats in LOGICAL order (chunk c sits at physical chunk c ^ (row & 7)), split, and stored
+                    // to this thread's TMEM lane: columns [0,32) of the stage = hi, [32,64) = lo
+                    uint32_t hv[TC_BK], lv[TC_BK];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 v = raw[c ^ (lane & 7)];
+                        nrm = fmaf(v.x, v.x, nrm); nrm = fmaf(v.y, v.y, nrm);
+                        nrm = fmaf(v.z, v.z, nrm); nrm = fmaf(v.w, v.w, nrm);
+                        const float hx = to_tf32_rna(v.x), hy = to_tf32_rna(v.y), hz = to_tf32_rna(v.z), hw = to_tf32_rna(v.w);
+                        hv[4 * c + 0] = __float_as_uint(hx); hv[4 * c + 1] = __float_as_uint(hy);
+                        hv[4 * c + 2] = __float_as_uint(hz); hv[4 * c + 3] = __float_as_uint(hw);
+                        lv[4 * c + 0] = __float_as_uint(to_tf32_rna(v.x - hx)); lv[4 * c + 1] = __float_as_uint(to_tf32_rna(v.y - hy));
+                        lv[4 * c + 2] = __float_as_uint(to_tf32_rna(v.z - hz)); lv[4 * c + 3] = __float_as_uint(to_tf32_rna(v.w - hw));
+                    }
+                    const uint32_t ta = tmem_base + ((uint32_t)((warp - TC_XF_WARP0) * 32) << 16) + (uint32_t)(P.a_col0 + s * 2 * TC_BK);
+                    tmem_st32(ta, hv);
+                    tmem_st32(ta + TC_BK, lv);
+                    tmem_st_wait();
+                    tc_fence_before();                           // tcgen05.st -> visible to the MMAs issued after the barrier
+                    mbar_arrive(&xf_bar[s]);
+                    mbar_arrive(&raw_empty[rs]);
+                    if (++s == stages) { s = 0; ph ^= 1; }
+                    if (++rs == nraw) { rs = 0; rph ^= 1; }
+                    continue;
+                }
                 float4* hi = reinterpret_cast<float4*>(st + (size_t)r * 128);
                 float4* lo = reinterpret_cast<float4*>(st + a_bytes + (size_t)r * 128);
 #pragma unroll
@@ -261,6 +301,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                             if (d2 < b1) { b2 = b1; b1 = d2; bi = k; }
                             else if (d2 < b2) b2 = d2;
                             mx = fmaxf(mx, d2);
+                            // one 2-byte store per entry, 64 contiguous bytes per warp.  (Staging the tile through shared
+                            // memory for 16-byte stores was measured on B200: slower, 0.86 vs 0.82 ms at K = 128 and 1.70 vs
+                            // 1.43 ms at K = 256 per 1 M rows - the barriers and the lost raw-ring slot cost more.)
                             if (sp) sp[(long long)k * ld] = __float2half_rn(-sqrtf(d2));
                         }
                     }
@@ -331,7 +374,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         for (int i = threadIdx.x; i < P.K; i += TC_THREADS)
             if (cnt_s[i]) atomicAdd(&P.o.counts[i], cnt_s[i]);
     if (warp == TC_MMA_WARP) {
-        uint32_t ncols = 2u * (uint32_t)P.tmem_cols;
+        uint32_t ncols = (uint32_t)P.tmem_alloc;
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
     }
 }
@@ -403,21 +446,38 @@ int score_pass_tc(const float* x, long long n, int dim, const float* c, int K, f
         const char* dbg = getenv("RQK_SCORE_DEBUG");
         P.debug = dbg ? atoi(dbg) : 0;
     }
-    const size_t stage_bytes = 2 * (size_t)TC_BM * TC_BK * 4 + 2 * (size_t)KC * TC_BK * 4;
+    // K <= 128: two accumulators leave at least 256 TMEM columns, enough for four 64-column A-operand stages
+    static const bool no_atmem = [] { const char* e = getenv("RQK_SCORE_A_SMEM"); return e && e[0] == '1'; }();
+    const bool atmem = !no_atmem && 2 * tcols + 4 * 2 * TC_BK <= 512;
+    const size_t stage_bytes = (atmem ? 0 : 2 * (size_t)TC_BM * TC_BK * 4) + 2 * (size_t)KC * TC_BK * 4;
     const size_t tail = 8 * 8 * 3 + 2 * 8 * 3 + 2 * 8 * TC_MAX_RAW + 16 + 2 * TC_BM * 4 + 256 * 4 + 256 * 4 + 64;
     const size_t raw_bytes = (size_t)TC_BM * TC_BK * 4;
     const long long room = 225 * 1024 - (long long)tail - 1024;
     // two operand stages (A hi/lo + centroid hi/lo blocks); the rest of shared memory is the raw X ring
     int stages = 2;
-    if (room < (long long)(stages * stage_bytes + raw_bytes))
-        return fail(RQK_ERR_UNSUPPORTED, "score_pass_tc: K=%s%lld does not fit two pipeline stages", "", K);
-    int raw = (int)((room - (long long)(stages * stage_bytes)) / (long long)raw_bytes);
-    if (raw > TC_MAX_RAW) {                      // small K: spend the surplus on a third operand stage
-        if (room >= (long long)(3 * stage_bytes + 4 * raw_bytes)) {
-            stages = 3;
-            raw = (int)((room - (long long)(stages * stage_bytes)) / (long long)raw_bytes);
-        }
+    int raw;
+    if (atmem) {
+        stages = 4;                                  // centroid blocks in smem + A blocks in TMEM, stage for stage
+        raw = (int)((room - (long long)(stages * stage_bytes)) / (long long)raw_bytes);
         if (raw > TC_MAX_RAW) raw = TC_MAX_RAW;
+        if (raw < 2) return fail(RQK_ERR_INTERNAL, "score_pass_tc: no room for the raw ring%s");
+        P.a_col0 = 2 * tcols;
+        int need = 2 * tcols + stages * 2 * TC_BK, alloc = 32;
+        while (alloc < need) alloc <<= 1;
+        P.tmem_alloc = alloc;
+    } else {
+        if (room < (long long)(stages * stage_bytes + raw_bytes))
+            return fail(RQK_ERR_UNSUPPORTED, "score_pass_tc: K=%s%lld does not fit two pipeline stages", "", K);
+        raw = (int)((room - (long long)(stages * stage_bytes)) / (long long)raw_bytes);
+        if (raw > TC_MAX_RAW) {                      // small K: spend the surplus on a third operand stage
+            if (room >= (long long)(3 * stage_bytes + 4 * raw_bytes)) {
+                stages = 3;
+                raw = (int)((room - (long long)(stages * stage_bytes)) / (long long)raw_bytes);
+            }
+            if (raw > TC_MAX_RAW) raw = TC_MAX_RAW;
+        }
+        P.a_col0 = 0;
+        P.tmem_alloc = 2 * tcols;
     }
     P.stages = stages;
     P.raw = raw;
@@ -430,10 +490,11 @@ int score_pass_tc(const float* x, long long n, int dim, const float* c, int K, f
     if ((rc = make_map_2d(&mx, x, n, dim, TC_BM, CU_TENSOR_MAP_L2_PROMOTION_L2_128B))) return rc;
     if ((rc = make_map_2d(&mhi, chi, K, dim, KC, CU_TENSOR_MAP_L2_PROMOTION_L2_256B))) return rc;
     if ((rc = make_map_2d(&mlo, clo, K, dim, KC, CU_TENSOR_MAP_L2_PROMOTION_L2_256B))) return rc;
-    RQK_CUDA_OK(cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = atmem ? score_tc_kernel<true> : score_tc_kernel<false>;
+    RQK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long ntiles = ceil_div<long long>(n, TC_BM);
     int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
-    score_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(mx, mhi, mlo, P);
+    kern<<<grid, TC_THREADS, smem, stream>>>(mx, mhi, mlo, P);
     RQK_LAUNCH_OK();
     return 0;
 }
