@@ -91,7 +91,9 @@ struct AuctionState {
     int force_scan;     // debugging / tests: never use the lists
     int list_passes;    // BID passes served from the lists
     int sink[4];        // statistics: worker-rounds whose threshold sank by < 64, < 128, < 250, >= 250 keys
-    int pad_[8];
+    int branch[4];      // statistics (directly after sink[]): worker-passes that ended in a refine inside a coarse bin /
+                        // in the gap of a split window / in a slide after a miss / in a coarse restart
+    int pad_[4];
 };
 
 struct AuctionPtrs {
@@ -409,6 +411,7 @@ __device__ __forceinline__ void resolve_one_worker(const AuctionPtrs& p, int w, 
                 p.take[w] = (int)(jpw - (long long)g_above);
                 p.res_pass[w] = passes;
             } else {   // refine inside the bin that holds the threshold
+                atomicAdd(&sink[4], 1);
                 int nshift = shift >= 8 ? shift - 8 : 0;
                 const int nb2 = base + (found_bin << shift);
                 p.win_base[w] = nb2;
@@ -421,6 +424,7 @@ __device__ __forceinline__ void resolve_one_worker(const AuctionPtrs& p, int w, 
         }
     } else if (lane == 0 && in_gap) {
         // the threshold lies between the two halves of a split window: histogram just that range
+        atomicAdd(&sink[5], 1);
         int nb2 = base + nlo, span = hbase - nb2, nshift = 0;
         while ((span >> nshift) > AUC_W) ++nshift;
         p.win_base[w] = nb2;
@@ -436,6 +440,7 @@ __device__ __forceinline__ void resolve_one_worker(const AuctionPtrs& p, int w, 
         const int run = p.miss_run[w];
         const bool is_above = ab >= (unsigned long long)need;
         int nb = is_above ? (shift == 0 ? hbase + (AUC_W - nlo) : base + (AUC_W << shift)) : base - (AUC_W << shift);
+        atomicAdd(&sink[(shift != 0 || run >= 2 || nb < AUC_MIN_KEY || nb > 65536 - AUC_W) ? 7 : 6], 1);
         if (shift != 0 || run >= 2 || nb < AUC_MIN_KEY || nb > 65536 - AUC_W) {
             p.win_base[w] = 0;
             p.win_hbase[w] = AUC_HALF;
@@ -2138,17 +2143,12 @@ __device__ __forceinline__ void merge_worker_dumps(const AuctionPtrs& p, int K, 
     __syncthreads();
 }
 
-// Exclusive prefix over this rank's CTAs of the number of values equal to worker w's resolved threshold (bin of the
-// per-CTA dumps), offset by the ties lower ranks hold.  All threads of the CTA; contains __syncthreads.
-__device__ __forceinline__ void tie_prefix_worker(const AuctionPtrs& p, int K, int G, int w, MergeSmem& m, unsigned int rank_off) {
+// m.cnt[b] = number of values equal to worker w's threshold in CTA b's job range (0 for b >= G): exclusive prefix over
+// the CTAs, offset by the ties lower ranks hold, -> tieprefix / tie_total.  All threads of the CTA; contains __syncthreads.
+__device__ __forceinline__ void tie_scan_store(const AuctionPtrs& p, int K, int G, int w, MergeSmem& m, unsigned int rank_off) {
     const int tid = threadIdx.x;
-    const int tk = p.tkey[w];
-    const int base = p.win_base[w], hbase = p.win_hbase[w], nlo = p.win_nlo[w];
-    const int bin = tk >= hbase ? nlo + tk - hbase : tk - base;   // shift is 0 when resolved
-    unsigned int c = 0;
-    if (tid < G) c = p.hist_cta[((size_t)tid * K + w) * AUC_W + bin];
-    m.cnt[tid] = c;
     __syncthreads();
+    const unsigned int c = m.cnt[tid];
     for (int d = 1; d < AUC_MAX_CTAS; d <<= 1) {                  // Hillis-Steele inclusive scan
         unsigned int v = (tid >= d) ? m.cnt[tid - d] : 0;
         __syncthreads();
@@ -2157,6 +2157,81 @@ __device__ __forceinline__ void tie_prefix_worker(const AuctionPtrs& p, int K, i
     }
     if (tid < G) p.tieprefix[(size_t)tid * K + w] = m.cnt[tid] - c + rank_off;
     if (tid == AUC_MAX_CTAS - 1) p.tie_total[w] = m.cnt[AUC_MAX_CTAS - 1];
+}
+
+// The per-CTA tie counts from the per-CTA dumps of the HIST pass (bin of the resolved threshold).
+__device__ __forceinline__ void tie_prefix_worker(const AuctionPtrs& p, int K, int G, int w, MergeSmem& m, unsigned int rank_off) {
+    const int tid = threadIdx.x;
+    const int tk = p.tkey[w];
+    const int base = p.win_base[w], hbase = p.win_hbase[w], nlo = p.win_nlo[w];
+    const int bin = tk >= hbase ? nlo + tk - hbase : tk - base;   // shift is 0 when resolved
+    unsigned int c = 0;
+    if (tid < G) c = p.hist_cta[((size_t)tid * K + w) * AUC_W + bin];
+    m.cnt[tid] = c;
+    tie_scan_store(p, K, G, w, m, rank_off);
+}
+
+// Refine from the survivor lists.  The worker's window had coarse bins (2^shift0 keys each, from `base0`) and the
+// resolve step has just found the bin that holds the threshold and aimed a one-key window [nb2, nb2 + 2^shift0) at it
+// for another HIST pass over the worker's row.  But the pass that has just run already pushed EVERY value >= base0 of
+// this worker into its survivor lists (job, exact key), so the one-key histogram of that bin - and the per-CTA tie
+// counts at the threshold - can be taken from the lists (L2-resident, ~2 % of the row) right here, and the extra pass
+// over S never happens.  Returns false (nothing changed: the next HIST pass refines as before) if a list overflowed.
+// All threads of the CTA; m.part is reused as scratch.
+__device__ __forceinline__ bool refine_from_lists(const AuctionPtrs& p, int K, int G, int spc, int w, MergeSmem& m,
+                                                  unsigned long long above_bin, int nb2, int range, long long jpw, int passes) {
+    __shared__ int s_over, s_T;
+    __shared__ unsigned int s_above_T;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned int* fh = &m.part[0][0];                          // [range <= 8 * 256] one-key histogram of [nb2, nb2 + range)
+    const int nseg = G * spc;
+    for (int i = tid; i < range; i += AUC_MAX_CTAS) fh[i] = 0;
+    if (tid == 0) { s_over = 0; s_T = -1; }
+    m.cnt[tid] = 0;
+    __syncthreads();
+    for (int seg = warp; seg < nseg; seg += AUC_MAX_CTAS / 32) {
+        const unsigned int cnt = __ldcg(p.seg_cnt + (size_t)seg * K + w);
+        if (cnt > AUC_SEG_CAP) { if (lane == 0) s_over = 1; continue; }
+        const unsigned int* L = p.seg_list + ((size_t)seg * K + w) * AUC_SEG_CAP;
+        for (unsigned int i = lane; i < cnt; i += 32) {
+            const int key = (int)(__ldcg(L + i) & 0xffffu);
+            if (key >= nb2 && key < nb2 + range) atomicAdd(&fh[key - nb2], 1u);
+        }
+    }
+    __syncthreads();
+    if (s_over) return false;
+    if (tid == 0) {
+        const unsigned long long need = (unsigned long long)(jpw + 1);
+        unsigned long long c = above_bin;
+        for (int k = range - 1; k >= 0; --k) {
+            if (c < need && c + fh[k] >= need) { s_T = nb2 + k; s_above_T = (unsigned int)c; break; }
+            c += fh[k];
+        }
+    }
+    __syncthreads();
+    const int T = s_T;
+    if (T < 0) return false;                                   // cannot happen with complete lists
+    for (int seg = warp; seg < nseg; seg += AUC_MAX_CTAS / 32) {
+        const unsigned int cnt = __ldcg(p.seg_cnt + (size_t)seg * K + w);
+        const unsigned int* L = p.seg_list + ((size_t)seg * K + w) * AUC_SEG_CAP;
+        unsigned int n = 0;
+        for (unsigned int i = lane; i < cnt; i += 32) n += ((int)(__ldcg(L + i) & 0xffffu) == T) ? 1u : 0u;
+        n = __reduce_add_sync(0xffffffffu, n);
+        if (lane == 0 && n) atomicAdd(&m.cnt[seg / spc], n);
+    }
+    if (tid == 0) {
+        const int tp = p.tprev[w];
+        if (tp >= 0) {
+            const int d = tp - T;
+            atomicAdd(&p.st->sink[d < 64 ? 0 : d < 128 ? 1 : d < 250 ? 2 : 3], 1);
+        }
+        p.tkey[w] = T;
+        p.take[w] = (int)(jpw - (long long)s_above_T);
+        p.res_pass[w] = passes;
+        p.miss_run[w] = 0;
+    }
+    tie_scan_store(p, K, G, w, m, p.rank_off[w]);
+    return true;
 }
 
 // State transition after a HIST pass whose workers were resolved one per CTA (part 4 of auction_resolve_body); run
@@ -2196,22 +2271,50 @@ __device__ __forceinline__ void resolve_worker_from_smem(const AuctionPtrs& p, i
 // transition of the resolve step.  Workers settled by an earlier pass of the round keep what that pass left
 // (threshold, dump, tie prefix).
 __global__ void __launch_bounds__(AUC_MAX_CTAS, 1)
-auction_merge_resolve_kernel(AuctionPtrs p, int K, int G, long long jpw) {
+auction_merge_resolve_kernel(AuctionPtrs p, int K, int G, long long jpw, int spc, int list_refine) {
     pdl_launch_dependents();
     pdl_wait();
     __shared__ MergeSmem m;
-    __shared__ int s_flag[2], s_mode, s_passes;
+    __shared__ int s_flag[2], s_mode, s_passes, s_scan;
     const int w = blockIdx.x, tid = threadIdx.x, warp = tid >> 5;
-    if (tid == 0) { s_mode = p.st->mode; s_passes = p.st->passes; s_flag[0] = 0; s_flag[1] = 0; }
+    if (tid == 0) { s_mode = p.st->mode; s_passes = p.st->passes; s_scan = p.st->force_scan; s_flag[0] = 0; s_flag[1] = 0; }
     __syncthreads();
     if (s_mode != MODE_HIST) return;                         // no HIST pass has just run (done, or a no-op round)
+    if (s_scan) list_refine = 0;                             // the S-scanning route stays independent of the lists
     const bool settled = p.tkey[w] >= 0;
     if (!settled) {
         unsigned int abt, gpt;
         merge_worker_dumps(p, K, G, w, m, &abt, &gpt);
+        const int base0 = p.win_base[w], shift0 = p.win_shift[w];   // the window the pass ran with
+        const int hbase0 = p.win_hbase[w], nlo0 = p.win_nlo[w];
+        __syncthreads();
         if (warp == 0) resolve_worker_from_smem(p, w, m, abt, gpt, jpw, s_passes, s_flag);
         __syncthreads();
-        if (p.tkey[w] >= 0) tie_prefix_worker(p, K, G, w, m, p.rank_off[w]);
+        if (p.tkey[w] >= 0) {
+            tie_prefix_worker(p, K, G, w, m, p.rank_off[w]);
+        } else if (list_refine && base0 > 0 && shift0 >= 1 && shift0 <= 8 && p.win_shift[w] == 0 && p.win_base[w] >= base0) {
+            // resolved to a coarse bin of a sampled window: finish from the survivor lists instead of another pass
+            const int nb2 = p.win_base[w], bin = (nb2 - base0) >> shift0;
+            unsigned long long above_bin = abt;
+            for (int i = bin + 1; i < AUC_W; ++i) above_bin += m.hist[i];
+            __syncthreads();                                   // m.hist / m.part are about to be reused
+            if (refine_from_lists(p, K, G, spc, w, m, above_bin, nb2, 1 << shift0, jpw, s_passes) && tid == 0) {
+                s_flag[0] = 0;
+                atomicAdd(&p.st->branch[0], -1);               // statistics: this refine did not cost a pass
+            }
+        } else if (list_refine && base0 > 0 && shift0 == 0 && hbase0 > base0 + nlo0 && p.win_base[w] == base0 + nlo0 &&
+                   hbase0 - (base0 + nlo0) <= 8 * AUC_W) {
+            // the threshold fell into the gap of a split window (keys [base0 + nlo0, hbase0), up to 2048 of them):
+            // those values are in the survivor lists as well
+            unsigned long long above_gap = abt;
+            for (int i = nlo0; i < AUC_W; ++i) above_gap += m.hist[i];
+            __syncthreads();
+            if (refine_from_lists(p, K, G, spc, w, m, above_gap, base0 + nlo0, hbase0 - (base0 + nlo0), jpw, s_passes) && tid == 0) {
+                s_flag[0] = 0;
+                atomicAdd(&p.st->branch[1], -1);
+            }
+        }
+        __syncthreads();
         if (tid == 0) {
             if (s_flag[0]) atomicAdd(&p.unres_g[0], 1);
             if (s_flag[1]) atomicAdd(&p.unres_g[1], 1);
@@ -2393,6 +2496,12 @@ static cudaError_t launch_round_kernel(void (*kernel)(KArgs...), unsigned grid, 
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// RQK_AUCTION_NO_LIST_REFINE=1 (tests, timing): coarse windows are always refined by another HIST pass
+static bool auction_list_refine_ok() {
+    static const bool ok = [] { const char* e = getenv("RQK_AUCTION_NO_LIST_REFINE"); return !(e && e[0] == '1'); }();
+    return ok;
+}
+
 static bool auction_pdl_ok() {
     static const bool ok = [] { const char* e = getenv("RQK_NO_PDL"); return !(e && e[0] == '1'); }();
     return ok;
@@ -2434,7 +2543,7 @@ static int auction_launch(const AuctionArgs& a, const void* scores_t, int64_t ld
     if (which & 8) {
         if (fused)      // HIST only dumped: merge + resolve + tie prefix, one CTA per worker
             RQK_CUDA_OK(launch_round_kernel(auction_merge_resolve_kernel, (unsigned)k, (unsigned)AUC_MAX_CTAS, 0, stream, pdl,
-                                            a.p, (int)k, a.G, (long long)(n_global / k)));
+                                            a.p, (int)k, a.G, (long long)(n_global / k), spc, auction_list_refine_ok() ? 1 : 0));
         else
             RQK_CUDA_OK(launch_round_kernel(auction_tieprefix_kernel, (unsigned)k, (unsigned)AUC_MAX_CTAS, 0, stream, pdl, a.p, (int)k, a.G));
     }
@@ -2799,6 +2908,15 @@ int rqk_auction(const void* scores_t, int64_t ld, int64_t n, int32_t k, const vo
         st.window_misses = fin->window_misses; st.frozen_exit = fin->frozen_exit; st.counter = fin->counter;
         st.eps_bits = (uint16_t)fin->eps_bits;
         st.list_passes = (uint16_t)(fin->list_passes > 65535 ? 65535 : fin->list_passes);
+    }
+    if (fin) {
+        static const bool dbg = [] { const char* e = getenv("RQK_AUCTION_DEBUG"); return e && e[0] == '1'; }();
+        if (dbg)
+            fprintf(stderr, "rqk_auction n=%lld k=%d: rounds %d passes %d (HIST %d, from lists %d) window misses %d | worker-passes: "
+                    "refine in coarse bin %d, in gap %d, slide %d, coarse restart %d | sink <64 %d <128 %d <250 %d >=250 %d\n",
+                    (long long)n, (int)k, fin->rounds, fin->passes, fin->cold_passes, fin->list_passes, fin->window_misses,
+                    fin->branch[0], fin->branch[1], fin->branch[2], fin->branch[3], fin->sink[0], fin->sink[1], fin->sink[2],
+                    fin->sink[3]);
     }
     if (!st.done) return fail(RQK_ERR_INTERNAL, "rqk_auction: did not terminate%s");
     if ((rc = rqk_auction_finalize(n, ld, k, workspace, workspace_bytes, assign, stream_))) return rc;
