@@ -2117,7 +2117,8 @@ __device__ __forceinline__ void merge_worker_dumps(const AuctionPtrs& p, int K, 
     const unsigned int* d32 = reinterpret_cast<const unsigned int*>(p.hist_cta);
     const int word = tid & 127, grp = tid >> 7;              // 8 groups of 128 threads, group q takes CTAs q, q+8, ..
     unsigned int lo = 0, hi = 0;
-    for (int g = grp; g < G; g += 8) {
+#pragma unroll 8
+    for (int g = grp; g < G; g += 8) {                       // ~37 independent loads per thread: keep 8 in flight
         const unsigned int h = __ldcg(d32 + ((size_t)g * K + w) * (AUC_W / 2) + word);
         lo += h & 0xffffu;
         hi += h >> 16;

@@ -459,6 +459,35 @@ def encode_train_chain(x: np.ndarray, centers_list: Sequence[np.ndarray],
     return out
 
 
+def encode_train_chain_gram(x: np.ndarray, centers_list: Sequence[np.ndarray]):
+    """The identity behind csrc/encode_fused.cu, restated in fp64 (unit weights, one dim-group): the ids of
+    encode_train_chain WITHOUT ever forming a residual.  With r_0 = x and r_{l+1} = (r_l - C_l[id_l]) / s_l,
+    s_l = |r_l - C_l[id_l]| + 1e-8 (hierarchical_rq_kmeans.py:1111-1122), every score is a corrected dot product with
+    the original row:  r_m . C_m[k] = (..((x . C_m[k] - G_0m[id_0][k]) / s_0 - G_1m[id_1][k]) / s_1 ..) / s_{m-1},
+    G_lm = C_l C_m^T,  |r_{l+1}|^2 = (d_l / s_l)^2,  and d_l is the distance the level's argmin has just produced.
+    Returns (ids per level, relative top-2 gap of d^2 per level) - tests compare with the literal chain."""
+    x64 = np.asarray(x, np.float64)
+    cs = [np.asarray(c, np.float64) for c in centers_list]
+    n = len(x64)
+    rows = np.arange(n)
+    rn2 = (x64 * x64).sum(1)
+    ids, gaps, inv_s = [], [], []
+    for m, cm in enumerate(cs):
+        dot = x64 @ cm.T
+        for l in range(m):
+            dot = (dot - (cs[l] @ cm.T)[ids[l]]) * inv_s[l][:, None]
+        d2 = np.maximum(rn2[:, None] + (cm * cm).sum(1)[None, :] - 2.0 * dot, 0.0)
+        i = np.argmin(d2, axis=1)
+        part = np.partition(d2, 1, axis=1) if d2.shape[1] > 1 else np.concatenate([d2, d2 + 1], 1)
+        gaps.append((part[:, 1] - part[:, 0]) / np.maximum(part[:, 1], 1e-300))
+        d = np.sqrt(d2[rows, i])
+        s = d + 1e-8
+        ids.append(i.astype(np.int64))
+        inv_s.append(1.0 / s)
+        rn2 = (d / s) ** 2
+    return ids, gaps
+
+
 def predict_hierarchy(x: np.ndarray, centers_list: Sequence[np.ndarray], need_clusters: Sequence[int],
                       group_dims: Sequence[int], weights: Sequence[Sequence[float]],
                       match_matrices: Optional[list] = None) -> np.ndarray:

@@ -253,3 +253,26 @@ def test_last_layer_match_matrix_restatement_against_reference_run(golden_dir):
                                match_matrices=[g["match"].tolist()])
     assert np.array_equal(pred, g["predict_ids"])
     assert g["predict_ids"][:, 2].max() >= need[2]                            # raw candidate ids at predict time
+
+
+def test_residual_free_encode_identity():
+    """The algebra of the single-kernel encoder (csrc/encode_fused.cu), on the CPU: ids from corrected dot products
+    with the ORIGINAL rows and Gram tables of the centres equal the literal chain (predict + normalised residual per
+    level) - everywhere except rows whose top-2 gap is at rounding level (the chain works on fp32 residuals)."""
+    n, dim, cl = 6000, 96, [16, 24, 32, 8]
+    x = O.synth_mix(n, dim, seed=13, modes=80)
+    rng = np.random.default_rng(2)
+    cur, cs = x, []
+    for k in cl:
+        c = cur[rng.integers(0, n, (k, 3))].mean(axis=1).astype(np.float32)
+        cs.append(c)
+        cur = O.residual_normalised(cur, O.predict(cur, c), c, [dim])
+    chain = O.encode_train_chain(x, cs, [dim], [[1.0]] * len(cl))
+    ids, gaps = O.encode_train_chain_gram(x, cs)
+    alive = np.ones(n, bool)
+    for l in range(len(cl)):
+        diff = alive & (ids[l] != chain[l])
+        assert (gaps[l][diff] < 1e-5).all(), (l, int(diff.sum()))
+        assert diff.sum() <= 3
+        alive &= ~diff
+    assert alive.sum() >= n - 6
