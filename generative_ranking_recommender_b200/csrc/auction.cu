@@ -2172,33 +2172,71 @@ __device__ __forceinline__ void tie_prefix_worker(const AuctionPtrs& p, int K, i
     tie_scan_store(p, K, G, w, m, rank_off);
 }
 
+// One sweep over worker w's survivor lists (nseg segments of <= AUC_SEG_CAP entries) by all warps of the CTA.  A warp
+// takes 8 consecutive segments at a time: their lengths with one load, then chunk c of all eight in flight together -
+// the sweep is a chain of L2 round trips, so what counts is how few of them there are (at 10 M rows a worker has
+// 2664 segments).  MODE 0: fh[key - lo] += 1 for lo <= key < lo + range;  MODE 1: cnt_cta[seg / spc] += #(key == lo).
+// Returns (to lane 0 of each warp, OR it over the warps) whether a segment had overflowed.
+template <int MODE>
+__device__ __forceinline__ bool sweep_worker_lists(const AuctionPtrs& p, int K, int w, int nseg, int spc, int lo, int range,
+                                                   unsigned int* out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NWARP = blockDim.x >> 5;
+    bool over = false;
+    for (int s0 = warp * 8; s0 < nseg; s0 += NWARP * 8) {
+        unsigned int cnt_l = 0;
+        if (lane < 8 && s0 + lane < nseg) cnt_l = __ldcg(p.seg_cnt + (size_t)(s0 + lane) * K + w);
+        unsigned int cnt[8], mx = 0, nt[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            cnt[u] = __shfl_sync(0xffffffffu, cnt_l, u);
+            if (cnt[u] > AUC_SEG_CAP) { over = true; cnt[u] = 0; }
+            mx = cnt[u] > mx ? cnt[u] : mx;
+            nt[u] = 0;
+        }
+        for (unsigned int c = 0; c * 32 < mx; ++c) {
+            const unsigned int i = c * 32 + lane;
+            unsigned int e[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                e[u] = (i < cnt[u]) ? __ldcg(p.seg_list + ((size_t)(s0 + u) * K + w) * AUC_SEG_CAP + i) : 0xffffffffu;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (e[u] == 0xffffffffu) continue;               // (a job offset is < 4096: never a real entry)
+                const int key = (int)(e[u] & 0xffffu);
+                if (MODE == 0) { if (key >= lo && key < lo + range) atomicAdd(&out[key - lo], 1u); }
+                else nt[u] += (key == lo) ? 1u : 0u;
+            }
+        }
+        if (MODE == 1) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const unsigned int n = __reduce_add_sync(0xffffffffu, nt[u]);
+                if (lane == 0 && n) atomicAdd(&out[(s0 + u) / spc], n);
+            }
+        }
+    }
+    return over;
+}
+
 // Refine from the survivor lists.  The worker's window had coarse bins (2^shift0 keys each, from `base0`) and the
-// resolve step has just found the bin that holds the threshold and aimed a one-key window [nb2, nb2 + 2^shift0) at it
-// for another HIST pass over the worker's row.  But the pass that has just run already pushed EVERY value >= base0 of
-// this worker into its survivor lists (job, exact key), so the one-key histogram of that bin - and the per-CTA tie
-// counts at the threshold - can be taken from the lists (L2-resident, ~2 % of the row) right here, and the extra pass
-// over S never happens.  Returns false (nothing changed: the next HIST pass refines as before) if a list overflowed.
-// All threads of the CTA; m.part is reused as scratch.
+// resolve step has just found the bin that holds the threshold and aimed a one-key window [nb2, nb2 + range) at it
+// for another HIST pass over the worker's row (likewise for the gap of a split window).  But the pass that has just
+// run already pushed EVERY value >= base0 of this worker into its survivor lists (job, exact key), so the one-key
+// histogram of that range - and the per-CTA tie counts at the threshold - can be taken from the lists (L2-resident,
+// ~2 % of the row) right here, and the extra pass over S never happens.  Returns false (nothing changed: the next
+// HIST pass refines as before) if a list overflowed.  All threads of the CTA; m.part is reused as scratch.
 __device__ __forceinline__ bool refine_from_lists(const AuctionPtrs& p, int K, int G, int spc, int w, MergeSmem& m,
                                                   unsigned long long above_bin, int nb2, int range, long long jpw, int passes) {
     __shared__ int s_over, s_T;
     __shared__ unsigned int s_above_T;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     unsigned int* fh = &m.part[0][0];                          // [range <= 8 * 256] one-key histogram of [nb2, nb2 + range)
     const int nseg = G * spc;
     for (int i = tid; i < range; i += AUC_MAX_CTAS) fh[i] = 0;
     if (tid == 0) { s_over = 0; s_T = -1; }
     m.cnt[tid] = 0;
     __syncthreads();
-    for (int seg = warp; seg < nseg; seg += AUC_MAX_CTAS / 32) {
-        const unsigned int cnt = __ldcg(p.seg_cnt + (size_t)seg * K + w);
-        if (cnt > AUC_SEG_CAP) { if (lane == 0) s_over = 1; continue; }
-        const unsigned int* L = p.seg_list + ((size_t)seg * K + w) * AUC_SEG_CAP;
-        for (unsigned int i = lane; i < cnt; i += 32) {
-            const int key = (int)(__ldcg(L + i) & 0xffffu);
-            if (key >= nb2 && key < nb2 + range) atomicAdd(&fh[key - nb2], 1u);
-        }
-    }
+    if (sweep_worker_lists<0>(p, K, w, nseg, spc, nb2, range, fh) && lane == 0) s_over = 1;
     __syncthreads();
     if (s_over) return false;
     if (tid == 0) {
@@ -2212,14 +2250,7 @@ __device__ __forceinline__ bool refine_from_lists(const AuctionPtrs& p, int K, i
     __syncthreads();
     const int T = s_T;
     if (T < 0) return false;                                   // cannot happen with complete lists
-    for (int seg = warp; seg < nseg; seg += AUC_MAX_CTAS / 32) {
-        const unsigned int cnt = __ldcg(p.seg_cnt + (size_t)seg * K + w);
-        const unsigned int* L = p.seg_list + ((size_t)seg * K + w) * AUC_SEG_CAP;
-        unsigned int n = 0;
-        for (unsigned int i = lane; i < cnt; i += 32) n += ((int)(__ldcg(L + i) & 0xffffu) == T) ? 1u : 0u;
-        n = __reduce_add_sync(0xffffffffu, n);
-        if (lane == 0 && n) atomicAdd(&m.cnt[seg / spc], n);
-    }
+    sweep_worker_lists<1>(p, K, w, nseg, spc, T, 1, m.cnt);
     if (tid == 0) {
         const int tp = p.tprev[w];
         if (tp >= 0) {
