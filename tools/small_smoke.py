@@ -1,6 +1,6 @@
 """Quick look at the round-2 kernels on small inputs (seconds): single-kernel encoder vs level chain in both modes, and
 an auction on clustered unit-norm rows at K = 256 / 128, where the windows get coarse bins and the merge kernel refines
-from the survivor lists (HIST passes == rounds).  python tools/sanitize_small.py [encode|auction]"""
+from the survivor lists (HIST passes == rounds).  python tools/small_smoke.py [encode|auction]"""
 import os
 import sys
 
